@@ -1,0 +1,481 @@
+// acq.cu -- K6: the fused batched acquisition step (one launch over all M candidate columns).
+//
+// Replaces, per BO iteration, the reference's multi-restart search: acquire_max (src/acquisition.jl:54-68) ->
+// NLopt -> wrap_gradient (:11-17) -> acquisitionfunction(a, model)(x) (src/acquisitionfunctions.jl:4-9) ->
+// mean_var = EXT GP.predict_f (src/models/gp.jl:2-5,8) -> functor a(mu, s2) (acquisitionfunctions.jl:24-27,47-50,
+// 96,108,111,141).  Per candidate tile (64 columns, one persistent CTA):
+//   forward, block row i:  R = k(X_i, x*) - sum_{j<i} L_ij V_j ;  V_i = L_ii^-1 R        (DMMA GEMMs, K = 128 i)
+//                          mu += alpha_i' k(X_i, x*),  ssum += colsum(V_i^2)
+//   scores:                s2 = max(sf2 - ssum, 0),  a(mu, s2) and its partials, tile arg-max
+//   backward (gradient):   R = V_i - sum_{j>i} L_ji' W_j ;  W_i = L_ii^-T R  (same rows of the mirrored factor)
+//                          grad_d -= 1/l_d * sum_m (a_mu alpha_m - 2 a_s2 W_m) sf2 psi(r2_m) (z*_d - z_md)
+// k(X_i, x*) tiles are generated on the fly and never stored; V/W panels live in a per-CTA scratch that stays
+// in L2.  Every candidate's sums are taken in a fixed order that does not depend on its column position, so a
+// batched call equals the per-point call bit for bit (reference test/acquisitionfunctions.jl:10).
+#include "common.cuh"
+#include "handle.h"
+
+namespace b200bo {
+
+constexpr int AQ_BM = NB, AQ_BN = TILE_N, AQ_THREADS = 256, AQ_STAGES = 3;
+constexpr int RB_STRIDE = NB;   // resident R/G tile [TILE_N][NB], swizzled
+
+struct AcqArgs {
+  const double* L; int64_t ld; const double* Linv; const double* LinvT;
+  const double* Z; const double* alpha; const double* inv_ell; const double* Xs;
+  double* V;
+  int64_t M; int N; int nblk; int D; int ntiles;
+  double sf2, beta;
+  int acq; double p0, p1; unsigned long long seed; int64_t idx_offset;
+  double *values, *grad, *mu, *var;
+  b200bo_best_t* cta_best;
+};
+
+// ---- Philox4x32-10 keyed by (seed, global candidate index); identical to oracle/gp_oracle.py:philox_normal ----
+__device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned long long idx) {
+  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const unsigned long long a = ((unsigned long long)c0 << 32) | c1, b = ((unsigned long long)c2 << 32) | c3;
+  const double u1 = ((double)(a >> 11) + 1.0) * 1.1102230246251565e-16;
+  const double u2 = (double)(b >> 11) * 1.1102230246251565e-16;
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+}
+
+// ---- the functors AS CODED in the reference (quirks 1-3 of SURVEY 0.4) and their partials (App. A table) ----
+__device__ __forceinline__ void acq_eval(int kind, double p0, double p1, double mu, double s2, double eps, double& val, double& amu,
+                                         double& as2) {
+  const double INV_SQRT_2PI = 0.3989422804014327;
+  amu = 1.0; as2 = 0.0;
+  switch (kind) {
+    case B200BO_ACQ_PI:
+    case B200BO_ACQ_EI: {
+      const double d = mu - p0;
+      if (s2 == 0.0) {
+        const double gt = mu > p0 ? 1.0 : 0.0;
+        val = (kind == B200BO_ACQ_PI) ? gt : (mu > p0 ? d : 0.0);
+        amu = (kind == B200BO_ACQ_PI) ? 0.0 : gt;
+        return;
+      }
+      const double sig = sqrt(s2);
+      const double cdf = 0.5 * (1.0 + erf(d / sqrt(2.0 * s2)));                            // utils.jl:49
+      const double z = d / sig;
+      const double ph = INV_SQRT_2PI * exp(-0.5 * z * z);
+      if (kind == B200BO_ACQ_PI) {
+        val = cdf; amu = ph / sig; as2 = -z * ph / (2.0 * s2);
+      } else {
+        const double pdf = 1.0 / sqrt(6.283185307179586 * s2) * exp(-(d * d) / (2.0 * s2));  // utils.jl:48
+        val = d * cdf + sig * pdf;                                                           // acquisitionfunctions.jl:49
+        amu = cdf + z * ph * (1.0 - 1.0 / sig);
+        as2 = z * z * (1.0 - sig) * ph / (2.0 * s2);
+      }
+      return;
+    }
+    case B200BO_ACQ_UCB: {
+      const double sig = sqrt(s2);
+      val = mu + p0 * sig;
+      as2 = s2 == 0.0 ? 0.0 : p0 / (2.0 * sig);
+      return;
+    }
+    case B200BO_ACQ_MI: {
+      const double den = sqrt(s2 + p1);
+      val = mu + p0 * (den - sqrt(p1));
+      as2 = den == 0.0 ? 0.0 : p0 / (2.0 * den);
+      return;
+    }
+    case B200BO_ACQ_TS:
+      val = mu + sqrt(s2) * eps;
+      return;
+    default:
+      val = mu;
+      return;
+  }
+}
+
+__device__ __forceinline__ bool better(double v, int64_t i, double bv, int64_t bi) {
+  return (v > bv) || (v == bv && bi >= 0 && i < bi);
+}
+
+// MODE 0: acquisition step.  MODE 1: the right-hand sides are the columns of I (candidate n of tile t is e_{64 t + n}),
+// scores are skipped and the backward pass always runs, leaving Sigma^-1 in the panels (used by the MAP gradient).
+template <int FAM, int MODE>
+__global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int D = a.D;
+  double* stages = sm;                                              // AQ_STAGES x (128 + 64) x 16
+  double* Rb = stages + AQ_STAGES * (AQ_BM + AQ_BN) * KC;           // [64][128] swizzled
+  double* zx = Rb + TILE_N * RB_STRIDE;                             // [D][128]
+  double* zc = zx + D * NB;                                         // [D][64]
+  double* alb = zc + D * TILE_N;                                    // [128]
+  double* red = alb + NB;                                           // [2][4][64]
+  double* c_mu = red + 2 * 4 * TILE_N;                              // [64] each
+  double* c_s2 = c_mu + TILE_N;
+  double* c_amu = c_s2 + TILE_N;
+  double* c_as2 = c_amu + TILE_N;
+  double* c_val = c_as2 + TILE_N;
+  double* ie = c_val + TILE_N;                                      // [D] inverse length-scales
+  __shared__ double best_v;
+  __shared__ long long best_i;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;     // 4 x 2 warps, warp tile 32 x 32
+  const int g = lane >> 2, q = lane & 3;
+  const bool want_grad = MODE == 1 || a.grad != nullptr;
+
+  if (tid == 0) { best_v = -INFINITY; best_i = -1; }
+  for (int d = tid; d < D; d += AQ_THREADS) ie[d] = a.inv_ell[d];
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    __syncthreads();
+    const int64_t c0 = (int64_t)tile * TILE_N;
+    // solve panel [64][ld]: one per resident CTA (MODE 0) or one per tile so the result survives (MODE 1)
+    double* Vs = a.V + (int64_t)(MODE == 1 ? tile : (int)blockIdx.x) * TILE_N * a.ld;
+    const int ib0 = MODE == 1 ? (int)(c0 / NB) : 0;                 // rows above the identity column are zero
+    if (MODE == 0)
+    for (int e = tid; e < TILE_N * D; e += AQ_THREADS) {
+      const int n = e / D, d = e - n * D;
+      int64_t gi = c0 + n;
+      if (gi >= a.M) gi = a.M - 1;                                  // ragged tail: replicate a valid column
+      zc[d * TILE_N + n] = a.Xs[gi * D + d] * ie[d];
+    }
+    double mu_p[4][2], ss_p[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mu_p[nt][0] = mu_p[nt][1] = ss_p[nt][0] = ss_p[nt][1] = 0.0;
+
+    // ======================================= forward solve =======================================
+    for (int ib = 0; ib < a.nblk; ++ib) {
+      __syncthreads();
+      if (MODE == 1 && ib < ib0) {
+        for (int e = tid; e < TILE_N * NB; e += AQ_THREADS) Vs[(int64_t)(e >> 7) * a.ld + ib * NB + (e & 127)] = 0.0;
+        continue;
+      }
+      if (MODE == 0) {
+        for (int e = tid; e < NB * D; e += AQ_THREADS) {
+          const int m = e / D, d = e - m * D;
+          zx[d * NB + m] = a.Z[((int64_t)ib * NB + m) * D + d];
+        }
+        if (tid < NB) alb[tid] = a.alpha[ib * NB + tid];
+      }
+      __syncthreads();
+      double acc[4][4][2];
+      if (MODE == 1) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
+              acc[mt][nt][e] = ((int64_t)ib * NB + m == c0 + n) ? -1.0 : 0.0;
+            }
+      } else {
+        double r2[4][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) r2[mt][nt][0] = r2[mt][nt][1] = 0.0;
+        for (int d = 0; d < D; ++d) {
+          double xm[4];
+          double2 xn[4];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) xm[mt] = zx[d * NB + wm * 32 + mt * 8 + g];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) xn[nt] = *reinterpret_cast<const double2*>(zc + d * TILE_N + wn * 32 + nt * 8 + 2 * q);
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const double d0 = xm[mt] - xn[nt].x, d1 = xm[mt] - xn[nt].y;
+              r2[mt][nt][0] = fma(d0, d0, r2[mt][nt][0]);
+              r2[mt][nt][1] = fma(d1, d1, r2[mt][nt][1]);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const int m = wm * 32 + mt * 8 + g;
+          const bool live = ib * NB + m < a.N;
+          const double al = alb[m];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const double ks = live ? a.sf2 * kern_phi<FAM>(r2[mt][nt][e]) : 0.0;
+              mu_p[nt][e] = fma(al, ks, mu_p[nt][e]);
+              acc[mt][nt][e] = -ks;
+            }
+        }
+      }
+      gemm_mainloop<AQ_BM, AQ_BN, 4, 4, AQ_STAGES, AQ_THREADS, false>(acc, a.L + (int64_t)ib * NB * a.ld + (int64_t)ib0 * NB, a.ld,
+                                                                     Vs + (int64_t)ib0 * NB, a.ld, (ib - ib0) * (NB / KC), stages, nullptr, 0,
+                                                                     wm, wn, lane, tid, 0, (ib - ib0) * (NB / KC));
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
+            Rb[tile_off(n, m, RB_STRIDE)] = -acc[mt][nt][e];
+            acc[mt][nt][e] = 0.0;
+          }
+      __syncthreads();
+      gemm_mainloop<AQ_BM, AQ_BN, 4, 4, AQ_STAGES, AQ_THREADS, true>(acc, a.Linv + (int64_t)ib * NB * NB, NB, nullptr, 0, NB / KC, stages, Rb,
+                                                                    RB_STRIDE, wm, wn, lane, tid, 0, 2 * wm + 2);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
+            const double v = acc[mt][nt][e];
+            Vs[(int64_t)n * a.ld + ib * NB + m] = v;
+            ss_p[nt][e] = fma(v, v, ss_p[nt][e]);
+          }
+    }
+    // ---- per-candidate reductions: over g (shuffles), then over the 4 warp rows (fixed order) ----
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double m_ = mu_p[nt][e], s_ = ss_p[nt][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          m_ += __shfl_xor_sync(0xffffffffu, m_, o);
+          s_ += __shfl_xor_sync(0xffffffffu, s_, o);
+        }
+        if (g == 0) {
+          const int n = wn * 32 + nt * 8 + 2 * q + e;
+          red[(0 * 4 + wm) * TILE_N + n] = m_;
+          red[(1 * 4 + wm) * TILE_N + n] = s_;
+        }
+      }
+    __syncthreads();
+    if (MODE == 0 && tid < TILE_N) {
+      const int n = tid;
+      const int64_t gi = c0 + n;
+      const double mu = a.beta + (((red[0 * TILE_N + n] + red[1 * TILE_N + n]) + red[2 * TILE_N + n]) + red[3 * TILE_N + n]);
+      const double ss = ((red[4 * TILE_N + n] + red[5 * TILE_N + n]) + red[6 * TILE_N + n]) + red[7 * TILE_N + n];
+      const double s2 = fmax(a.sf2 - ss, 0.0);
+      double val = mu, amu = 1.0, as2 = 0.0;
+      if (a.acq >= 0) {
+        const double eps = a.acq == B200BO_ACQ_TS ? philox_normal(a.seed, (unsigned long long)(a.idx_offset + gi)) : 0.0;
+        acq_eval(a.acq, a.p0, a.p1, mu, s2, eps, val, amu, as2);
+      }
+      c_mu[n] = mu; c_s2[n] = s2; c_amu[n] = amu; c_as2[n] = as2; c_val[n] = val;
+      if (gi < a.M) {
+        if (a.mu) a.mu[gi] = mu;
+        if (a.var) a.var[gi] = s2;
+        if (a.values) a.values[gi] = val;
+      }
+    }
+    __syncthreads();
+    if (MODE == 0 && tid == 0 && a.acq >= 0) {   // tile arg-max in index order: first strict maximum, NaN never wins
+      double bv = best_v; long long bi = best_i;
+      for (int n = 0; n < TILE_N; ++n) {
+        const int64_t gi = c0 + n;
+        if (gi < a.M && better(c_val[n], a.idx_offset + gi, bv, bi)) { bv = c_val[n]; bi = a.idx_offset + gi; }
+      }
+      best_v = bv; best_i = bi;
+    }
+
+    // ======================================= backward solve + gradient =======================================
+    if (want_grad) {
+      const int gn = tid & (TILE_N - 1), gd = tid >> 6;     // gradient accumulators: candidate gn, dims gd, gd+4, ...
+      double gacc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gacc[k] = 0.0;
+      for (int ib = a.nblk - 1; ib >= 0; --ib) {
+        __syncthreads();
+        if (MODE == 0) {
+          for (int e = tid; e < NB * D; e += AQ_THREADS) {
+            const int m = e / D, d = e - m * D;
+            zx[d * NB + m] = a.Z[((int64_t)ib * NB + m) * D + d];
+          }
+          if (tid < NB) alb[tid] = a.alpha[ib * NB + tid];
+        }
+        double acc[4][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
+              acc[mt][nt][e] = -__ldcg(Vs + (int64_t)n * a.ld + ib * NB + m);
+            }
+        const int nch = (a.nblk - 1 - ib) * (NB / KC);
+        gemm_mainloop<AQ_BM, AQ_BN, 4, 4, AQ_STAGES, AQ_THREADS, false>(acc, a.L + (int64_t)ib * NB * a.ld + (int64_t)(ib + 1) * NB, a.ld,
+                                                                       Vs + (int64_t)(ib + 1) * NB, a.ld, nch, stages, nullptr, 0, wm, wn, lane,
+                                                                       tid, 0, nch);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
+              Rb[tile_off(n, m, RB_STRIDE)] = -acc[mt][nt][e];
+              acc[mt][nt][e] = 0.0;
+            }
+        __syncthreads();
+        gemm_mainloop<AQ_BM, AQ_BN, 4, 4, AQ_STAGES, AQ_THREADS, true>(acc, a.LinvT + (int64_t)ib * NB * NB, NB, nullptr, 0, NB / KC, stages, Rb,
+                                                                      RB_STRIDE, wm, wn, lane, tid, 2 * wm, NB / KC);
+        // W_i -> panel (overwrites V_i), and G = (a_mu alpha - 2 a_s2 W) * sf2 psi(r2) -> Rb
+        if (MODE == 1) {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
+                Vs[(int64_t)n * a.ld + ib * NB + m] = acc[mt][nt][e];
+              }
+          continue;
+        }
+        {
+          double r2[4][4][2];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) r2[mt][nt][0] = r2[mt][nt][1] = 0.0;
+          for (int d = 0; d < D; ++d) {
+            double xm[4];
+            double2 xn[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) xm[mt] = zx[d * NB + wm * 32 + mt * 8 + g];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) xn[nt] = *reinterpret_cast<const double2*>(zc + d * TILE_N + wn * 32 + nt * 8 + 2 * q);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) {
+                const double d0 = xm[mt] - xn[nt].x, d1 = xm[mt] - xn[nt].y;
+                r2[mt][nt][0] = fma(d0, d0, r2[mt][nt][0]);
+                r2[mt][nt][1] = fma(d1, d1, r2[mt][nt][1]);
+              }
+          }
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            const int m = wm * 32 + mt * 8 + g;
+            const bool live = ib * NB + m < a.N;
+            const double al = alb[m];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int n = wn * 32 + nt * 8 + 2 * q + e;
+                const double w = acc[mt][nt][e];
+                Vs[(int64_t)n * a.ld + ib * NB + m] = w;
+                double phi, psi;
+                kern_phi_psi<FAM>(r2[mt][nt][e], phi, psi);
+                const double c = fma(c_amu[n], al, -2.0 * c_as2[n] * w);
+                Rb[tile_off(n, m, RB_STRIDE)] = live ? c * a.sf2 * psi : 0.0;
+              }
+          }
+        }
+        __syncthreads();
+        for (int m = 0; m < NB; ++m) {
+          const double gv = Rb[tile_off(gn, m, RB_STRIDE)];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int d = gd + 4 * k;
+            if (d < D) gacc[k] = fma(gv, zc[d * TILE_N + gn] - zx[d * NB + m], gacc[k]);
+          }
+        }
+      }
+      const int64_t gi = c0 + gn;
+      if (MODE == 0 && gi < a.M) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int d = gd + 4 * k;
+          if (d < D) a.grad[gi * D + d] = -gacc[k] * ie[d];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { a.cta_best[blockIdx.x].value = best_v; a.cta_best[blockIdx.x].index = best_i; }
+}
+
+// K8 (single-GPU part): reduce the per-CTA bests in index order (value, then lowest index).
+__global__ void argmax_reduce_kernel(const b200bo_best_t* __restrict__ cta_best, int n, b200bo_best_t* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double bv = -INFINITY; long long bi = -1;
+    for (int i = 0; i < n; ++i) {
+      const double v = cta_best[i].value; const long long ix = cta_best[i].index;
+      if (ix >= 0 && better(v, ix, bv, bi)) { bv = v; bi = ix; }
+    }
+    out->value = bv; out->index = bi;
+  }
+}
+
+size_t acq_smem_bytes(int D) {
+  const size_t dbl = (size_t)AQ_STAGES * (AQ_BM + AQ_BN) * KC + (size_t)TILE_N * RB_STRIDE + (size_t)D * NB + (size_t)D * TILE_N + NB +
+                     2 * 4 * TILE_N + 5 * TILE_N + D;
+  return dbl * sizeof(double);
+}
+
+cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& l) {
+  AcqArgs a;
+  a.L = h->dL; a.ld = h->ld; a.Linv = h->dLinv; a.LinvT = h->dLinvT;
+  a.Z = h->dZ; a.alpha = h->dalpha; a.inv_ell = h->dinv_ell; a.Xs = l.dXs; a.V = h->dV;
+  a.M = l.M; a.N = (int)h->N; a.nblk = (int)(h->Np / NB); a.D = h->D;
+  a.ntiles = (int)((l.M + TILE_N - 1) / TILE_N);
+  a.sf2 = exp(2.0 * h->hp.lsigma);
+  a.beta = h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0;
+  a.acq = l.acq_kind; a.p0 = l.p0; a.p1 = l.p1; a.seed = l.seed; a.idx_offset = l.idx_offset;
+  a.values = l.dvalues; a.grad = l.dgrad; a.mu = l.dmu; a.var = l.dvar;
+  a.cta_best = h->dcta_best;
+  if (a.ntiles == 0) return cudaSuccess;
+  const int grid = (int)(a.ntiles < h->nslots ? a.ntiles : h->nslots);
+  const size_t smem = acq_smem_bytes(h->D);
+#define B200BO_ACQ(F)                                                                                   \
+  do {                                                                                                  \
+    cudaFuncSetAttribute(acq_fused_kernel<F, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    acq_fused_kernel<F, 0><<<grid, AQ_THREADS, smem, h->stream>>>(a);                                   \
+  } while (0)
+  switch (h->fam) {
+    case FAM_SE: B200BO_ACQ(FAM_SE); break;
+    case FAM_MAT12: B200BO_ACQ(FAM_MAT12); break;
+    case FAM_MAT32: B200BO_ACQ(FAM_MAT32); break;
+    default: B200BO_ACQ(FAM_MAT52); break;
+  }
+#undef B200BO_ACQ
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (l.dbest && l.acq_kind >= 0) {
+    argmax_reduce_kernel<<<1, 32, 0, h->stream>>>(h->dcta_best, grid, l.dbest);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+// Sigma^-1 = L^-T L^-1 by the same fused forward/backward sweep applied to the columns of I.  Result: h->dV viewed
+// as [Np][ld] (row j = column j of the symmetric inverse).
+cudaError_t launch_kinv(b200bo_handle_s* h) {
+  AcqArgs a = {};
+  a.L = h->dL; a.ld = h->ld; a.Linv = h->dLinv; a.LinvT = h->dLinvT;
+  a.V = h->dV; a.M = h->Np; a.N = (int)h->N; a.nblk = (int)(h->Np / NB); a.D = 0;
+  a.ntiles = (int)(h->Np / TILE_N);
+  a.acq = -1; a.cta_best = h->dcta_best;
+  if (a.ntiles == 0) return cudaSuccess;
+  if (a.ntiles > h->nslots) return cudaErrorInvalidValue;
+  const size_t smem = acq_smem_bytes(0);
+  cudaFuncSetAttribute(acq_fused_kernel<FAM_SE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  acq_fused_kernel<FAM_SE, 1><<<a.ntiles, AQ_THREADS, smem, h->stream>>>(a);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace b200bo

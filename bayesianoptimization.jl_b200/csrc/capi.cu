@@ -1,0 +1,528 @@
+// capi.cu -- the C ABI of libb200bo.so (include/b200bo.h).  Host orchestration only; all arithmetic is in the
+// CUDA kernels (kmat.cu, chol.cu, solve.cu, acq.cu, mll.cu).  No CPU fallback: without a device every compute
+// entry fails with B200BO_ERR_CUDA.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <limits>
+#include <new>
+#include "common.cuh"
+#include "handle.h"
+
+using namespace b200bo;
+
+namespace {
+
+thread_local std::string g_err;   // for errors raised without a handle
+
+int32_t fail(b200bo_handle_t h, int32_t code, const std::string& msg) {
+  if (h) h->err = msg; else g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(h, B200BO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+int fam_of(int kind) { return kind >> 1; }          // SE, Mat12, Mat32, Mat52
+bool iso_of(int kind) { return (kind & 1) == 0; }
+
+int num_params(const b200bo_handle_s* h) {
+  return 1 + (h->mean_kind == B200BO_MEAN_CONST ? 1 : 0) + (int)h->hp.ll.size() + 1;
+}
+
+void free_device(b200bo_handle_s* h) {
+  cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dinv_ell);
+  cudaFree(h->dL); cudaFree(h->dLinv); cudaFree(h->dLinvT); cudaFree(h->dV); cudaFree(h->dscal); cudaFree(h->dinfo);
+  cudaFree(h->dcta_best); cudaFree(h->dbest); cudaFree(h->dpart);
+  h->dX = h->dZ = h->dy = h->dw = h->dalpha = h->dinv_ell = h->dL = h->dLinv = h->dLinvT = h->dV = h->dscal = h->dpart = nullptr;
+  h->dinfo = nullptr; h->dcta_best = nullptr; h->dbest = nullptr;
+}
+
+int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
+  cap = std::max<int64_t>(NB, (cap + NB - 1) / NB * NB);
+  free_device(h);
+  h->cap = cap; h->ld = cap;
+  h->nslots = std::max<int64_t>(h->num_sms, cap / TILE_N);
+  const int64_t nb = cap / NB;
+  const int64_t T = cap / 64;
+  CU(cudaMalloc(&h->dX, sizeof(double) * cap * h->D));
+  CU(cudaMalloc(&h->dZ, sizeof(double) * cap * h->D));
+  CU(cudaMalloc(&h->dy, sizeof(double) * cap));
+  CU(cudaMalloc(&h->dw, sizeof(double) * cap));
+  CU(cudaMalloc(&h->dalpha, sizeof(double) * cap));
+  CU(cudaMalloc(&h->dinv_ell, sizeof(double) * h->D));
+  CU(cudaMalloc(&h->dL, sizeof(double) * cap * cap));
+  CU(cudaMalloc(&h->dLinv, sizeof(double) * nb * NB * NB));
+  CU(cudaMalloc(&h->dLinvT, sizeof(double) * nb * NB * NB));
+  CU(cudaMalloc(&h->dV, sizeof(double) * h->nslots * TILE_N * cap));
+  CU(cudaMalloc(&h->dscal, sizeof(double) * 64));
+  CU(cudaMalloc(&h->dinfo, sizeof(int)));
+  CU(cudaMalloc(&h->dcta_best, sizeof(b200bo_best_t) * h->nslots));
+  CU(cudaMalloc(&h->dbest, sizeof(b200bo_best_t)));
+  CU(cudaMalloc(&h->dpart, sizeof(double) * T * T * 35));
+  CU(cudaMemsetAsync(h->dX, 0, sizeof(double) * cap * h->D, h->stream));
+  CU(cudaMemsetAsync(h->dZ, 0, sizeof(double) * cap * h->D, h->stream));
+  CU(cudaMemsetAsync(h->dalpha, 0, sizeof(double) * cap, h->stream));
+  CU(cudaMemsetAsync(h->dy, 0, sizeof(double) * cap, h->stream));
+  return B200BO_OK;
+}
+
+int32_t ensure_io(b200bo_handle_s* h, int64_t bytes) {
+  if (bytes <= h->dio_bytes) return B200BO_OK;
+  if (h->dio) cudaFree(h->dio);
+  h->dio = nullptr; h->dio_bytes = 0;
+  CU(cudaMalloc(&h->dio, (size_t)bytes));
+  h->dio_bytes = bytes;
+  return B200BO_OK;
+}
+
+void upload_inv_ell(b200bo_handle_s* h, std::vector<double>& ie) {
+  ie.resize(h->D);
+  for (int d = 0; d < h->D; ++d) ie[d] = exp(-(h->iso ? h->hp.ll[0] : h->hp.ll[d]));
+}
+
+// Sigma assembly + Cholesky (with the make_posdef! jitter rule) + alpha + mll on the current data and params.
+int32_t refit(b200bo_handle_s* h) {
+  h->jitter = 0;
+  if (h->N == 0) { h->fitted = true; h->mll = 0.0; h->Np = 0; return B200BO_OK; }
+  std::vector<double> ie;
+  upload_inv_ell(h, ie);
+  CU(cudaMemcpyAsync(h->dinv_ell, ie.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
+  CU(launch_scale_inputs(h, 0, h->Np));
+  const double sf2 = exp(2.0 * h->hp.lsigma);
+  double noise = exp(2.0 * h->hp.lognoise) + std::numeric_limits<double>::epsilon();   // quirk 10
+  for (;;) {
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    CU(launch_kmat(h, h->dL, h->ld, h->N, h->Np, noise, true));
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    CU(launch_cholesky(h));
+    CU(cudaEventRecord(h->ev[2], h->stream));
+    int info = 0;
+    CU(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (info == 0) break;
+    if (h->jitter >= 10) return fail(h, B200BO_ERR_NOTPD, "covariance not positive definite after 10 jitter retries");
+    noise += 1e-6 * (sf2 + noise);      // 1e-6 * tr(Sigma)/n with diag(Sigma) = sf2 + noise (EXT make_posdef!)
+    h->jitter++;
+  }
+  CU(launch_alpha_mll(h));
+  CU(cudaEventRecord(h->ev[3], h->stream));
+  double sc[2];
+  CU(cudaMemcpyAsync(sc, h->dscal, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->mll = -0.5 * (sc[1] + sc[0] + (double)h->N * 1.8378770664093453);
+  cudaEventElapsedTime(&h->timing[B200BO_T_KMAT], h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&h->timing[B200BO_T_CHOL], h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&h->timing[B200BO_T_ALPHA], h->ev[2], h->ev[3]);
+  h->fitted = true;
+  return B200BO_OK;
+}
+
+int32_t ensure_fitted(b200bo_handle_s* h) { return h->fitted ? B200BO_OK : refit(h); }
+
+int32_t upload_data(b200bo_handle_s* h) {
+  const int64_t N = h->N;
+  if (N > h->cap) {
+    int32_t rc = alloc_device(h, std::max<int64_t>(N, 2 * h->cap));
+    if (rc) return rc;
+  }
+  h->Np = (N + NB - 1) / NB * NB;
+  if (N > 0) {
+    CU(cudaMemcpyAsync(h->dX, h->hX.data(), sizeof(double) * N * h->D, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dy, h->hy.data(), sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+    if (h->Np > N) {
+      CU(cudaMemsetAsync(h->dX + N * h->D, 0, sizeof(double) * (h->Np - N) * h->D, h->stream));
+      CU(cudaMemsetAsync(h->dy + N, 0, sizeof(double) * (h->Np - N), h->stream));
+    }
+  }
+  h->fitted = false;
+  return B200BO_OK;
+}
+
+int32_t check_acq(b200bo_handle_t h, int32_t kind, int32_t n_params, bool grad) {
+  static const int need[6] = {1, 1, 1, 0, 2, 0};
+  if (kind < 0 || kind > B200BO_ACQ_MAXMEAN) return fail(h, B200BO_ERR_ARG, "unknown acquisition kind");
+  if (n_params < need[kind]) return fail(h, B200BO_ERR_ARG, "too few acquisition parameters");
+  if (grad && kind == B200BO_ACQ_TS)
+    return fail(h, B200BO_ERR_ARG, "ThompsonSamplingSimple is derivative-free (reference src/acquisition.jl:7-9)");
+  return B200BO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+B200BO_API int32_t b200bo_version(void) { return 100; }
+
+B200BO_API const char* b200bo_last_error(b200bo_handle_t h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+B200BO_API int32_t b200bo_create(b200bo_handle_t* out, int32_t device, int32_t D, int64_t capacity, int32_t kernel_kind, int32_t mean_kind) {
+  b200bo_handle_t h = nullptr;
+  if (!out) return fail(h, B200BO_ERR_ARG, "null handle pointer");
+  *out = nullptr;
+  if (D < 1 || D > 32) return fail(h, B200BO_ERR_ARG, "input dimension D must be in 1..32");
+  if (kernel_kind < 0 || kernel_kind > B200BO_KERNEL_MAT52ARD) return fail(h, B200BO_ERR_ARG, "unknown kernel kind");
+  if (mean_kind != B200BO_MEAN_ZERO && mean_kind != B200BO_MEAN_CONST) return fail(h, B200BO_ERR_ARG, "unknown mean kind");
+  if (capacity < 0) return fail(h, B200BO_ERR_ARG, "negative capacity");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, B200BO_ERR_CUDA, "no CUDA device: libb200bo has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(h, B200BO_ERR_ARG, "device index out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(h, B200BO_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(h, B200BO_ERR_CUDA, "libb200bo is built for sm_100a (B200) only");
+  h = new (std::nothrow) b200bo_handle_s();
+  if (!h) return fail(nullptr, B200BO_ERR_ALLOC, "out of host memory");
+  h->device = device; h->D = D; h->kernel_kind = kernel_kind; h->mean_kind = mean_kind;
+  h->fam = fam_of(kernel_kind); h->iso = iso_of(kernel_kind);
+  h->num_sms = prop.multiProcessorCount;
+  h->hp.ll.assign(h->iso ? 1 : D, 0.0);
+  cudaSetDevice(device);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, B200BO_ERR_CUDA, "stream create failed"); }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  int32_t rc = alloc_device(h, capacity);
+  if (rc != B200BO_OK) { g_err = h->err; free_device(h); cudaStreamDestroy(h->stream); delete h; return rc; }
+  h->fitted = true;   // empty model: prior
+  *out = h;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
+  if (!h) return B200BO_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_device(h);
+  if (h->dio) cudaFree(h->dio);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_set_stream(b200bo_handle_t h, void* s) {
+  if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (s) { h->stream = (cudaStream_t)s; h->own_stream = false; }
+  else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_sync(b200bo_handle_t h) {
+  if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
+  CU(cudaStreamSynchronize(h->stream));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_num_params(b200bo_handle_t h, int32_t* P) {
+  if (!h || !P) return fail(h, B200BO_ERR_ARG, "null argument");
+  *P = num_params(h);
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_set_params(b200bo_handle_t h, const double* th, int32_t P) {
+  if (!h || !th) return fail(h, B200BO_ERR_ARG, "null argument");
+  if (P != num_params(h)) return fail(h, B200BO_ERR_ARG, "parameter vector has the wrong length");
+  for (int i = 0; i < P; ++i) if (!isfinite(th[i])) return fail(h, B200BO_ERR_ARG, "non-finite hyper-parameter");
+  int i = 0;
+  h->hp.lognoise = th[i++];
+  if (h->mean_kind == B200BO_MEAN_CONST) h->hp.beta = th[i++];
+  for (auto& l : h->hp.ll) l = th[i++];
+  h->hp.lsigma = th[i++];
+  h->fitted = (h->N == 0);
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_get_params(b200bo_handle_t h, double* th, int32_t P) {
+  if (!h || !th) return fail(h, B200BO_ERR_ARG, "null argument");
+  if (P != num_params(h)) return fail(h, B200BO_ERR_ARG, "parameter vector has the wrong length");
+  int i = 0;
+  th[i++] = h->hp.lognoise;
+  if (h->mean_kind == B200BO_MEAN_CONST) th[i++] = h->hp.beta;
+  for (auto l : h->hp.ll) th[i++] = l;
+  th[i++] = h->hp.lsigma;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_fit(b200bo_handle_t h, const double* X, const double* y, int64_t N) {
+  if (!h || N < 0 || (N > 0 && (!X || !y))) return fail(h, B200BO_ERR_ARG, "bad arguments to fit");
+  cudaSetDevice(h->device);
+  h->hX.assign(X, X + N * h->D);
+  h->hy.assign(y, y + N);
+  h->N = N;
+  int32_t rc = upload_data(h);
+  if (rc) return rc;
+  return refit(h);
+}
+
+B200BO_API int32_t b200bo_append(b200bo_handle_t h, const double* Xn, const double* yn, int64_t m) {
+  if (!h || m < 0 || (m > 0 && (!Xn || !yn))) return fail(h, B200BO_ERR_ARG, "bad arguments to append");
+  cudaSetDevice(h->device);
+  h->hX.insert(h->hX.end(), Xn, Xn + m * h->D);
+  h->hy.insert(h->hy.end(), yn, yn + m);
+  h->N += m;
+  int32_t rc = upload_data(h);
+  if (rc) return rc;
+  return refit(h);
+}
+
+B200BO_API int32_t b200bo_refit(b200bo_handle_t h) {
+  if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
+  cudaSetDevice(h->device);
+  return refit(h);
+}
+
+B200BO_API int32_t b200bo_dims(b200bo_handle_t h, int32_t* D, int64_t* N) {
+  if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
+  if (D) *D = h->D;
+  if (N) *N = h->N;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_maxy(b200bo_handle_t h, double* m) {
+  if (!h || !m) return fail(h, B200BO_ERR_ARG, "null argument");
+  double v = -INFINITY;
+  for (double y : h->hy) v = y > v ? y : v;
+  *m = v;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_get_data(b200bo_handle_t h, double* X, double* y) {
+  if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
+  if (X && !h->hX.empty()) memcpy(X, h->hX.data(), sizeof(double) * h->hX.size());
+  if (y && !h->hy.empty()) memcpy(y, h->hy.data(), sizeof(double) * h->hy.size());
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_get_mll(b200bo_handle_t h, double* mll) {
+  if (!h || !mll) return fail(h, B200BO_ERR_ARG, "null argument");
+  cudaSetDevice(h->device);
+  int32_t rc = ensure_fitted(h);
+  if (rc) return rc;
+  *mll = h->mll;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_get_alpha(b200bo_handle_t h, double* alpha) {
+  if (!h || !alpha) return fail(h, B200BO_ERR_ARG, "null argument");
+  cudaSetDevice(h->device);
+  int32_t rc = ensure_fitted(h);
+  if (rc) return rc;
+  if (h->N) CU(cudaMemcpyAsync(alpha, h->dalpha, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_get_factor(b200bo_handle_t h, double* U) {
+  if (!h || !U) return fail(h, B200BO_ERR_ARG, "null argument");
+  cudaSetDevice(h->device);
+  int32_t rc = ensure_fitted(h);
+  if (rc) return rc;
+  const int64_t N = h->N;
+  if (N == 0) return B200BO_OK;
+  // row-major L (lower) == column-major U (upper); zero the mirrored other half on the host
+  CU(cudaMemcpy2DAsync(U, sizeof(double) * N, h->dL, sizeof(double) * h->ld, sizeof(double) * N, N, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int64_t r = 0; r < N; ++r)           // memory row r = column r of U: entries below the diagonal are zero
+    for (int64_t c = r + 1; c < N; ++c) U[r * N + c] = 0.0;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_jitter_tries(b200bo_handle_t h, int32_t* t) {
+  if (!h || !t) return fail(h, B200BO_ERR_ARG, "null argument");
+  *t = h->jitter;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_kmat_dev(b200bo_handle_t h, double* dK, int64_t ld) {
+  if (!h || !dK) return fail(h, B200BO_ERR_ARG, "null argument");
+  if (ld < h->N || (ld & 1) || ((uintptr_t)dK & 15)) return fail(h, B200BO_ERR_ARG, "dK must be 16-byte aligned with even ld >= N");
+  cudaSetDevice(h->device);
+  std::vector<double> ie;
+  upload_inv_ell(h, ie);
+  CU(cudaMemcpyAsync(h->dinv_ell, ie.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));   // ie is a host temporary
+  CU(launch_scale_inputs(h, 0, h->Np));
+  const double noise = exp(2.0 * h->hp.lognoise) + std::numeric_limits<double>::epsilon();
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  CU(launch_kmat(h, dK, ld, h->N, h->Np, noise, false));
+  CU(cudaEventRecord(h->ev[1], h->stream));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_kmat(b200bo_handle_t h, double* K) {
+  if (!h || !K) return fail(h, B200BO_ERR_ARG, "null argument");
+  const int64_t N = h->N;
+  if (N == 0) return B200BO_OK;
+  cudaSetDevice(h->device);
+  const int64_t ldk = (N + 1) & ~(int64_t)1;
+  int32_t rc = ensure_io(h, sizeof(double) * ldk * N);
+  if (rc) return rc;
+  rc = b200bo_kmat_dev(h, h->dio, ldk);
+  if (rc) return rc;
+  CU(cudaMemcpy2DAsync(K, sizeof(double) * N, h->dio, sizeof(double) * ldk, sizeof(double) * N, N, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->timing[B200BO_T_KMAT], h->ev[0], h->ev[1]);
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_acquire_dev(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* dXs, int64_t M, uint64_t seed,
+                           int64_t idx_offset, double* dvalues, double* dgrad, double* dmu, double* dvar, b200bo_best_t* dbest) {
+  if (!h || M < 0 || (M > 0 && !dXs)) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire");
+  int32_t rc = check_acq(h, kind, np, dgrad != nullptr);
+  if (rc) return rc;
+  if (np > 0 && !p) return fail(h, B200BO_ERR_ARG, "null acquisition parameters");
+  cudaSetDevice(h->device);
+  rc = ensure_fitted(h);
+  if (rc) return rc;
+  AcqLaunch l;
+  l.acq_kind = kind; l.p0 = np > 0 ? p[0] : 0.0; l.p1 = np > 1 ? p[1] : 0.0; l.seed = seed; l.idx_offset = idx_offset;
+  l.dXs = dXs; l.M = M; l.dvalues = dvalues; l.dgrad = dgrad; l.dmu = dmu; l.dvar = dvar; l.dbest = dbest;
+  CU(cudaEventRecord(h->ev[4], h->stream));
+  if (M == 0 && dbest) {
+    const b200bo_best_t none = {-INFINITY, -1};
+    CU(cudaMemcpyAsync(dbest, &none, sizeof(none), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  CU(launch_acquire(h, l));
+  CU(cudaEventRecord(h->ev[5], h->stream));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_predict_dev(b200bo_handle_t h, const double* dXs, int64_t M, double* dmu, double* dvar) {
+  if (!h || M < 0 || (M > 0 && !dXs)) return fail(h, B200BO_ERR_ARG, "bad arguments to predict");
+  cudaSetDevice(h->device);
+  int32_t rc = ensure_fitted(h);
+  if (rc) return rc;
+  AcqLaunch l;
+  l.acq_kind = -1; l.dXs = dXs; l.M = M; l.dmu = dmu; l.dvar = dvar;
+  CU(cudaEventRecord(h->ev[4], h->stream));
+  CU(launch_acquire(h, l));
+  CU(cudaEventRecord(h->ev[5], h->stream));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* Xs, int64_t M, uint64_t seed,
+                       int64_t idx_offset, double* values, double* grad, double* mu, double* var, b200bo_best_t* best, double* best_x) {
+  if (!h || M < 0 || (M > 0 && !Xs)) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire");
+  int32_t rc = check_acq(h, kind, np, grad != nullptr);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  const int64_t D = h->D;
+  // staging layout: Xs [M*D] | values [M] | mu [M] | var [M] | grad [M*D] | best
+  const int64_t nd = M * D + 3 * M + (grad ? M * D : 0) + 2;
+  rc = ensure_io(h, sizeof(double) * nd);
+  if (rc) return rc;
+  double* dXs = h->dio;
+  double* dval = dXs + M * D;
+  double* dmu = dval + M;
+  double* dvar = dmu + M;
+  double* dgrad = grad ? dvar + M : nullptr;
+  b200bo_best_t* dbest = reinterpret_cast<b200bo_best_t*>(dvar + M + (grad ? M * D : 0));
+  if (M > 0) CU(cudaMemcpyAsync(dXs, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, h->stream));
+  rc = b200bo_acquire_dev(h, kind, p, np, dXs, M, seed, idx_offset, dval, dgrad, mu ? dmu : nullptr, var ? dvar : nullptr, dbest);
+  if (rc) return rc;
+  if (M > 0) {
+    if (values) CU(cudaMemcpyAsync(values, dval, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+    if (mu) CU(cudaMemcpyAsync(mu, dmu, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+    if (var) CU(cudaMemcpyAsync(var, dvar, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+    if (grad) CU(cudaMemcpyAsync(grad, dgrad, sizeof(double) * M * D, cudaMemcpyDeviceToHost, h->stream));
+  }
+  b200bo_best_t hb = {-INFINITY, -1};
+  CU(cudaMemcpyAsync(&hb, dbest, sizeof(hb), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
+  if (best) *best = hb;
+  if (best_x && hb.index >= 0) memcpy(best_x, Xs + (hb.index - idx_offset) * D, sizeof(double) * D);
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_predict(b200bo_handle_t h, const double* Xs, int64_t M, double* mu, double* var) {
+  if (!h || M < 0 || (M > 0 && (!Xs || !mu || !var))) return fail(h, B200BO_ERR_ARG, "bad arguments to predict");
+  cudaSetDevice(h->device);
+  const int64_t D = h->D;
+  int32_t rc = ensure_io(h, sizeof(double) * (M * D + 2 * M + 2));
+  if (rc) return rc;
+  double* dXs = h->dio;
+  double* dmu = dXs + M * D;
+  double* dvar = dmu + M;
+  if (M > 0) CU(cudaMemcpyAsync(dXs, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, h->stream));
+  rc = b200bo_predict_dev(h, dXs, M, dmu, dvar);
+  if (rc) return rc;
+  if (M > 0) {
+    CU(cudaMemcpyAsync(mu, dmu, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(var, dvar, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int32_t P, int32_t S, int32_t mask, double* mll, double* dmll) {
+  if (!h || !Theta || !mll || S < 0) return fail(h, B200BO_ERR_ARG, "bad arguments to mll_sweep");
+  const bool m_noise = mask & B200BO_MASK_NOISE, m_mean = (mask & B200BO_MASK_MEAN) && h->mean_kind == B200BO_MEAN_CONST,
+             m_kern = mask & B200BO_MASK_KERN;
+  const int nl = (int)h->hp.ll.size();
+  const int Pexp = (m_noise ? 1 : 0) + (m_mean ? 1 : 0) + (m_kern ? nl + 1 : 0);
+  if (P != Pexp) return fail(h, B200BO_ERR_ARG, "Theta has the wrong number of rows for this mask");
+  if (h->N == 0) return fail(h, B200BO_ERR_STATE, "mll needs observations");
+  cudaSetDevice(h->device);
+  const Hyper saved = h->hp;
+  int32_t rc = B200BO_OK;
+  cudaEventRecord(h->ev[6], h->stream);
+  for (int s = 0; s < S && rc == B200BO_OK; ++s) {
+    const double* th = Theta + (int64_t)s * P;
+    int i = 0;
+    if (m_noise) h->hp.lognoise = th[i++];
+    if (m_mean) h->hp.beta = th[i++];
+    if (m_kern) { for (auto& l : h->hp.ll) l = th[i++]; h->hp.lsigma = th[i++]; }
+    rc = refit(h);
+    if (rc) break;
+    mll[s] = h->mll;
+    if (dmll) {
+      double raw[35];
+      cudaError_t e = launch_kinv(h);
+      if (e == cudaSuccess) e = launch_dmll(h, mask, h->dscal + 8);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(raw, h->dscal + 8, sizeof(raw), cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { rc = fail(h, B200BO_ERR_CUDA, std::string("mll gradient: ") + cudaGetErrorString(e)); break; }
+      double* g = dmll + (int64_t)s * P;
+      int j = 0;
+      if (m_noise) g[j++] = exp(2.0 * h->hp.lognoise) * raw[33];
+      if (m_mean) g[j++] = raw[34];
+      if (m_kern) {
+        if (h->iso) { double t = 0.0; for (int d = 0; d < h->D; ++d) t += raw[d]; g[j++] = 0.5 * t; }
+        else for (int d = 0; d < h->D; ++d) g[j++] = 0.5 * raw[d];
+        g[j++] = raw[32];
+      }
+    }
+  }
+  cudaEventRecord(h->ev[7], h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaEventElapsedTime(&h->timing[B200BO_T_MLL], h->ev[6], h->ev[7]);
+  h->hp = saved;
+  h->fitted = false;   // the factor now belongs to the last swept setting; refactor lazily with the restored params
+  return rc;
+}
+
+B200BO_API int32_t b200bo_last_timing_ms(b200bo_handle_t h, int32_t which, float* ms) {
+  if (!h || !ms || which < 0 || which >= B200BO_T_COUNT) return fail(h, B200BO_ERR_ARG, "bad arguments to last_timing_ms");
+  if (which == B200BO_T_ACQ) {   // the _dev entries do not synchronise; resolve the event pair on demand
+    cudaSetDevice(h->device);
+    if (cudaEventSynchronize(h->ev[5]) == cudaSuccess) cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
+  }
+  *ms = h->timing[which];
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_launch_count(b200bo_handle_t h, int64_t* n) {
+  if (!h || !n) return fail(h, B200BO_ERR_ARG, "null argument");
+  *n = h->launches;
+  return B200BO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// handle.h -- host-side state of one GP model resident on one B200, and the launcher prototypes of the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/b200bo.h"
+
+namespace b200bo {
+
+struct Hyper {               // current hyper-parameters (EXT GaussianProcesses.jl parametrisation)
+  double lognoise = -2.0;    // sigma_n = exp(lognoise)
+  double beta = 0.0;         // MeanConst
+  double lsigma = 0.0;       // sigma_f = exp(lsigma)
+  std::vector<double> ll;    // log length-scales: 1 (Iso) or D (Ard)
+};
+
+}  // namespace b200bo
+
+struct b200bo_handle_s {
+  int device = 0, D = 0, kernel_kind = 0, mean_kind = 0, fam = 0;
+  bool iso = false;
+  int num_sms = 148;
+  int64_t cap = 0;           // capacity in points, multiple of NB
+  int64_t N = 0, Np = 0;     // observations, padded to a multiple of NB
+  int64_t ld = 0;            // leading dimension of the factor (== cap)
+  b200bo::Hyper hp;
+  std::vector<double> hX, hy;     // host copies of model.x (D x N col-major), model.y
+  // device buffers
+  double* dX = nullptr;      // [cap][D] raw inputs (point-major == D x N column-major)
+  double* dZ = nullptr;      // [cap][D] inputs scaled by 1/l_d
+  double* dy = nullptr;      // [cap]
+  double* dw = nullptr;      // [cap] work vector for the single-RHS solves
+  double* dalpha = nullptr;  // [cap] (zero in the padding)
+  double* dinv_ell = nullptr;  // [D]
+  double* dL = nullptr;      // [ld][ld] mirrored factor: lower = L (row-major) == U column-major, upper = L^T
+  double* dLinv = nullptr;   // [cap/NB][NB][NB] inverses of the diagonal blocks
+  double* dLinvT = nullptr;  //   and their transposes
+  double* dV = nullptr;      // per-CTA solve panels [nslots][TILE_N][ld]
+  int64_t nslots = 0;
+  double* dscal = nullptr;   // small scalar outputs (logdet, r'alpha, ...)
+  int* dinfo = nullptr;      // non-PD flag
+  b200bo_best_t* dcta_best = nullptr;   // [grid]
+  b200bo_best_t* dbest = nullptr;
+  double* dpart = nullptr;   // partial sums for the mll gradient
+  double* dio = nullptr;     // staging for host-pointer entry points
+  int64_t dio_bytes = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev[8] = {};
+  bool fitted = false;
+  double mll = 0.0;
+  int jitter = 0;
+  int64_t launches = 0;
+  float timing[B200BO_T_COUNT] = {};
+  std::string err;
+};
+
+namespace b200bo {
+
+// kmat.cu
+cudaError_t launch_scale_inputs(b200bo_handle_s* h, int64_t n0, int64_t n1);
+cudaError_t launch_kmat(b200bo_handle_s* h, double* dK, int64_t ld, int64_t N, int64_t Np, double noise, bool pad_identity);
+// chol.cu
+cudaError_t launch_cholesky(b200bo_handle_s* h);   // in place on h->dL (lower triangle), fills dLinv/dLinvT, upper mirror
+// solve.cu
+cudaError_t launch_alpha_mll(b200bo_handle_s* h);  // dw = y - m -> dalpha, dscal[0] = logdet, dscal[1] = r'alpha
+// acq.cu
+struct AcqLaunch {
+  int acq_kind = -1;         // -1: predict only
+  double p0 = 0.0, p1 = 0.0;
+  uint64_t seed = 0;
+  int64_t idx_offset = 0;
+  const double* dXs = nullptr;
+  int64_t M = 0;
+  double *dvalues = nullptr, *dgrad = nullptr, *dmu = nullptr, *dvar = nullptr;
+  b200bo_best_t* dbest = nullptr;
+};
+cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& a);
+size_t acq_smem_bytes(int D);
+// mll.cu
+cudaError_t launch_kinv(b200bo_handle_s* h);       // K^-1 into h->dV (panel layout [n][ld])
+cudaError_t launch_dmll(b200bo_handle_s* h, int mask, double* dout /*P*/);
+
+}  // namespace b200bo

@@ -1,0 +1,122 @@
+// solve.cu -- K5: alpha = Sigma^-1 (y - m) by two single-RHS triangular solves, logdet, r'alpha.
+//
+// Replaces EXT GaussianProcesses.jl `update_mll!`:  alpha = cK \ (y - mean);  mll = -(y'alpha + logdet + N log 2pi)/2
+// (reached from update!(model,x,y), reference src/models/gp.jl:11-18; SURVEY App. A "Fit").
+// HBM-bound: each solve reads the triangle once (4 N^2 bytes).  Right-looking over 128-wide blocks, one launch
+// per block: CTA b applies the just-solved block to its 128 rows; the CTA that owns the next diagonal block
+// then solves it with the pre-inverted block (fixed summation order => deterministic).
+#include "common.cuh"
+#include "handle.h"
+
+namespace b200bo {
+
+__global__ void residual_kernel(const double* __restrict__ y, double beta, double* __restrict__ w, int N, int Np) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Np) w[i] = i < N ? y[i] - beta : 0.0;
+}
+
+// z_blk = M * w_blk with M given TRANSPOSED (MT[c][m]) so that threads m read coalesced.
+__device__ __forceinline__ void diag_apply(const double* __restrict__ MT, const double* wblk, double* out, double* sh, int tid) {
+  if (tid < NB) sh[tid] = wblk[tid];
+  __syncthreads();
+  if (tid < NB) {
+    double s = 0.0;
+    for (int c = 0; c < NB; ++c) s = fma(MT[c * NB + tid], sh[c], s);
+    out[tid] = s;
+  }
+}
+
+// forward step i (i = -1: only the first diagonal solve).  grid = nblk - i - 1 CTAs (min 1), 256 threads.
+__global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ LinvT,
+                                                       double* __restrict__ w, double* __restrict__ z, int i) {
+  __shared__ double sh[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rb = i + 1 + blockIdx.x;     // row block handled by this CTA
+  if (i >= 0) {
+    if (tid < NB) sh[tid] = z[i * NB + tid];
+    __syncthreads();
+    // w[r] -= L[r][i*NB .. +127] . z_i ; one warp per row, 16 rows per warp
+    for (int rr = warp; rr < NB; rr += 8) {
+      const int64_t r = (int64_t)rb * NB + rr;
+      const double* Lr = L + r * ld + (int64_t)i * NB;
+      const double2 a = *reinterpret_cast<const double2*>(Lr + 4 * lane);
+      const double2 b = *reinterpret_cast<const double2*>(Lr + 4 * lane + 2);
+      double s = a.x * sh[4 * lane];
+      s = fma(a.y, sh[4 * lane + 1], s);
+      s = fma(b.x, sh[4 * lane + 2], s);
+      s = fma(b.y, sh[4 * lane + 3], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) w[r] -= s;
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) diag_apply(LinvT + (int64_t)rb * NB * NB, w + (int64_t)rb * NB, z + (int64_t)rb * NB, sh, tid);
+}
+
+// backward step i (descending; i = nblk: only the last diagonal solve).  grid = max(i,1) CTAs.
+//   w[c] -= sum_m L[i*NB+m][c] * alpha_i[m] for the 128 columns c of column block cb; CTA cb == i-1 then solves it.
+__global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ Linv,
+                                                       double* __restrict__ w, double* __restrict__ alpha, int i, int nblk) {
+  __shared__ double sh[NB];
+  __shared__ double part[2][NB];
+  const int tid = threadIdx.x;
+  const int cb = (i < nblk) ? (int)blockIdx.x : nblk - 1;
+  if (i < nblk) {
+    if (tid < NB) sh[tid] = alpha[i * NB + tid];
+    __syncthreads();
+    const int c = tid & 127, half = tid >> 7;   // two halves of the 128 rows, fixed combine order
+    const double* Lc = L + ((int64_t)i * NB + half * 64) * ld + (int64_t)cb * NB + c;
+    double s = 0.0;
+    for (int m = 0; m < 64; ++m) s = fma(Lc[(int64_t)m * ld], sh[half * 64 + m], s);
+    part[half][c] = s;
+    __syncthreads();
+    if (tid < NB) w[(int64_t)cb * NB + tid] -= part[0][tid] + part[1][tid];
+    __syncthreads();
+  }
+  if (i == nblk || cb == i - 1)   // alpha_cb = L_cb^-T w_cb : (Linv^T) given transposed == Linv
+    diag_apply(Linv + (int64_t)cb * NB * NB, w + (int64_t)cb * NB, alpha + (int64_t)cb * NB, sh, tid);
+}
+
+// scal[0] = logdet = 2 sum log L_ii (i < N), scal[1] = r'alpha.  Single CTA, fixed order.
+__global__ void __launch_bounds__(256) logdet_dot_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ y,
+                                                         double beta, const double* __restrict__ alpha, int N, double* __restrict__ scal) {
+  __shared__ double s0[256], s1[256];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) {
+    a += log(L[(int64_t)i * ld + i]);
+    b = fma(y[i] - beta, alpha[i], b);
+  }
+  s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { scal[0] = 2.0 * s0[0]; scal[1] = s1[0]; }
+}
+
+cudaError_t launch_alpha_mll(b200bo_handle_s* h) {
+  const int nblk = (int)(h->Np / NB);
+  const double beta = h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0;
+  residual_kernel<<<(int)((h->Np + 255) / 256), 256, 0, h->stream>>>(h->dy, beta, h->dw, (int)h->N, (int)h->Np);
+  h->launches++;
+  double* z = h->dalpha;   // forward result lives in dalpha, then becomes w of the backward pass
+  for (int i = -1; i < nblk - 1; ++i) {
+    const int grid = i < 0 ? 1 : nblk - i - 1;
+    fwd_step_kernel<<<grid, 256, 0, h->stream>>>(h->dL, h->ld, h->dLinvT, h->dw, z, i);
+    h->launches++;
+  }
+  // backward: w := z, alpha overwrites block by block (block i of w is final before alpha_i is written)
+  cudaMemcpyAsync(h->dw, z, sizeof(double) * h->Np, cudaMemcpyDeviceToDevice, h->stream);
+  for (int i = nblk; i >= 1; --i) {
+    const int grid = (i < nblk) ? i : 1;
+    bwd_step_kernel<<<grid, 256, 0, h->stream>>>(h->dL, h->ld, h->dLinv, h->dw, h->dalpha, i, nblk);
+    h->launches++;
+  }
+  logdet_dot_kernel<<<1, 256, 0, h->stream>>>(h->dL, h->ld, h->dy, beta, h->dalpha, (int)h->N, h->dscal);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace b200bo

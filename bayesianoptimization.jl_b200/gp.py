@@ -1,0 +1,255 @@
+"""Model adapter: the reference's model plugin API (src/models/gp.jl) on top of libb200bo.
+
+`B200GPE` stands where the reference uses `ElasticGPE(D; mean, kernel, logNoise, capacity)` (README.md:22-26):
+it implements the generic functions the BO loop dispatches on -- mean_var, myrand, dims, maxy, update!,
+optimizemodel! -- by calling the C ABI (same calls as julia/B200BayesOpt.jl makes with ccall).  Points are
+COLUMNS (D x N) as in the reference (gp.jl:9).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, dptr
+
+
+# --- EXT GaussianProcesses.jl constructors used in reference scripts (README.md:22-26, test/branin.jl:24-26) ---
+class MeanZero:
+    kind = "MeanZero"
+    params = ()
+
+
+class MeanConst:
+    kind = "MeanConst"
+
+    def __init__(self, beta: float = 0.0):
+        self.beta = float(beta)
+
+    @property
+    def params(self):
+        return (self.beta,)
+
+
+class _Kernel:
+    def __init__(self, kind, ll, lsigma):
+        self.kind = kind
+        self.ll = np.atleast_1d(np.asarray(ll, float)).copy()
+        self.lsigma = float(lsigma)
+
+
+def SEIso(ll, lsigma): return _Kernel("SEIso", [ll], lsigma)
+def SEArd(ll, lsigma): return _Kernel("SEArd", ll, lsigma)
+def Mat12Iso(ll, lsigma): return _Kernel("Mat12Iso", [ll], lsigma)
+def Mat12Ard(ll, lsigma): return _Kernel("Mat12Ard", ll, lsigma)
+def Mat32Iso(ll, lsigma): return _Kernel("Mat32Iso", [ll], lsigma)
+def Mat32Ard(ll, lsigma): return _Kernel("Mat32Ard", ll, lsigma)
+def Mat52Iso(ll, lsigma): return _Kernel("Mat52Iso", [ll], lsigma)
+def Mat52Ard(ll, lsigma): return _Kernel("Mat52Ard", ll, lsigma)
+
+
+class B200GPE:
+    """ElasticGPE-shaped GP whose factor, alpha and data live in B200 HBM."""
+
+    def __init__(self, D: int, mean=None, kernel=None, logNoise: float = -2.0, capacity: int = 3000, device: int = 0):
+        mean = MeanZero() if mean is None else mean
+        kernel = SEArd(np.zeros(D), 0.0) if kernel is None else kernel
+        if not kernel.kind.endswith("Iso") and kernel.ll.size != D:
+            raise ValueError("ARD kernel needs one length-scale per input dimension")
+        self.D = int(D)
+        self.mean_kind, self.kernel_kind = mean.kind, kernel.kind
+        self._h = C.c_void_p()
+        check(lib.b200bo_create(C.byref(self._h), device, self.D, int(capacity), _lib.KERNEL_KINDS[kernel.kind],
+                                _lib.MEAN_KINDS[mean.kind]))
+        theta = [float(logNoise), *mean.params, *kernel.ll.tolist(), kernel.lsigma]
+        self.set_params(np.array(theta, float))
+
+    @classmethod
+    def from_data(cls, X, y, mean=None, kernel=None, logNoise: float = -2.0, **kw):
+        """GPE(x, y, mean, kernel, logNoise) (test/acquisitionfunctions.jl:4, test/acquisition.jl:2)."""
+        X = np.asarray(X, float)
+        X = X.reshape(1, -1) if X.ndim == 1 else X
+        gp = cls(X.shape[0], mean=mean, kernel=kernel, logNoise=logNoise, capacity=max(X.shape[1], 1), **kw)
+        gp.fit(X, y)
+        return gp
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.b200bo_destroy(h)
+
+    # -- hyper-parameters: theta = [logNoise, (beta), ll..., lsigma] ------------------------------------------
+    @property
+    def num_params(self) -> int:
+        p = C.c_int32()
+        check(lib.b200bo_num_params(self._h, C.byref(p)), self._h)
+        return p.value
+
+    def get_params(self) -> np.ndarray:
+        th = np.empty(self.num_params)
+        check(lib.b200bo_get_params(self._h, dptr(th), th.size), self._h)
+        return th
+
+    def set_params(self, theta):
+        th = np.ascontiguousarray(theta, float)
+        check(lib.b200bo_set_params(self._h, dptr(th), th.size), self._h)
+
+    # -- data ------------------------------------------------------------------------------------------------
+    def fit(self, X, y):
+        X = np.asfortranarray(np.asarray(X, float).reshape(self.D, -1))
+        y = np.ascontiguousarray(y, float).ravel()
+        if X.shape[1] != y.size:
+            raise ValueError("X must be D x N with N == length(y)")
+        check(lib.b200bo_fit(self._h, dptr(X), dptr(y), y.size), self._h)
+
+    def append(self, X, y):
+        X = np.asfortranarray(np.asarray(X, float).reshape(self.D, -1))
+        y = np.ascontiguousarray(y, float).ravel()
+        if X.shape[1] != y.size:
+            raise ValueError("X must be D x m with m == length(y)")
+        check(lib.b200bo_append(self._h, dptr(X), dptr(y), y.size), self._h)
+
+    @property
+    def nobs(self) -> int:
+        n = C.c_int64()
+        check(lib.b200bo_dims(self._h, None, C.byref(n)), self._h)
+        return n.value
+
+    @property
+    def x(self) -> np.ndarray:          # model.x, D x N
+        X = np.empty((self.D, self.nobs), order="F")
+        check(lib.b200bo_get_data(self._h, dptr(X), None), self._h)
+        return X
+
+    @property
+    def y(self) -> np.ndarray:          # model.y
+        y = np.empty(self.nobs)
+        check(lib.b200bo_get_data(self._h, None, dptr(y)), self._h)
+        return y
+
+    @property
+    def mll(self) -> float:
+        v = C.c_double()
+        check(lib.b200bo_get_mll(self._h, C.byref(v)), self._h)
+        return v.value
+
+    @property
+    def alpha(self) -> np.ndarray:
+        a = np.empty(self.nobs)
+        check(lib.b200bo_get_alpha(self._h, dptr(a)), self._h)
+        return a
+
+    @property
+    def factor(self) -> np.ndarray:     # upper U, Sigma = U'U
+        n = self.nobs
+        U = np.empty((n, n), order="F")
+        check(lib.b200bo_get_factor(self._h, dptr(U)), self._h)
+        return U
+
+    @property
+    def jitter_tries(self) -> int:
+        t = C.c_int32()
+        check(lib.b200bo_jitter_tries(self._h, C.byref(t)), self._h)
+        return t.value
+
+    def kmat(self) -> np.ndarray:
+        n = self.nobs
+        K = np.empty((n, n), order="F")
+        check(lib.b200bo_kmat(self._h, dptr(K)), self._h)
+        return K
+
+    def timing_ms(self, which: int) -> float:
+        ms = C.c_float()
+        check(lib.b200bo_last_timing_ms(self._h, which, C.byref(ms)), self._h)
+        return ms.value
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(lib.b200bo_launch_count(self._h, C.byref(n)), self._h)
+        return n.value
+
+    # -- posterior / acquisition ------------------------------------------------------------------------------
+    def _cands(self, X):
+        X = np.asarray(X, float)
+        if X.ndim == 1:
+            X = X.reshape(-1, 1)
+        if X.shape[0] != self.D:
+            raise ValueError(f"candidates must be {self.D} x M")
+        return np.asfortranarray(X)
+
+    def predict(self, X):
+        Xs = self._cands(X)
+        M = Xs.shape[1]
+        mu, var = np.empty(M), np.empty(M)
+        check(lib.b200bo_predict(self._h, dptr(Xs), M, dptr(mu), dptr(var)), self._h)
+        return mu, var
+
+    def acquire(self, kind: str, params, X, seed: int = 0, idx_offset: int = 0, want_values=True, want_grad=False,
+                want_mu_var=False):
+        """One fused acquisition step over the columns of X.  Returns a dict with best_value, best_index, best_x and
+        the optional per-candidate arrays."""
+        Xs = self._cands(X)
+        M = Xs.shape[1]
+        p = np.ascontiguousarray(params, float).ravel()
+        vals = np.empty(M) if want_values else None
+        grad = np.empty((self.D, M), order="F") if want_grad else None
+        mu = np.empty(M) if want_mu_var else None
+        var = np.empty(M) if want_mu_var else None
+        best = _lib.Best()
+        bx = np.full(self.D, np.nan)
+        check(lib.b200bo_acquire(self._h, _lib.ACQ_KINDS[kind], dptr(p) if p.size else None, p.size, dptr(Xs), M,
+                                 seed & 0xFFFFFFFFFFFFFFFF, idx_offset, dptr(vals), dptr(grad), dptr(mu), dptr(var),
+                                 C.byref(best), dptr(bx)), self._h)
+        return dict(best_value=best.value, best_index=best.index, best_x=bx, values=vals, grad=grad, mu=mu, var=var)
+
+    def mll_sweep(self, Theta, noise=True, domean=True, kern=True, want_grad=True):
+        Theta = np.asfortranarray(np.asarray(Theta, float))
+        Theta = Theta.reshape(-1, 1) if Theta.ndim == 1 else Theta
+        P, S = Theta.shape
+        mask = (_lib.MASK_NOISE if noise else 0) | (_lib.MASK_MEAN if domean else 0) | (_lib.MASK_KERN if kern else 0)
+        mll = np.empty(S)
+        dmll = np.empty((P, S), order="F") if want_grad else None
+        check(lib.b200bo_mll_sweep(self._h, dptr(Theta), P, S, mask, dptr(mll), dptr(dmll)), self._h)
+        return mll, dmll
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the generic functions of src/models/gp.jl, same names and argument meaning
+# ------------------------------------------------------------------------------------------------------------
+def mean_var(model: B200GPE, x):
+    """gp.jl:2-5 (vector -> scalars) and :8 (matrix -> vectors)."""
+    x = np.asarray(x, float)
+    mu, var = model.predict(x)
+    return (float(mu[0]), float(var[0])) if x.ndim == 1 else (mu, var)
+
+
+def myrand(model: B200GPE, x, seed: int = 0, idx_offset: int = 0):
+    """gp.jl:6-7.  Independent per-candidate posterior samples mu + sigma eps (quirk 9), eps from the Philox stream
+    keyed by (seed, global candidate index)."""
+    x = np.asarray(x, float)
+    r = model.acquire("TS", (), x, seed=seed, idx_offset=idx_offset)
+    return float(r["values"][0]) if x.ndim == 1 else r["values"]
+
+
+def dims(model: B200GPE):
+    """gp.jl:9 -- size(model.x) = (D, N)."""
+    return model.D, model.nobs
+
+
+def maxy(model: B200GPE) -> float:
+    """gp.jl:10."""
+    v = C.c_double()
+    check(lib.b200bo_maxy(model._h, C.byref(v)), model._h)
+    return v.value
+
+
+def update(model: B200GPE, x, y):
+    """update!(model, x, y), gp.jl:11-18: elastic append; an empty y refits on the current data."""
+    y = np.asarray(y, float).ravel()
+    if y.size == 0:
+        check(lib.b200bo_refit(model._h), model._h)
+    else:
+        model.append(x, y)

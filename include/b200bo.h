@@ -1,0 +1,142 @@
+/* b200bo.h -- C ABI of libb200bo.so: the B200-native (sm_100a) GP-posterior + acquisition-search path.
+ *
+ * The reference (jbrea/BayesianOptimization.jl) has no FFI; its plugin boundary is Julia multiple dispatch
+ * on the model type (src/models/gp.jl:2-18,42-77) plus the NLopt-backed search (src/acquisition.jl:20-68).
+ * Each entry below names the reference interface it replaces.  A Julia host binds these with `ccall`
+ * (bayesianoptimization.jl_b200/julia/B200BayesOpt.jl); the Python host mirror binds the
+ * same symbols with ctypes.
+ *
+ * Conventions
+ *  - all reals IEEE Float64, all sizes int64_t, matrices COLUMN-MAJOR with points as columns (model.x is
+ *    D x N, src/models/gp.jl:9; candidates D x M, test/acquisitionfunctions.jl:6).
+ *  - every entry returns an int32 status (B200BO_OK == 0, negative = error) and never throws.
+ *  - pointers are HOST pointers unless the entry name ends in `_dev`; `_dev` entries take DEVICE pointers,
+ *    only enqueue work on the handle's stream and return without synchronising (use b200bo_sync).
+ *  - a handle is not re-entrant; distinct handles are independent.
+ *  - there is NO CPU fallback: without a usable CUDA device every compute entry returns B200BO_ERR_CUDA.
+ */
+#ifndef B200BO_H
+#define B200BO_H
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200BO_API __attribute__((visibility("default")))
+#else
+#define B200BO_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200bo_handle_s* b200bo_handle_t;
+
+/* status codes */
+enum {
+  B200BO_OK = 0,
+  B200BO_ERR_ARG = -1,       /* invalid argument (the reference throws ArgumentError / DimensionMismatch) */
+  B200BO_ERR_CUDA = -2,      /* CUDA runtime / driver error, or no device */
+  B200BO_ERR_NOTPD = -3,     /* not positive definite after 10 jitter retries (EXT make_posdef!) */
+  B200BO_ERR_STATE = -4,     /* call needs a fitted model */
+  B200BO_ERR_ALLOC = -5
+};
+
+/* EXT GaussianProcesses.jl kernels reachable from the reference (README.md:22-26, BayesianOptimization.jl:259-264,
+ * test/acquisitionfunctions.jl:4).  Kernel parameter vector: Iso = [ll, lsigma], Ard = [ll_1..ll_D, lsigma]. */
+enum {
+  B200BO_KERNEL_SEISO = 0, B200BO_KERNEL_SEARD = 1,
+  B200BO_KERNEL_MAT12ISO = 2, B200BO_KERNEL_MAT12ARD = 3,
+  B200BO_KERNEL_MAT32ISO = 4, B200BO_KERNEL_MAT32ARD = 5,
+  B200BO_KERNEL_MAT52ISO = 6, B200BO_KERNEL_MAT52ARD = 7
+};
+enum { B200BO_MEAN_ZERO = 0, B200BO_MEAN_CONST = 1 };
+
+/* acquisition functors, src/acquisitionfunctions.jl:21-28 (PI), :40-50 (EI), :81-96 (UCB), :107-108 (TS),
+ * :126-141 (MI), :110-111 (MaxMean).  acq_params: PI/EI = {tau}; UCB = {beta_t}; MI = {sqrt_alpha, gamma_hat};
+ * TS/MaxMean = none.  The host computes them in setparams! (:3,44-46,91-95,131-140). */
+enum {
+  B200BO_ACQ_PI = 0, B200BO_ACQ_EI = 1, B200BO_ACQ_UCB = 2, B200BO_ACQ_TS = 3, B200BO_ACQ_MI = 4,
+  B200BO_ACQ_MAXMEAN = 5
+};
+
+/* parameter-selection mask for b200bo_mll_sweep == get_params_kwargs(gp; noise, domean, kern) (gp.jl:55-58) */
+enum { B200BO_MASK_NOISE = 1, B200BO_MASK_MEAN = 2, B200BO_MASK_KERN = 4 };
+
+/* which device timing b200bo_last_timing_ms returns (CUDA events on the handle's stream) */
+enum {
+  B200BO_T_KMAT = 0,      /* kernel-matrix assembly (K1) of the last fit */
+  B200BO_T_CHOL = 1,      /* blocked Cholesky (K2-K4) of the last fit */
+  B200BO_T_SYRK = 2,      /* sum of trailing-update launches (K4) of the last fit */
+  B200BO_T_ALPHA = 3,     /* alpha / logdet (K5) of the last fit */
+  B200BO_T_ACQ = 4,       /* fused acquisition launch (K6) of the last predict/acquire */
+  B200BO_T_MLL = 5,       /* last mll sweep, all settings */
+  B200BO_T_COUNT = 6
+};
+
+typedef struct { double value; int64_t index; } b200bo_best_t;   /* index = -1: nothing beat -Inf */
+
+/* -- lifecycle: replaces ElasticGPE(D; mean, kernel, logNoise, capacity) (README.md:22-26) ------------------- */
+B200BO_API int32_t b200bo_create(b200bo_handle_t* h, int32_t device, int32_t D, int64_t capacity,
+                      int32_t kernel_kind, int32_t mean_kind);
+B200BO_API int32_t b200bo_destroy(b200bo_handle_t h);
+B200BO_API const char* b200bo_last_error(b200bo_handle_t h);          /* valid until the next call on h; h may be NULL */
+B200BO_API int32_t b200bo_set_stream(b200bo_handle_t h, void* cuda_stream);   /* borrow a caller stream (NULL = own) */
+B200BO_API int32_t b200bo_sync(b200bo_handle_t h);
+
+/* -- hyper-parameters: EXT get_params / set_params! (gp.jl:55-58,60,74). theta = [logNoise, (beta), kernel...] */
+B200BO_API int32_t b200bo_num_params(b200bo_handle_t h, int32_t* P);
+B200BO_API int32_t b200bo_set_params(b200bo_handle_t h, const double* theta, int32_t P);   /* invalidates the factor */
+B200BO_API int32_t b200bo_get_params(b200bo_handle_t h, double* theta, int32_t P);
+
+/* -- model update: update!(model, X, y) (gp.jl:11-18).  fit = full refactor (GP.fit!), append = elastic append! */
+B200BO_API int32_t b200bo_fit(b200bo_handle_t h, const double* X, const double* y, int64_t N);
+B200BO_API int32_t b200bo_append(b200bo_handle_t h, const double* Xnew, const double* ynew, int64_t m);
+B200BO_API int32_t b200bo_refit(b200bo_handle_t h);                   /* refactor with current data + params */
+
+/* -- model queries: dims / maxy / model.x / model.y (gp.jl:9-10, BayesianOptimization.jl:117-119) ------------ */
+B200BO_API int32_t b200bo_dims(b200bo_handle_t h, int32_t* D, int64_t* N);
+B200BO_API int32_t b200bo_maxy(b200bo_handle_t h, double* maxy);      /* -Inf when empty */
+B200BO_API int32_t b200bo_get_data(b200bo_handle_t h, double* X, double* y);
+B200BO_API int32_t b200bo_get_mll(b200bo_handle_t h, double* mll);    /* gp.mll / gp.target */
+B200BO_API int32_t b200bo_get_alpha(b200bo_handle_t h, double* alpha);
+B200BO_API int32_t b200bo_get_factor(b200bo_handle_t h, double* U);   /* N x N column-major upper factor, Sigma = U'U */
+B200BO_API int32_t b200bo_jitter_tries(b200bo_handle_t h, int32_t* tries);
+
+/* -- posterior: mean_var(model, X) = GP.predict_f (gp.jl:2-5,8) ---------------------------------------------- */
+B200BO_API int32_t b200bo_predict(b200bo_handle_t h, const double* Xs, int64_t M, double* mu, double* var);
+
+/* -- acquisition step: acquisitionfunction(a, model)(X) + the selection rule of acquire_max
+ *    (acquisitionfunctions.jl:4-9, acquisition.jl:54-68).  One fused launch over the M candidate columns:
+ *    k(x*,X), both triangular solves, mu, sigma^2, a(mu, sigma^2), optional gradient D x M, arg-max with
+ *    first-strict-maximum (lowest index) tie-break, NaN never wins.  idx_offset = global index of column 0 (keys
+ *    the TS Philox stream and is added to best->index) so shards of one candidate matrix agree with the whole. */
+B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params,
+                       const double* Xs, int64_t M, uint64_t seed, int64_t idx_offset,
+                       double* values /*M or NULL*/, double* grad /*D x M or NULL*/,
+                       double* mu /*M or NULL*/, double* var /*M or NULL*/,
+                       b200bo_best_t* best /*or NULL*/, double* best_x /*D or NULL*/);
+
+/* -- MAP objective: the closure of optimizemodel! (gp.jl:59-64): for each column of Theta (P x S) set the
+ *    masked params, refactor, return mll[S] and dmll (P x S, may be NULL).  Leaves the model at its
+ *    previous parameters. */
+B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int32_t P, int32_t S, int32_t mask,
+                         double* mll, double* dmll);
+
+/* -- device-pointer variants (inputs resident in HBM; enqueue only) ------------------------------------------ */
+B200BO_API int32_t b200bo_kmat_dev(b200bo_handle_t h, double* dK, int64_t ld);   /* K1 only: Sigma into dK (ld >= N) */
+B200BO_API int32_t b200bo_predict_dev(b200bo_handle_t h, const double* dXs, int64_t M, double* dmu, double* dvar);
+B200BO_API int32_t b200bo_acquire_dev(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params,
+                           const double* dXs, int64_t M, uint64_t seed, int64_t idx_offset,
+                           double* dvalues, double* dgrad, double* dmu, double* dvar,
+                           b200bo_best_t* dbest);
+
+/* -- introspection for benches / tests ----------------------------------------------------------------------- */
+B200BO_API int32_t b200bo_kmat(b200bo_handle_t h, double* K);         /* N x N Sigma = K + (e^{2 logNoise}+eps) I to host */
+B200BO_API int32_t b200bo_last_timing_ms(b200bo_handle_t h, int32_t which, float* ms);
+B200BO_API int32_t b200bo_launch_count(b200bo_handle_t h, int64_t* launches);   /* kernels launched since create */
+B200BO_API int32_t b200bo_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BO_H */
