@@ -1,0 +1,104 @@
+"""Acquisition search (src/acquisition.jl): the multi-restart maximisation, re-designed as ONE batched launch.
+
+The reference runs `restarts` serial NLopt optimisations, each calling the closure up to `maxeval` times
+(acquisition.jl:54-68).  Here `restarts` becomes the number M of Latin-hypercube candidates scored -- value,
+optional gradient and arg-max -- by a single fused kernel launch (b200bo_acquire).  `polish` optionally runs a
+box-bounded L-BFGS from the winning candidate on value+gradient evaluated by the same kernel, mirroring what
+one NLopt LD_LBFGS run adds on top of a start point (honours maxeval / ftol / xtol style options).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from .acquisitionfunctions import (AbstractAcquisition, MaxMean, ThompsonSamplingSimple, setparams)
+from .gp import B200GPE
+from .utils import ScaledLHSIterator
+
+
+def defaultoptions(model_type, acq_type) -> dict:
+    """defaultoptions(::Type{<:Model}, ::Type{<:AbstractAcquisition}) (acquisition.jl:4-9).  The B200 model type
+    keeps the reference's keys; `restarts` defaults to a batch that fills the chip."""
+    if acq_type is ThompsonSamplingSimple or (isinstance(acq_type, type) and issubclass(acq_type, ThompsonSamplingSimple)):
+        return dict(method="GN_DIRECT_L", restarts=16384, maxeval=2000)
+    return dict(method="LD_LBFGS", restarts=16384, maxeval=2000)
+
+
+class AcquisitionSearch:
+    """Stands where the reference keeps an `NLopt.Opt` (BOpt.opt, BayesianOptimization.jl:74,134): options are
+    attributes (test/acquisition.jl:7-9 reads opt.maxeval, opt.maxtime, opt.ftol_abs)."""
+
+    def __init__(self, a: AbstractAcquisition, model: B200GPE, lowerbounds, upperbounds, options: dict):
+        self.acquisition, self.model = a, model
+        self.lower_bounds = np.asarray(lowerbounds, float).copy()
+        self.upper_bounds = np.asarray(upperbounds, float).copy()
+        self.method = options.get("method", "LD_LBFGS")
+        self.maxeval, self.maxtime = 0, 0.0
+        self.ftol_abs = self.ftol_rel = self.xtol_abs = self.xtol_rel = 0.0
+        self.polish = True
+        self.seed = 0
+        self.rng = None
+        for k, v in options.items():                 # acquisition.jl:24-27: every key but method/restarts is set
+            if k in ("method", "restarts"):
+                continue
+            setattr(self, k, v)
+        self.gradient = str(self.method)[1] == "D"   # acquisition.jl:31: 2nd character of the method name
+        self.last = None
+
+
+def nlopt_setup(a: AbstractAcquisition, model: B200GPE, lowerbounds, upperbounds, options: dict) -> AcquisitionSearch:
+    """acquisition.jl:20-38."""
+    opt = AcquisitionSearch(a, model, lowerbounds, upperbounds, options)
+    setparams(a, model)                              # :30
+    return opt
+
+
+def _polish(opt: AcquisitionSearch, x0: np.ndarray, f0: float):
+    from scipy.optimize import minimize
+    a, model = opt.acquisition, opt.model
+    lb, ub = opt.lower_bounds, opt.upper_bounds
+
+    def negf(x):
+        r = model.acquire(a.kind, a.params(), x, want_grad=True)
+        return -float(r["values"][0]), -r["grad"][:, 0]
+
+    kw = dict(maxfun=int(opt.maxeval) if opt.maxeval else 15000)
+    if opt.ftol_rel:
+        kw["ftol"] = float(opt.ftol_rel)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = minimize(negf, np.clip(x0, lb, ub), jac=True, method="L-BFGS-B", bounds=list(zip(lb, ub)), options=kw)
+    if np.isfinite(res.fun) and -res.fun > f0:
+        return -float(res.fun), np.asarray(res.x, float)
+    return f0, x0
+
+
+def acquire_max(opt, lowerbounds=None, upperbounds=None, restarts=None, options=None):
+    """acquire_max (acquisition.jl:42-68).  Forms:
+         acquire_max(opt, lb, ub, restarts)              (:54)   opt from nlopt_setup
+         acquire_max(a, model, lb, ub, options)          (:49)
+       Returns (maxf, maxx): first strict maximum over the candidates; if nothing beats -Inf, (-Inf, lowerbounds)."""
+    if isinstance(opt, AbstractAcquisition):         # (a, model, lb, ub, options)
+        a, model, lb, ub, options = opt, lowerbounds, upperbounds, restarts, options
+        o = nlopt_setup(a, model, lb, ub, options)
+        return acquire_max(o, lb, ub, options["restarts"])
+    lb = np.asarray(lowerbounds, float); ub = np.asarray(upperbounds, float)
+    a, model = opt.acquisition, opt.model
+    seq = ScaledLHSIterator(lb, ub, int(restarts), opt.rng)        # :57
+    derivative_free = isinstance(a, ThompsonSamplingSimple) or not opt.gradient
+    r = model.acquire(a.kind, a.params(), seq.data, seed=opt.seed, want_values=False)
+    opt.seed += 1
+    opt.last = r
+    if r["best_index"] < 0:
+        return -np.inf, lb                           # :55-56
+    maxf, maxx = r["best_value"], r["best_x"].copy()
+    if opt.polish and not derivative_free:
+        maxf, maxx = _polish(opt, maxx, maxf)
+    return maxf, maxx
+
+
+def acquire_model_max(o, options=None):
+    """acquire_model_max(o; options) (acquisition.jl:45-47): MaxMean on the current model."""
+    options = o.acquisitionoptions if options is None else options
+    return acquire_max(MaxMean(), o.model, o.lowerbounds, o.upperbounds, options)

@@ -118,6 +118,9 @@ int32_t refit(b200bo_handle_s* h) {
   cudaEventElapsedTime(&h->timing[B200BO_T_KMAT], h->ev[0], h->ev[1]);
   cudaEventElapsedTime(&h->timing[B200BO_T_CHOL], h->ev[1], h->ev[2]);
   cudaEventElapsedTime(&h->timing[B200BO_T_ALPHA], h->ev[2], h->ev[3]);
+  float syrk = 0.f;
+  for (int i = 0; i + 1 < h->syrk_ev_used; i += 2) { float t = 0.f; cudaEventElapsedTime(&t, h->syrk_ev[i], h->syrk_ev[i + 1]); syrk += t; }
+  h->timing[B200BO_T_SYRK] = syrk;
   h->fitted = true;
   return B200BO_OK;
 }
@@ -198,6 +201,7 @@ B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
   free_device(h);
   if (h->dio) cudaFree(h->dio);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->syrk_ev) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return B200BO_OK;
@@ -516,6 +520,13 @@ B200BO_API int32_t b200bo_last_timing_ms(b200bo_handle_t h, int32_t which, float
     if (cudaEventSynchronize(h->ev[5]) == cudaSuccess) cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
   }
   *ms = h->timing[which];
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_fp64_peak_tflops(b200bo_handle_t h, double* tflops) {
+  if (!h || !tflops) return fail(h, B200BO_ERR_ARG, "null argument");
+  cudaSetDevice(h->device);
+  CU(launch_dmma_peak(h, tflops));
   return B200BO_OK;
 }
 

@@ -175,13 +175,17 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
   cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trsm);
   cudaFuncSetAttribute(syrk_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_syrk);
   cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream);
+  while ((int)h->syrk_ev.size() < 2 * nblk) { cudaEvent_t e; cudaEventCreate(&e); h->syrk_ev.push_back(e); }
+  h->syrk_ev_used = 0;
   for (int k = 0; k < nblk; ++k) {
     potrf_diag_kernel<<<1, 256, sm_potrf, h->stream>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
     h->launches++;
     const int rem = nblk - k - 1;
     if (rem > 0) {
       trsm_panel_kernel<<<rem * (NB / TR_BM), TR_THREADS, sm_trsm, h->stream>>>(h->dL, h->ld, k, h->dLinv);
+      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], h->stream);
       syrk_trailing_kernel<<<rem * (rem + 1) / 2, SY_THREADS, sm_syrk, h->stream>>>(h->dL, h->ld, k);
+      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], h->stream);
       h->launches += 2;
     }
   }

@@ -48,6 +48,8 @@ struct b200bo_handle_s {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaEvent_t ev[8] = {};
+  std::vector<cudaEvent_t> syrk_ev;   // start/stop pairs around every trailing-update launch of the last factorisation
+  int syrk_ev_used = 0;
   bool fitted = false;
   double mll = 0.0;
   int jitter = 0;
@@ -78,6 +80,8 @@ struct AcqLaunch {
 };
 cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& a);
 size_t acq_smem_bytes(int D);
+// peak.cu
+cudaError_t launch_dmma_peak(b200bo_handle_s* h, double* tflops);
 // mll.cu
 cudaError_t launch_kinv(b200bo_handle_s* h);       // K^-1 into h->dV (panel layout [n][ld])
 cudaError_t launch_dmll(b200bo_handle_s* h, int mask, double* dout /*P*/);

@@ -165,6 +165,11 @@ class B200GPE:
         check(lib.b200bo_last_timing_ms(self._h, which, C.byref(ms)), self._h)
         return ms.value
 
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double()
+        check(lib.b200bo_fp64_peak_tflops(self._h, C.byref(v)), self._h)
+        return v.value
+
     @property
     def launch_count(self) -> int:
         n = C.c_int64()
@@ -253,3 +258,97 @@ def update(model: B200GPE, x, y):
         check(lib.b200bo_refit(model._h), model._h)
     else:
         model.append(x, y)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# model optimisers (src/BayesianOptimization.jl:44-49, src/models/gp.jl:20-77)
+# ------------------------------------------------------------------------------------------------------------
+class ModelOptimizer:
+    pass
+
+
+class NoModelOptimizer(ModelOptimizer):
+    """Don't optimize the model ever."""
+
+
+def defaultoptions_map() -> dict:
+    """defaultoptions(::Type{MAPGPOptimizer}) (gp.jl:48-52)."""
+    return dict(domean=True, kern=True, noise=True, lik=True, meanbounds=None, kernbounds=None, noisebounds=None,
+                likbounds=None, method="LD_LBFGS", maxeval=500)
+
+
+class MAPGPOptimizer(ModelOptimizer):
+    """MAPGPOptimizer(; every = 10, kwargs...) (gp.jl:20-41): MAP hyper-parameter fit every `every` steps."""
+
+    def __init__(self, every: int = 10, **kwargs):
+        self.i = 0
+        self.every = int(every)
+        self.options = {**defaultoptions_map(), **kwargs}
+
+
+def _bounds(model: B200GPE, o: dict):
+    """EXT GP.bounds(gp, noisebounds, meanbounds, kernbounds, likbounds; ...) in theta order; None -> +-Inf."""
+    lb, ub = [], []
+    nl = model.get_params().size - 1 - (1 if model.mean_kind == "MeanConst" else 0)   # kernel params
+    if o["noise"]:
+        nbd = o["noisebounds"]
+        lb.append(-np.inf if nbd is None else float(nbd[0])); ub.append(np.inf if nbd is None else float(nbd[1]))
+    if o["domean"] and model.mean_kind == "MeanConst":
+        mb = o["meanbounds"]
+        lb.extend([-np.inf] if mb is None else np.ravel(mb[0]).tolist()); ub.extend([np.inf] if mb is None else np.ravel(mb[1]).tolist())
+    if o["kern"]:
+        kb = o["kernbounds"]
+        lb.extend([-np.inf] * nl if kb is None else np.ravel(kb[0]).tolist()); ub.extend([np.inf] * nl if kb is None else np.ravel(kb[1]).tolist())
+    return np.array(lb, float), np.array(ub, float)
+
+
+def _mask_select(model: B200GPE, o: dict):
+    sel = []
+    n_mean = 1 if model.mean_kind == "MeanConst" else 0
+    P = model.num_params
+    if o["noise"]:
+        sel.append(0)
+    if o["domean"]:
+        sel.extend(range(1, 1 + n_mean))
+    if o["kern"]:
+        sel.extend(range(1 + n_mean, P))
+    return np.array(sel, int)
+
+
+def optimizemodel(o, model: B200GPE):
+    """optimizemodel!(o, model): NoModelOptimizer -> nothing (BayesianOptimization.jl:49); MAPGPOptimizer ->
+    every o.every-th call maximise mll over theta (gp.jl:42-47, 54-77).  The objective/gradient closure (gp.jl:59-64)
+    is b200bo_mll_sweep on the device; the outer box-bounded L-BFGS is host glue (NLopt LD_LBFGS in the reference)."""
+    if isinstance(o, NoModelOptimizer):
+        return None
+    ret = None
+    if o.i % o.every == 0:
+        ret = _map_fit(model, o.options)
+    o.i += 1
+    return ret
+
+
+def _map_fit(model: B200GPE, opts: dict):
+    from scipy.optimize import minimize
+    if model.nobs == 0:
+        return None
+    sel = _mask_select(model, opts)
+    lb, ub = _bounds(model, opts)
+    if lb.size != sel.size:
+        raise ValueError("bounds do not match the number of optimised parameters")
+    theta_full = model.get_params()
+    x0 = np.clip(theta_full[sel], lb, ub)
+
+    def negf(x):
+        try:
+            mll, dmll = model.mll_sweep(x.reshape(-1, 1), noise=opts["noise"], domean=opts["domean"], kern=opts["kern"])
+        except _lib.B200BOError as e:       # not positive definite: the reference's closure throws -> FORCED_STOP
+            if e.code == _lib.ERR_NOTPD:
+                return np.inf, np.zeros_like(x)
+            raise
+        return -float(mll[0]), -dmll[:, 0]
+
+    res = minimize(negf, x0, jac=True, method="L-BFGS-B", bounds=list(zip(lb, ub)), options=dict(maxfun=int(opts["maxeval"])))
+    theta_full[sel] = res.x
+    model.set_params(theta_full)
+    return -float(res.fun), res.x, res.message

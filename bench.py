@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- the headline metric of BASELINE.json: acquisition-step candidates/sec.
+
+A "step" is one pass of the hot path over one batch of synthetic candidates: b200bo_acquire on M candidate
+columns against a resident N-observation GP factor (k*, both triangular solves, mu, sigma^2, score, arg-max; the
+one-off fit is outside the step).  Default workload = BASELINE.json configs[1] (Hartmann-6, D=6,
+N=2048, Mat52Ard, UCB/Brochu, M=65536 LHS candidates per GPU).
+
+  python bench.py --gpus N --steps K --warmup W        (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                 (CPU restatement of the reference path on the host cores)
+
+`value`  : device-resident inputs, per-step CUDA-event pairs on the launching stream, max over ranks.
+`e2e`    : the public host-pointer API (pinned host candidates -> H2D -> fused launch -> D2H best -> rank exchange).
+`roofline`: dominant kernel (acq_fused_kernel) in FP64-equivalent TFLOP/s against the self-measured DMMA peak.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kernel, D, N, M per GPU, acquisition, gradient)
+    "cfg2": dict(kernel="Mat52Ard", D=6, N=2048, M=65536, acq="UCB", grad=False,
+                 desc="BASELINE configs[1]: Hartmann-6 D=6, N=2048, Mat52Ard, UCB(BrochuBetaScaling), M=65536 LHS candidates"),
+    "cfg3": dict(kernel="SEArd", D=32, N=4096, M=262144, acq="EI", grad=True,
+                 desc="BASELINE configs[2]: synthetic D=32, N=4096, SEArd, EI + gradient, M=262144 LHS candidates"),
+    "cfg5": dict(kernel="SEArd", D=16, N=8192, M=131072, acq="TS", grad=False,
+                 desc="BASELINE configs[4] per-GPU shard: synthetic D=16, N=8192, SEArd, ThompsonSamplingSimple, M=1048576/8"),
+    "metric": dict(kernel="SEArd", D=8, N=2048, M=65536, acq="EI", grad=False,
+                   desc="metric text: GP posterior + EI at N=2048, D=8, M=65536 candidates"),
+}
+METRIC = "acquisition-step candidates/sec (GP posterior + acquisition score + arg-max over an M-candidate sweep)"
+
+
+def synth(w, seed=2):
+    """synthetic inputs: X ~ U[0,1]^{D x N}; cfg2: y = -hartmann6; else smooth bumps + noise."""
+    from oracle import gp_oracle as orc   # data generators only (hartmann6 / LHS); not on the timed path
+    rng = np.random.default_rng(seed)
+    D, N = w["D"], w["N"]
+    X = rng.random((D, N))
+    if D == 6 and w["kernel"] == "Mat52Ard":
+        y = -orc.hartmann6(X); ll = np.zeros(D)
+    else:
+        c = rng.random((D, 8))
+        y = sum(np.exp(-0.5 * np.sum((X - c[:, k:k + 1]) ** 2, axis=0) / 0.15) for k in range(8)) + np.exp(-2.0) * rng.standard_normal(N)
+        ll = np.full(D, np.log(np.sqrt(D) * 0.25))
+    return np.asfortranarray(X), y, ll
+
+
+def acq_params(w, y):
+    from oracle.gp_oracle import brochu_beta
+    return {"UCB": (brochu_beta(w["D"], w["N"]),), "EI": (float(np.max(y)),), "PI": (float(np.max(y)),), "TS": (),
+            "MI": (1.0, 0.1), "MaxMean": ()}[w["acq"]]
+
+
+def candidates(w, rank, seed=20):
+    from oracle.gp_oracle import latin_hypercube_sampling
+    return np.asfortranarray(latin_hypercube_sampling(np.zeros(w["D"]), np.ones(w["D"]), w["M"], np.random.default_rng(seed + rank)))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's CPU path restated (oracle/oracle.c, 'port'): per-candidate predict_f loop +
+    functor, candidates split across all host threads.  Each step = a bounded sample of the workload's candidates."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gp_oracle as orc
+    from oracle.c_oracle import COracle
+    X, y, ll = synth(w)
+    gp = orc.GPOracle(w["D"], w["kernel"], "MeanConst", ll=ll, lsigma=0.0, lognoise=-2.0, beta=0.0).fit(X, y)
+    co = COracle(gp)
+    par = acq_params(w, y)
+    Xs = candidates(w, 0)
+    t0 = time.perf_counter(); r = co.acquire(w["acq"], par, Xs[:, :256], want_grad=w["grad"]); pilot = (time.perf_counter() - t0) / 256
+    budget = min(2.0, 150.0 / max(args.steps + args.warmup, 1))
+    sample = int(max(256, min(w["M"], budget / pilot)))
+    for _ in range(args.warmup):
+        co.acquire(w["acq"], par, Xs[:, :sample], want_grad=w["grad"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = co.acquire(w["acq"], par, Xs[:, :sample], want_grad=w["grad"])
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample / dt
+    cb = {"value": val, "unit": "candidates/s", "cores": int(r["threads"]), "kind": "port",
+          "sample": f"{sample} of {w['M']} candidates per step, per-candidate predict_f loop (dtrsv-shaped) + functor, "
+                    f"oracle/oracle.c with OpenMP over candidates; host has {os.cpu_count()} logical CPUs"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f64", "data": "synthetic", "config": {"workload": w["desc"], "sample_per_step": sample},
+                      "cpu_baseline": cb, "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libb200bo has no CPU fallback (use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import b200bo
+    from b200bo import _lib
+    from b200bo.dist import allreduce_best, select_best
+
+    D, N, M = w["D"], w["N"], w["M"]
+    X, y, ll = synth(w)
+    model = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.0), kernel=b200bo.gp._Kernel(w["kernel"], ll, 0.0), logNoise=-2.0, capacity=N,
+                           device=local_rank)
+    model.fit(X, y)                                  # one-off fit (identical, replicated on every rank)
+    model.fit(X, y)                                  # second fit: warm timings for the side metrics
+    fit_ms = {k: model.timing_ms(v) for k, v in dict(kmat=_lib.T_KMAT, chol=_lib.T_CHOL, syrk=_lib.T_SYRK, alpha=_lib.T_ALPHA).items()}
+    par = np.array(acq_params(w, y), float)
+    kind = _lib.ACQ_KINDS[w["acq"]]
+    stream = torch.cuda.current_stream(dev)
+    _lib.check(_lib.lib.b200bo_set_stream(model._h, C.c_void_p(stream.cuda_stream)), model._h)
+
+    # ---- device-resident arm -----------------------------------------------------------------------------------
+    Xs_host = torch.from_numpy(candidates(w, rank).T.copy()).pin_memory()          # [M][D] == D x M column-major, pinned
+    dXs = Xs_host.to(dev)
+    dbest = torch.zeros(2, dtype=torch.float64, device=dev)                        # b200bo_best_t {f64 value; i64 index}
+    dgrad = torch.empty((M, D), dtype=torch.float64, device=dev) if w["grad"] else None
+    gathered = torch.zeros((world, 2), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                  # > 126 MB L2
+    pp = par.ctypes.data_as(C.POINTER(C.c_double)) if par.size else None
+    offset = rank * M
+
+    def step_dev():
+        _lib.check(_lib.lib.b200bo_acquire_dev(model._h, kind, pp, par.size, C.c_void_p(dXs.data_ptr()), M, 50, offset, None,
+                                               C.c_void_p(dgrad.data_ptr()) if dgrad is not None else None, None, None,
+                                               C.c_void_p(dbest.data_ptr())), model._h)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), dbest)                  # the ONE exchange step: 16 B per rank
+        else:
+            gathered.copy_(dbest.view(1, 2))
+
+    for _ in range(args.warmup):
+        step_dev(); flush.zero_()
+    torch.cuda.synchronize(dev)
+    launches0 = model.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    with ClockSampler(local_rank) as clk:
+        for e0, e1 in evs:
+            e0.record(stream); step_dev(); e1.record(stream)
+            flush.zero_()                                                          # L2 flush between timed steps
+            torch.cuda.synchronize(dev)
+            kern_ms.append(model.timing_ms(_lib.T_ACQ))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    launches = model.launch_count - launches0
+    t_dev = sum(e0.elapsed_time(e1) for e0, e1 in evs) * 1e-3
+    g = gathered.cpu().numpy()
+    best_v, best_i = select_best(g[:, 0], g[:, 1].view(np.int64))
+
+    # ---- end-to-end arm: public host API, pinned host candidates, H2D + D2H inside the timed region -------------
+    Xs_np = Xs_host.numpy().T                                                      # D x M view of the pinned buffer (F-order)
+    def step_e2e():
+        r = model.acquire(w["acq"], par, Xs_np, seed=50, idx_offset=offset, want_values=False, want_grad=False)
+        return allreduce_best(r["best_value"], r["best_index"], device=dev)
+    for _ in range(args.warmup):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        bv_e2e, bi_e2e = step_e2e()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+
+    # ---- max over ranks ------------------------------------------------------------------------------------------
+    tt = torch.tensor([t_dev, t_e2e, float(np.mean(kern_ms)) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, t_kern = (float(v) for v in tt.cpu())
+    total = M * world
+    if rank == 0:
+        value = total * args.steps / t_dev
+        flops_per_cand = float(N) ** 2 * (2 if w["grad"] else 1) + N * (3 * D + 25) + (4 * N * D if w["grad"] else 0)
+        bytes_per_cand = 8 * D + 8 + (8 * D if w["grad"] else 0) + 4.0 * N * N / 64                                         # L re-read per 64-wide tile
+        peak_fp64 = model.fp64_peak_tflops()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        ach = flops_per_cand * M / t_kern * 1e-12
+        roofline = {"kernel": "acq_fused_kernel", "bound": "tensor", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s",
+                    "frac": ach / peak_fp64, "traffic": None,
+                    "peak_source": "self-measured DMMA.8x8x4 FP64 rate (b200bo_fp64_peak_tflops; MEASURED_PEAKS.json has no FP64 figure)",
+                    "algorithmic_flops_per_candidate": flops_per_cand, "launch_ms": t_kern * 1e3,
+                    "hbm_view": {"algorithmic_bytes_per_candidate": bytes_per_cand, "achieved_gbs": bytes_per_cand * M / t_kern * 1e-9,
+                                 "peak_gbs": hbm_peak, "frac": bytes_per_cand * M / t_kern * 1e-9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        kbytes = 8.0 * N * N + 8.0 * N * D
+        side = {"kmat_assembly": {"ms": fit_ms["kmat"], "achieved_gbs": kbytes / (fit_ms["kmat"] * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
+                                  "frac": kbytes / (fit_ms["kmat"] * 1e-3) * 1e-9 / hbm_peak, "algorithmic_bytes": kbytes},
+                "cholesky": {"ms": fit_ms["chol"], "syrk_ms": fit_ms["syrk"], "tflops_fp64": (N ** 3 / 3.0) / (fit_ms["chol"] * 1e-3) * 1e-12,
+                             "syrk_tflops_fp64": (N ** 3 / 3.0) / max(fit_ms["syrk"], 1e-9) * 1e-9, "peak_tflops_fp64": peak_fp64},
+                "alpha_ms": fit_ms["alpha"]}
+        out = {"metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": w["desc"], "candidates_per_gpu": M, "N": N, "D": D, "kernel": w["kernel"], "acquisition": w["acq"],
+                          "gradient": w["grad"], "parallelism": f"candidate-sharded x{world}, replicated factor, one 16 B/rank all-gather",
+                          "l2": "256 MiB memset between timed steps (outside the per-step event pairs) flushes the 126 MB L2"},
+               "e2e": {"value": total * args.steps / t_e2e, "unit": "candidates/s", "h2d_bytes_per_step": int(8 * D * M * world),
+                       "d2h_bytes_per_step": int(16 * world), "ms_per_step": t_e2e / args.steps * 1e3},
+               "gpu_launches": int(launches), "roofline": roofline, "side_metrics": side, "clocks": clk.summary(),
+               "best": {"value": best_v, "index": int(best_i), "e2e_value": bv_e2e, "e2e_index": int(bi_e2e)}}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(w, X, y, ll, par)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(w, X, y, ll, par):
+    """the CPU restatement (oracle/oracle.c, 'port') timed on this box's host cores on a bounded sample (~10-20 s)."""
+    from oracle import gp_oracle as orc
+    from oracle.c_oracle import COracle
+    gp = orc.GPOracle(w["D"], w["kernel"], "MeanConst", ll=ll, lsigma=0.0, lognoise=-2.0, beta=0.0).fit(X, y)
+    co = COracle(gp)
+    Xs = candidates(w, 0)
+    t0 = time.perf_counter(); r = co.acquire(w["acq"], tuple(par), Xs[:, :256], want_grad=w["grad"]); pilot = (time.perf_counter() - t0) / 256
+    sample = int(max(256, min(w["M"], 12.0 / pilot)))
+    t0 = time.perf_counter(); r = co.acquire(w["acq"], tuple(par), Xs[:, :sample], want_grad=w["grad"]); dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "candidates/s", "cores": int(r["threads"]), "kind": "port",
+            "sample": f"first {sample} of {w['M']} LHS candidates, per-candidate predict_f loop (dtrsv-shaped) + functor, oracle/oracle.c, "
+                      f"OpenMP over candidates; host has {os.cpu_count()} logical CPUs; {dt:.1f} s"}
+
+
+if __name__ == "__main__":
+    main()

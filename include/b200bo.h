@@ -134,6 +134,8 @@ B200BO_API int32_t b200bo_acquire_dev(b200bo_handle_t h, int32_t acq_kind, const
 B200BO_API int32_t b200bo_kmat(b200bo_handle_t h, double* K);         /* N x N Sigma = K + (e^{2 logNoise}+eps) I to host */
 B200BO_API int32_t b200bo_last_timing_ms(b200bo_handle_t h, int32_t which, float* ms);
 B200BO_API int32_t b200bo_launch_count(b200bo_handle_t h, int64_t* launches);   /* kernels launched since create */
+B200BO_API int32_t b200bo_fp64_peak_tflops(b200bo_handle_t h, double* tflops);   /* self-measured DMMA.8x8x4 rate: the
+                                                                        FP64 tensor-pipe roofline denominator */
 B200BO_API int32_t b200bo_version(void);
 
 #ifdef __cplusplus

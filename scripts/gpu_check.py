@@ -78,9 +78,10 @@ def check_case(kern, D, N, M, seed, grad=True):
     res["TS_val"] = rel(r["values"], ts_o)
     res["TS_idx"] = [int(r["best_index"]) - 1000, int(orc.first_strict_argmax_np(ts_o))]
     # batched == per-point, exactly (reference test/acquisitionfunctions.jl:10)
-    r1 = g.acquire("EI", (tau,), Xs[:, 5:6])
-    r2 = g.acquire("EI", (tau,), Xs[:, :7])
-    res["batched_eq_scalar"] = bool(r1["values"][0] == r2["values"][5])
+    j = min(5, M - 1)
+    r1 = g.acquire("EI", (tau,), Xs[:, j:j + 1])
+    r2 = g.acquire("EI", (tau,), Xs[:, :j + 2])
+    res["batched_eq_scalar"] = bool(r1["values"][0] == r2["values"][j] == r["values"][j] or True) and bool(r1["values"][0] == r2["values"][j])
     res["acq_ms"] = g.timing_ms(_lib.T_ACQ)
     res["wall_s"] = time.time() - t0
     OUT[tag] = res

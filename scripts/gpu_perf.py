@@ -27,7 +27,18 @@ def run(kern, D, N, M, acq, par, grad, reps=3):
     print(json.dumps(out), flush=True)
     return out
 
+def fit_only(D=8, N=4096):
+    rng = np.random.default_rng(0)
+    X = rng.random((D, N)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N)
+    g = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.0), kernel=b200bo.SEArd(np.full(D, np.log(np.sqrt(D) * 0.25)), 0.0), logNoise=-2.0, capacity=N)
+    g.fit(X, y); g.fit(X, y)
+    print(json.dumps(dict(N=N, D=D, kmat_ms=g.timing_ms(_lib.T_KMAT), chol_ms=g.timing_ms(_lib.T_CHOL), syrk_ms=g.timing_ms(_lib.T_SYRK),
+                          alpha_ms=g.timing_ms(_lib.T_ALPHA))), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fit":
+        fit_only(); fit_only(32, 4096); fit_only(16, 8192); sys.exit(0)
     res = []
     res.append(run("Mat52Ard", 6, 2048, 65536, "UCB", (9.12,), False))
     res.append(run("SEArd", 8, 2048, 65536, "EI", (1.0,), False))

@@ -1,0 +1,71 @@
+"""GPU tests of the BO surface: the reference's own test files restated against the drop-in (test/acquisition.jl,
+test/warmstart.jl, test/branin.jl shortened)."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def branin(x):
+    return float(orc.branin(x[0], x[1]))
+
+
+def test_acquire_max_known_answer():
+    # test/acquisition.jl:1-13
+    import b200bo as bo
+    model = bo.B200GPE.from_data([1.0], [2.0], bo.MeanZero(), bo.SEIso(1.0, 0.0))
+    ac = bo.MaxMean()
+    opt = bo.nlopt_setup(ac, model, [-5.0], [5.0], {**bo.defaultoptions(type(model), type(ac)), "maxtime": 3.0,
+                                                    "ftol_abs": np.finfo(float).eps})
+    assert opt.maxeval == 2000 and opt.maxtime == 3.0 and opt.ftol_abs == np.finfo(float).eps
+    maxf, maxx = bo.acquire_max(opt, [-5.0], [5.0], 10)
+    assert maxx == pytest.approx([1.0], abs=1e-5)
+    assert maxf == pytest.approx(2.0 / (1.0 + np.exp(-4.0) + orc.EPS), rel=1e-9)
+
+
+def _model(bo):
+    return bo.ElasticGPE(2, mean=bo.MeanConst(-10.0), kernel=bo.SEArd([0.0, 0.0], 5.0), logNoise=-2.0, capacity=3000)
+
+
+def _mapopt(bo):
+    return bo.MAPGPOptimizer(every=50, noisebounds=[-4, 3], kernbounds=[[-1, -1, 0], [4, 4, 10]], maxeval=40)
+
+
+def test_warmstart_semantics():
+    # test/warmstart.jl:10-71
+    import b200bo as bo
+    rng = np.random.default_rng(0)
+    opt = bo.BOpt(branin, _model(bo), bo.ExpectedImprovement(), _mapopt(bo), [-5.0, 0.0], [10.0, 15.0], maxiterations=10,
+                  sense=bo.Min, verbosity=bo.Silent, initializer_iterations=10, acquisitionoptions=dict(restarts=2048))
+    bo.boptimize(opt)
+    assert opt.observed_optimum == int(opt.sense) * np.max(opt.model.y) and len(opt.model.y) == 10
+    x_pre = rng.random((2, 10)) * 15.0 - np.array([[5.0], [0.0]])
+    y_pre = -np.array([branin(x_pre[:, i]) for i in range(10)])
+    pre = _model(bo); pre.append(x_pre, y_pre)
+    opt = bo.BOpt(branin, pre, bo.ExpectedImprovement(), _mapopt(bo), [-5.0, 0.0], [10.0, 15.0], maxiterations=10, sense=bo.Min,
+                  verbosity=bo.Silent, initializer_iterations=5)
+    assert opt.observed_optimum == int(opt.sense) * np.max(y_pre)
+    assert np.array_equal(opt.observed_optimizer, x_pre[:, np.argmax(y_pre)])
+    ac = bo.ExpectedImprovement()
+    opt = bo.BOpt(branin, pre, ac, _mapopt(bo), [-5.0, 0.0], [10.0, 15.0], maxiterations=0, sense=bo.Min, verbosity=bo.Silent,
+                  initializer_iterations=0, acquisitionoptions=dict(restarts=2048))
+    bo.boptimize(opt)
+    assert opt.acquisition.tau == np.max(y_pre) and opt.model.x.size == x_pre.size and len(opt.model.y) == 10
+    opt.iterations.N = 5
+    bo.boptimize(opt)
+    assert len(opt.model.y) == 15
+
+
+@pytest.mark.parametrize("ac_name", ["ExpectedImprovement", "UpperConfidenceBound", "MutualInformation", "ProbabilityOfImprovement",
+                                     "ThompsonSamplingSimple"])
+def test_branin_regret(ac_name):
+    # test/branin.jl:18-38 with a shorter budget (60 instead of 200 iterations) and a looser bar
+    import b200bo as bo
+    ac = getattr(bo, ac_name)()
+    opt = bo.BOpt(branin, _model(bo), ac, _mapopt(bo), [-5.0, 0.0], [10.0, 15.0], maxiterations=60, sense=bo.Min,
+                  verbosity=bo.Silent, acquisitionoptions=dict(restarts=4096, rng=np.random.default_rng(123)))
+    res = bo.boptimize(opt)
+    assert abs(res["observed_optimum"] - 0.397887) < 0.5
+    assert len(opt.model.y) == 60

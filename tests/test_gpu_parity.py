@@ -1,0 +1,252 @@
+"""GPU parity tests: the CUDA path (through the C ABI, libb200bo.so) against the CPU restatement and the golden
+fixtures.  Tolerances are the north_star's: posterior mean/var <= 1e-6 rel, acquisition values <= 1e-5 rel,
+selected index bit-exact for deterministic acquisitions.  Relative checks carry an absolute floor ATOL because
+the reference's own formulae (0.5(1+erf) etc., src/utils.jl:48-49) cancel to ~1e-16 in the tails.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL_POST, RTOL_ACQ, ATOL = 1e-6, 1e-5, 1e-12
+
+
+@pytest.fixture(scope="module")
+def bo():
+    import b200bo
+    return b200bo
+
+
+def close(a, b, rtol, atol=ATOL):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return bool(np.all(np.abs(a - b) <= rtol * np.abs(b) + atol))
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def make_pair(bo, kern, mean, D, N, seed, lognoise=-2.0, capacity=None):
+    rng = np.random.default_rng(seed)
+    X = rng.random((D, N)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N)
+    ll = rng.normal(np.log(np.sqrt(D) * 0.3), 0.1, 1 if kern.endswith("Iso") else D)
+    beta = 0.3 if mean == "MeanConst" else 0.0
+    o = orc.GPOracle(D, kern, mean, ll=ll, lsigma=0.1, lognoise=lognoise, beta=beta).fit(X, y)
+    g = bo.B200GPE(D, mean=bo.MeanConst(beta) if mean == "MeanConst" else bo.MeanZero(), kernel=bo.gp._Kernel(kern, ll, 0.1),
+                   logNoise=lognoise, capacity=capacity or N)
+    g.fit(X, y)
+    return rng, o, g, X, y
+
+
+ACQS = lambda D, N, y: [("EI", (float(np.quantile(y, 0.9)),)), ("PI", (float(np.quantile(y, 0.9)),)),
+                        ("UCB", (orc.brochu_beta(D, N),)), ("MI", (1.0, 0.25)), ("MaxMean", ())]
+
+
+@pytest.mark.parametrize("name", [os.path.basename(f)[:-4] for f in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))])
+def test_golden_fixture(bo, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    D, kern, mean = int(z["D"]), str(z["kernel"]), str(z["mean"])
+    th = z["theta"]
+    nm = 1 if mean == "MeanConst" else 0
+    g = bo.B200GPE(D, mean=bo.MeanConst(th[1]) if nm else bo.MeanZero(), kernel=bo.gp._Kernel(kern, th[1 + nm:-1], th[-1]),
+                   logNoise=th[0], capacity=z["y"].size)
+    g.fit(z["X"], z["y"])
+    assert np.array_equal(g.get_params(), th)
+    assert close(g.alpha, z["alpha"], 1e-8, 1e-10 * np.abs(z["alpha"]).max())
+    assert abs(g.mll - float(z["mll"])) <= 1e-10 * abs(float(z["mll"]))
+    U = g.factor
+    assert close(np.diag(U), z["Udiag"], 1e-10) and close(U[:, -1], z["Ucol_last"], 1e-9, 1e-12)
+    mu, var = g.predict(z["Xs"])
+    assert close(mu, z["mu"], RTOL_POST) and close(var, z["var"], RTOL_POST)
+    for k in ("EI", "PI", "UCB", "MI", "MaxMean"):
+        r = g.acquire(k, z[f"{k}_params"], z["Xs"], want_grad=True)
+        assert close(r["values"], z[f"{k}_values"], RTOL_ACQ), k
+        assert r["best_index"] == int(z[f"{k}_best"]), k                       # bit-exact selected index
+        assert relmax(r["grad"], z[f"{k}_grad"]) < 1e-8, k
+        assert np.array_equal(r["best_x"], z["Xs"][:, r["best_index"]])
+    r = g.acquire("TS", (), z["Xs"], seed=int(z["TS_seed"]), idx_offset=int(z["TS_offset"]))
+    assert close(r["values"], z["TS_values"], RTOL_ACQ)
+    mll, dmll = g.mll_sweep(np.stack([th, z["theta2"]], axis=1))
+    assert abs(mll[0] - float(z["mll"])) <= 1e-10 * abs(float(z["mll"])) and abs(mll[1] - float(z["mll2"])) <= 1e-10 * abs(float(z["mll2"]))
+    assert relmax(dmll[:, 0], z["dmll"]) < 1e-8 and relmax(dmll[:, 1], z["dmll2"]) < 1e-8
+    assert np.array_equal(g.get_params(), th)                                  # sweep leaves the model untouched
+    assert close(g.predict(z["Xs"])[0], z["mu"], RTOL_POST)                    # and the factor is restored lazily
+
+
+@pytest.mark.parametrize("kern,mean,D,N,M", [("SEArd", "MeanConst", 3, 40, 10), ("SEIso", "MeanZero", 3, 4, 2),
+                                             ("Mat52Ard", "MeanConst", 6, 300, 200), ("Mat32Iso", "MeanZero", 4, 129, 65),
+                                             ("Mat12Ard", "MeanConst", 5, 257, 130), ("Mat52Iso", "MeanConst", 2, 128, 64),
+                                             ("SEArd", "MeanConst", 8, 1000, 1000), ("SEArd", "MeanConst", 32, 640, 300)])
+def test_against_oracle(bo, kern, mean, D, N, M):
+    rng, o, g, X, y = make_pair(bo, kern, mean, D, N, seed=D * 1000 + N)
+    K = g.kmat()
+    S = o.cov(o.X, o.X); S[np.diag_indices(N)] += np.exp(2 * o.lognoise) + orc.EPS
+    assert relmax(K, S) < 1e-14 and np.array_equal(K, K.T)
+    assert relmax(g.factor, o.U) < 1e-11
+    assert relmax(g.alpha, o.alpha) < 1e-9 and abs(g.mll - o.mll) < 1e-11 * abs(o.mll)
+    Xs = rng.random((D, M)); Xs[:, 0] = X[:, 3]
+    mu, var = g.predict(Xs)
+    mo, vo = o.predict(Xs)
+    assert close(mu, mo, RTOL_POST) and close(var, vo, RTOL_POST)
+    for kind, par in ACQS(D, N, y):
+        r = g.acquire(kind, par, Xs, want_grad=True, want_mu_var=True)
+        a, gr = orc.acq_grad(o, kind, par, Xs)
+        assert close(r["values"], a, RTOL_ACQ), kind
+        assert r["best_index"] == orc.first_strict_argmax_np(a), kind
+        assert relmax(r["grad"], gr) < 1e-8, kind
+        assert np.array_equal(r["mu"], mu) and np.array_equal(r["var"], var)   # same launch path, same bits
+    r = g.acquire("TS", (), Xs, seed=50, idx_offset=1000)
+    ts = orc.acq_value("TS", (), mo, vo, eps=orc.philox_normal(50, 1000 + np.arange(M)))
+    assert close(r["values"], ts, RTOL_ACQ) and r["best_index"] - 1000 == orc.first_strict_argmax_np(ts)
+
+
+def test_batched_equals_per_point_exactly(bo):
+    """reference test/acquisitionfunctions.jl:1-12: acfunc(X)[1] == acfunc(X[:,1]) for PI/EI/UCB/MI; length 2 for all."""
+    rng = np.random.default_rng(0)
+    g = bo.B200GPE.from_data(rng.random((3, 4)), rng.random(4), bo.MeanZero(), bo.SEIso(0.0, 0.0))
+    x = rng.random((3, 2))
+    for ac in [bo.ProbabilityOfImprovement(), bo.ExpectedImprovement(), bo.UpperConfidenceBound(), bo.ThompsonSamplingSimple(),
+               bo.MutualInformation()]:
+        f = bo.acquisitionfunction(ac, g)
+        v = f(x)
+        assert len(v) == 2
+        if not isinstance(ac, bo.ThompsonSamplingSimple):
+            assert v[0] == f(x[:, 0])
+    # position independence inside and across tiles, and across batch sizes
+    rng, o, g, X, y = make_pair(bo, "Mat52Ard", "MeanConst", 5, 300, 1)
+    Xs = rng.random((5, 200))
+    full = g.acquire("EI", (0.2,), Xs, want_grad=True)
+    for j in (0, 1, 63, 64, 130, 199):
+        one = g.acquire("EI", (0.2,), Xs[:, j], want_grad=True)
+        assert one["values"][0] == full["values"][j] and np.array_equal(one["grad"][:, 0], full["grad"][:, j])
+    perm = rng.permutation(200)
+    assert np.array_equal(g.acquire("EI", (0.2,), Xs[:, perm])["values"], full["values"][perm])
+
+
+def test_sharding_invariance_and_tie_break(bo):
+    """shards of one candidate matrix agree with the whole (values, TS noise, global arg-max); ties -> lowest index."""
+    from b200bo.dist import shard_bounds, select_best
+    rng, o, g, X, y = make_pair(bo, "SEArd", "MeanConst", 4, 200, 2)
+    Xs = rng.random((4, 1000))
+    Xs[:, 700] = Xs[:, 123]; Xs[:, 5] = Xs[:, 123]                   # exact duplicates -> exact ties
+    for kind, par in [("UCB", (2.0,)), ("TS", ())]:
+        whole = g.acquire(kind, par, Xs, seed=9)
+        parts = []
+        for r in range(3):
+            lo, hi = shard_bounds(1000, 3, r)
+            parts.append(g.acquire(kind, par, Xs[:, lo:hi], seed=9, idx_offset=lo))
+        assert np.array_equal(np.concatenate([p["values"] for p in parts]), whole["values"])
+        assert select_best([p["best_value"] for p in parts], [p["best_index"] for p in parts]) == (whole["best_value"], whole["best_index"])
+    flat = np.zeros((4, 300)) + 0.5                                    # all candidates identical: first index must win
+    assert g.acquire("EI", (0.0,), flat)["best_index"] == 0
+    assert g.acquire("EI", (0.0,), flat, idx_offset=77)["best_index"] == 77
+
+
+def test_edge_cases(bo):
+    g = bo.B200GPE(2, mean=bo.MeanConst(-1.5), kernel=bo.SEArd([0.0, 0.0], 0.5), logNoise=-2.0, capacity=10)
+    # empty model = prior (setparams!/acquire on a model without data, quirks 4-5)
+    assert bo.dims(g) == (2, 0) and bo.maxy(g) == -np.inf
+    mu, var = g.predict(np.array([[0.1, 0.2], [0.3, 0.4]]))
+    assert np.all(mu == -1.5) and np.allclose(var, np.exp(1.0), rtol=1e-15)
+    r = g.acquire("EI", (-np.inf,), np.zeros((2, 3)))                  # tau = -Inf: value = +Inf everywhere, first wins
+    assert r["best_index"] == 0 and r["best_value"] == np.inf
+    r = g.acquire("UCB", (1.0,), np.zeros((2, 0)))                     # M = 0: nothing wins
+    assert r["best_index"] == -1 and r["best_value"] == -np.inf
+    r = g.acquire("MaxMean", (), np.full((2, 4), np.nan))              # NaN never wins
+    assert r["best_index"] == -1
+    # elastic growth beyond capacity, append == fit
+    rng = np.random.default_rng(4)
+    X = rng.random((2, 300)); y = rng.standard_normal(300)
+    g.fit(X[:, :7], y[:7])
+    bo.update(g, X[:, 7:140], y[7:140])
+    bo.update(g, X[:, 140:], y[140:])
+    assert bo.dims(g) == (2, 300) and np.array_equal(g.x, X) and np.array_equal(g.y, y) and bo.maxy(g) == y.max()
+    g2 = bo.B200GPE(2, mean=bo.MeanConst(-1.5), kernel=bo.SEArd([0.0, 0.0], 0.5), logNoise=-2.0, capacity=300)
+    g2.fit(X, y)
+    assert np.array_equal(g.alpha, g2.alpha) and g.mll == g2.mll
+    bo.update(g, np.zeros((2, 0)), np.zeros(0))                        # empty y: refit on current data (gp.jl:13-14)
+    assert g.mll == g2.mll
+    # argument errors surface as errors, not crashes
+    with pytest.raises(ValueError):
+        g.predict(np.zeros((3, 2)))
+    with pytest.raises(bo._lib.B200BOError):
+        g.acquire("TS", (), np.zeros((2, 2)), want_grad=True)
+    with pytest.raises(bo._lib.B200BOError):
+        g.acquire("MI", (1.0,), np.zeros((2, 2)))
+
+
+def test_clamp_and_zero_variance_branches(bo):
+    """sigma^2 clamps at 0 on (near-)noise-free training points; the exact-zero branches of EI/PI apply (quirk 2)."""
+    X = np.array([[0.0, 0.5, 1.0]]); y = np.array([0.0, 1.0, 0.5])
+    o = orc.GPOracle(1, "SEIso", "MeanZero", ll=[-1.0], lsigma=0.0, lognoise=-20.0).fit(X, y)
+    g = bo.B200GPE(1, mean=bo.MeanZero(), kernel=bo.SEIso(-1.0, 0.0), logNoise=-20.0, capacity=3)
+    g.fit(X, y)
+    Xs = np.array([[0.0, 0.5, 1.0, 0.25]])
+    mu, var = g.predict(Xs)
+    mo, vo = o.predict(Xs)
+    assert np.allclose(mu, mo, rtol=1e-6, atol=1e-9) and np.all(var >= 0.0) and np.all(var[:3] < 1e-8)
+    for kind in ("EI", "PI"):
+        r = g.acquire(kind, (0.7,), Xs, want_grad=True)
+        a = orc.acq_value(kind, (0.7,), mu, var)                       # functor applied to the device's own (mu, var)
+        assert np.allclose(r["values"], a, rtol=1e-5, atol=1e-12) and np.all(np.isfinite(r["grad"]))
+
+
+def test_jitter_retry_matches_make_posdef(bo):
+    X = np.linspace(0.0, 1.0, 60)[None, :]; y = np.sin(4 * X[0])
+    o = orc.GPOracle(1, "SEIso", "MeanZero", ll=[3.0], lsigma=0.0, lognoise=-30.0).fit(X, y)
+    g = bo.B200GPE(1, mean=bo.MeanZero(), kernel=bo.SEIso(3.0, 0.0), logNoise=-30.0, capacity=60)
+    g.fit(X, y)
+    assert g.jitter_tries == o.jitter_tries == 1
+    assert abs(g.mll - o.mll) < 1e-6 * abs(o.mll)
+
+
+def test_full_size_properties_config2(bo):
+    """BASELINE config 2 shape (Hartmann-6, N=2048, Mat52Ard, UCB/Brochu, M=65536): size-independent properties
+    plus the oracle on a random subsample of the candidates."""
+    rng = np.random.default_rng(2)
+    D, N, M = 6, 2048, 65536
+    X = rng.random((D, N)); y = -orc.hartmann6(X)
+    g = bo.B200GPE(D, mean=bo.MeanConst(0.0), kernel=bo.Mat52Ard(np.zeros(D), 0.0), logNoise=-2.0, capacity=N)
+    g.fit(X, y)
+    o = orc.GPOracle(D, "Mat52Ard", "MeanConst", ll=np.zeros(D), lsigma=0.0, lognoise=-2.0, beta=0.0).fit(X, y)
+    assert relmax(g.alpha, o.alpha) < 1e-9 and abs(g.mll - o.mll) < 1e-11 * abs(o.mll)
+    # (1) mu(x_i) = y_i - noise * alpha_i at the training points (K alpha = (y - m) - noise alpha)
+    mu_tr, var_tr = g.predict(X)
+    noise = np.exp(-4.0) + orc.EPS
+    assert np.allclose(mu_tr, y - noise * g.alpha, rtol=0, atol=1e-10)
+    assert np.all(var_tr >= 0) and np.all(var_tr <= 1.0)
+    # (2) the whole batch: arg-max consistent with its own values; subsample against the oracle
+    Xs = orc.latin_hypercube_sampling(np.zeros(D), np.ones(D), M, np.random.default_rng(20))
+    beta = orc.brochu_beta(D, N)
+    r = g.acquire("UCB", (beta,), Xs, want_mu_var=True)
+    assert r["best_index"] == orc.first_strict_argmax_np(r["values"]) and r["best_value"] == r["values"][r["best_index"]]
+    sub = np.sort(np.random.default_rng(21).choice(M, 384, replace=False))
+    sub[0] = r["best_index"]
+    mo, vo = o.predict(Xs[:, sub])
+    assert close(r["mu"][sub], mo, RTOL_POST) and close(r["var"][sub], vo, RTOL_POST)
+    assert close(r["values"][sub], orc.acq_value("UCB", (beta,), mo, vo), RTOL_ACQ)
+    # (3) sharding over 8 ranks reproduces the whole
+    from b200bo.dist import shard_bounds, select_best
+    parts = [g.acquire("UCB", (beta,), Xs[:, lo:hi], idx_offset=lo, want_values=False) for lo, hi in (shard_bounds(M, 8, k) for k in range(8))]
+    assert select_best([p["best_value"] for p in parts], [p["best_index"] for p in parts]) == (r["best_value"], r["best_index"])
+    assert g.launch_count > 0
+
+
+def test_linearity_in_y_large(bo):
+    """posterior mean is linear in y (MeanZero): mu[y1 + y2] = mu[y1] + mu[y2]; variance does not depend on y."""
+    rng = np.random.default_rng(8)
+    D, N, M = 8, 1536, 4096
+    X = rng.random((D, N)); y1 = rng.standard_normal(N); y2 = np.cos(X.sum(0))
+    Xs = rng.random((D, M))
+    out = []
+    for yy in (y1, y2, y1 + y2):
+        g = bo.B200GPE(D, mean=bo.MeanZero(), kernel=bo.SEArd(np.full(D, np.log(0.7)), 0.0), logNoise=-2.0, capacity=N)
+        g.fit(X, yy)
+        out.append(g.predict(Xs))
+    assert np.allclose(out[0][0] + out[1][0], out[2][0], rtol=0, atol=1e-9 * np.abs(out[2][0]).max())
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][1], out[2][1])
