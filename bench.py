@@ -183,7 +183,8 @@ def main():
     fit_ms = {k: model.timing_ms(v) for k, v in dict(kmat=_lib.T_KMAT, chol=_lib.T_CHOL, syrk=_lib.T_SYRK, alpha=_lib.T_ALPHA).items()}
     par = np.array(acq_params(w, y), float)
     kind = _lib.ACQ_KINDS[w["acq"]]
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)                 # a real (non-default) stream shared by torch, NCCL ordering and the library
+    torch.cuda.set_stream(stream)
     _lib.check(_lib.lib.b200bo_set_stream(model._h, C.c_void_p(stream.cuda_stream)), model._h)
 
     # ---- device-resident arm -----------------------------------------------------------------------------------

@@ -157,8 +157,6 @@ def test_edge_cases(bo):
     assert r["best_index"] == 0 and r["best_value"] == np.inf
     r = g.acquire("UCB", (1.0,), np.zeros((2, 0)))                     # M = 0: nothing wins
     assert r["best_index"] == -1 and r["best_value"] == -np.inf
-    r = g.acquire("MaxMean", (), np.full((2, 4), np.nan))              # NaN never wins
-    assert r["best_index"] == -1
     # elastic growth beyond capacity, append == fit
     rng = np.random.default_rng(4)
     X = rng.random((2, 300)); y = rng.standard_normal(300)
@@ -171,6 +169,11 @@ def test_edge_cases(bo):
     assert np.array_equal(g.alpha, g2.alpha) and g.mll == g2.mll
     bo.update(g, np.zeros((2, 0)), np.zeros(0))                        # empty y: refit on current data (gp.jl:13-14)
     assert g.mll == g2.mll
+    r = g.acquire("MaxMean", (), np.full((2, 4), np.nan))              # NaN never wins (acquisition.jl:62 `f > maxf`)
+    assert r["best_index"] == -1 and r["best_value"] == -np.inf
+    nan1 = rng.random((2, 5)); nan1[0, 1] = np.nan
+    r = g.acquire("UCB", (1.0,), nan1)
+    assert r["best_index"] in (0, 2, 3, 4) and np.isnan(r["values"][1]) and r["best_index"] == int(np.nanargmax(r["values"]))
     # argument errors surface as errors, not crashes
     with pytest.raises(ValueError):
         g.predict(np.zeros((3, 2)))
