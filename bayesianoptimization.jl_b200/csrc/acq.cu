@@ -12,12 +12,12 @@
 // k(X_i, x*) tiles are generated on the fly and never stored; V/W panels live in a per-CTA scratch that stays
 // in L2.  Every candidate's sums are taken in a fixed order that does not depend on its column position, so a
 // batched call equals the per-point call bit for bit (reference test/acquisitionfunctions.jl:10).
-#include "common.cuh"
+#include "tma.cuh"
 #include "handle.h"
 
 namespace b200bo {
 
-constexpr int AQ_BM = NB, AQ_BN = TILE_N, AQ_THREADS = 256, AQ_STAGES = 3;
+constexpr int AQ_BM = NB, AQ_BN = TILE_N, AQ_THREADS = 384, AQ_STAGES = 4;
 constexpr int RB_STRIDE = NB;   // resident R/G tile [TILE_N][NB], swizzled
 
 struct AcqArgs {
@@ -105,12 +105,35 @@ __device__ __forceinline__ bool better(double v, int64_t i, double bv, int64_t b
 
 // MODE 0: acquisition step.  MODE 1: the right-hand sides are the columns of I (candidate n of tile t is e_{64 t + n}),
 // scores are skipped and the backward pass always runs, leaving Sigma^-1 in the panels (used by the MAP gradient).
+//
+// Warp roles (384 threads = 3 warpgroups): warps 0-7 are MMA/epilogue consumers (setmaxnreg 240), warp 8 lane 0 is the
+// TMA producer (the rest of warpgroup 2 gives its registers away and exits).  Operand chunks (128 or 64 rows x 16 k)
+// travel global -> smem by cp.async.bulk.tensor through a AQ_STAGES-deep full/empty mbarrier ring; the consumers never
+// execute a CTA-wide barrier inside a contraction.  `vready` orders the consumers' generic-proxy panel writes before the
+// producer's async-proxy reads of the same block.
+struct AcqMaps { CUtensorMap L, V, Linv, LinvT; };
+
+constexpr int AQ_CONSUMERS = 256;
+constexpr uint32_t A_BYTES = AQ_BM * KC * sizeof(double), B_BYTES = AQ_BN * KC * sizeof(double);
+constexpr int STAGE_DBL = (AQ_BM + AQ_BN) * KC;
+constexpr int CH = NB / KC;   // chunks per 128-wide block
+
+__device__ __forceinline__ void produce_chunk(PipeState& p, double* stages, uint64_t* full, uint64_t* empty, const CUtensorMap* mapA, int ak,
+                                              int arow, const CUtensorMap* mapB, int bk, int brow) {
+  mbar_wait(&empty[p.s], p.ph ^ 1u);
+  double* st = stages + p.s * STAGE_DBL;
+  mbar_arrive_expect_tx(&full[p.s], mapB ? A_BYTES + B_BYTES : A_BYTES);
+  tma_load_2d(st, mapA, &full[p.s], ak, arow);
+  if (mapB) tma_load_2d(st + AQ_BM * KC, mapB, &full[p.s], bk, brow);
+  p.next<AQ_STAGES>();
+}
+
 template <int FAM, int MODE>
-__global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs a) {
-  extern __shared__ __align__(16) double sm[];
+__global__ void __launch_bounds__(384, 1) acq_fused_kernel(const AcqArgs a, const __grid_constant__ AcqMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  double* stages = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int D = a.D;
-  double* stages = sm;                                              // AQ_STAGES x (128 + 64) x 16
-  double* Rb = stages + AQ_STAGES * (AQ_BM + AQ_BN) * KC;           // [64][128] swizzled
+  double* Rb = stages + AQ_STAGES * STAGE_DBL;                       // [64][128] swizzled (1024-B aligned)
   double* zx = Rb + TILE_N * RB_STRIDE;                             // [D][128]
   double* zc = zx + D * NB;                                         // [D][64]
   double* alb = zc + D * TILE_N;                                    // [128]
@@ -121,49 +144,124 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
   double* c_as2 = c_amu + TILE_N;
   double* c_val = c_as2 + TILE_N;
   double* ie = c_val + TILE_N;                                      // [D] inverse length-scales
+  uint64_t* full = reinterpret_cast<uint64_t*>(ie + ((D + 1) & ~1));
+  uint64_t* empty = full + AQ_STAGES;
+  uint64_t* vready = empty + AQ_STAGES;
   __shared__ double best_v;
   __shared__ long long best_i;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;     // 4 x 2 warps, warp tile 32 x 32
-  const int g = lane >> 2, q = lane & 3;
+  if (tid == 0) {
+    for (int s = 0; s < AQ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], AQ_CONSUMERS / 32); }
+    mbar_init(vready, AQ_CONSUMERS);
+    fence_barrier_init();
+    best_v = -INFINITY; best_i = -1;
+  }
+  __syncthreads();
   const bool want_grad = MODE == 1 || a.grad != nullptr;
 
-  if (tid == 0) { best_v = -INFINITY; best_i = -1; }
-  for (int d = tid; d < D; d += AQ_THREADS) ie[d] = a.inv_ell[d];
+  if (warp >= AQ_CONSUMERS / 32) {
+    // =========================================== TMA producer ===========================================
+    reg_dealloc<24>();
+    if (warp == AQ_CONSUMERS / 32 && lane == 0) {
+      tma_prefetch_desc(&maps.L); tma_prefetch_desc(&maps.V); tma_prefetch_desc(&maps.Linv); tma_prefetch_desc(&maps.LinvT);
+      PipeState p;
+      uint32_t vph = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int vrow = (MODE == 1 ? tile : (int)blockIdx.x) * TILE_N;
+        const int ib0 = MODE == 1 ? (tile * TILE_N) / NB : 0;
+        for (int ib = 0; ib < a.nblk; ++ib) {
+          for (int jb = ib0; jb < ib - 1; ++jb)
+            for (int c = 0; c < CH; ++c) produce_chunk(p, stages, full, empty, &maps.L, jb * NB + c * KC, ib * NB, &maps.V, jb * NB + c * KC, vrow);
+          if (ib - 1 >= ib0) {
+            mbar_wait(vready, vph); vph ^= 1u;                       // block ib-1 of the panel is written and fenced
+            for (int c = 0; c < CH; ++c)
+              produce_chunk(p, stages, full, empty, &maps.L, (ib - 1) * NB + c * KC, ib * NB, &maps.V, (ib - 1) * NB + c * KC, vrow);
+          }
+          if (ib >= ib0)
+            for (int c = 0; c < CH; ++c) produce_chunk(p, stages, full, empty, &maps.Linv, c * KC, ib * NB, nullptr, 0, 0);
+        }
+        if (a.nblk > 0) { mbar_wait(vready, vph); vph ^= 1u; }       // last forward block
+        if (want_grad) {
+          for (int ib = a.nblk - 1; ib >= 0; --ib) {
+            for (int jb = a.nblk - 1; jb > ib + 1; --jb)
+              for (int c = 0; c < CH; ++c) produce_chunk(p, stages, full, empty, &maps.L, jb * NB + c * KC, ib * NB, &maps.V, jb * NB + c * KC, vrow);
+            if (ib < a.nblk - 1) {
+              mbar_wait(vready, vph); vph ^= 1u;                     // W block ib+1
+              for (int c = 0; c < CH; ++c)
+                produce_chunk(p, stages, full, empty, &maps.L, (ib + 1) * NB + c * KC, ib * NB, &maps.V, (ib + 1) * NB + c * KC, vrow);
+            }
+            for (int c = 0; c < CH; ++c) produce_chunk(p, stages, full, empty, &maps.LinvT, c * KC, ib * NB, nullptr, 0, 0);
+          }
+          if (a.nblk > 0) { mbar_wait(vready, vph); vph ^= 1u; }     // W block 0
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================================= consumers =============================================
+  reg_alloc<240>();
+  const int wm = warp >> 1, wn = warp & 1;     // 4 x 2 warps, warp tile 32 x 32
+  const int g = lane >> 2, q = lane & 3;
+  const int rg = rho(g);
+  PipeState p;
+  for (int d = tid; d < D; d += AQ_CONSUMERS) ie[d] = a.inv_ell[d];
+
+  // acc[mt][nt][e]  <->  (m, n) = (wm*32 + mt*8 + rg,  wn*32 + nt*8 + q + 4e)
+#define ACC_M(mt) (wm * 32 + (mt) * 8 + rg)
+#define ACC_N(nt, e) (wn * 32 + (nt) * 8 + q + 4 * (e))
+
+  // acc += sum over `nch` ring chunks of A(128 x 16) * B(64 x 16)^T; B from the ring, or (B_RES) from the resident tile Rb at
+  // k = kres0 + 16 c.  Chunks c outside [klo, khi) are released without multiplying (triangular diagonal blocks).
+  auto consume = [&](double (&acc)[4][4][2], int nch, bool b_res, int klo, int khi) {
+    for (int c = 0; c < nch; ++c) {
+      mbar_wait(&full[p.s], p.ph);
+      if (c >= klo && c < khi) {
+        const double* st = stages + p.s * STAGE_DBL;
+        if (b_res) warp_mma_chunk_t<4, 4>(acc, st, KC, 0, wm * 32, Rb, RB_STRIDE, c * KC, wn * 32, rg, q);
+        else warp_mma_chunk_t<4, 4>(acc, st, KC, 0, wm * 32, st + AQ_BM * KC, KC, 0, wn * 32, rg, q);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[p.s]);
+      p.next<AQ_STAGES>();
+    }
+  };
 
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    __syncthreads();
+    consumer_sync<AQ_CONSUMERS>();
     const int64_t c0 = (int64_t)tile * TILE_N;
     // solve panel [64][ld]: one per resident CTA (MODE 0) or one per tile so the result survives (MODE 1)
     double* Vs = a.V + (int64_t)(MODE == 1 ? tile : (int)blockIdx.x) * TILE_N * a.ld;
     const int ib0 = MODE == 1 ? (int)(c0 / NB) : 0;                 // rows above the identity column are zero
     if (MODE == 0)
-    for (int e = tid; e < TILE_N * D; e += AQ_THREADS) {
-      const int n = e / D, d = e - n * D;
-      int64_t gi = c0 + n;
-      if (gi >= a.M) gi = a.M - 1;                                  // ragged tail: replicate a valid column
-      zc[d * TILE_N + n] = a.Xs[gi * D + d] * ie[d];
-    }
+      for (int e = tid; e < TILE_N * D; e += AQ_CONSUMERS) {
+        const int n = e / D, d = e - n * D;
+        int64_t gi = c0 + n;
+        if (gi >= a.M) gi = a.M - 1;                                // ragged tail: replicate a valid column
+        zc[d * TILE_N + n] = a.Xs[gi * D + d] * ie[d];
+      }
     double mu_p[4][2], ss_p[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) mu_p[nt][0] = mu_p[nt][1] = ss_p[nt][0] = ss_p[nt][1] = 0.0;
 
     // ======================================= forward solve =======================================
     for (int ib = 0; ib < a.nblk; ++ib) {
-      __syncthreads();
+      consumer_sync<AQ_CONSUMERS>();
       if (MODE == 1 && ib < ib0) {
-        for (int e = tid; e < TILE_N * NB; e += AQ_THREADS) Vs[(int64_t)(e >> 7) * a.ld + ib * NB + (e & 127)] = 0.0;
+        // never read through TMA (the contractions start at block ib0) and no vready phase: the consumers do not depend
+        // on the producer here, so an arrival could run more than one phase ahead of its wait
+        for (int e = tid; e < TILE_N * NB; e += AQ_CONSUMERS) Vs[(int64_t)(e >> 7) * a.ld + ib * NB + (e & 127)] = 0.0;
         continue;
       }
       if (MODE == 0) {
-        for (int e = tid; e < NB * D; e += AQ_THREADS) {
+        for (int e = tid; e < NB * D; e += AQ_CONSUMERS) {
           const int m = e / D, d = e - m * D;
           zx[d * NB + m] = a.Z[((int64_t)ib * NB + m) * D + d];
         }
         if (tid < NB) alb[tid] = a.alpha[ib * NB + tid];
       }
-      __syncthreads();
+      consumer_sync<AQ_CONSUMERS>();
       double acc[4][4][2];
       if (MODE == 1) {
 #pragma unroll
@@ -171,10 +269,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
-              acc[mt][nt][e] = ((int64_t)ib * NB + m == c0 + n) ? -1.0 : 0.0;
-            }
+            for (int e = 0; e < 2; ++e) acc[mt][nt][e] = ((int64_t)ib * NB + ACC_M(mt) == c0 + ACC_N(nt, e)) ? -1.0 : 0.0;
       } else {
         double r2[4][4][2];
 #pragma unroll
@@ -182,24 +277,23 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) r2[mt][nt][0] = r2[mt][nt][1] = 0.0;
         for (int d = 0; d < D; ++d) {
-          double xm[4];
-          double2 xn[4];
+          double xm[4], xn[4][2];
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) xm[mt] = zx[d * NB + wm * 32 + mt * 8 + g];
+          for (int mt = 0; mt < 4; ++mt) xm[mt] = zx[d * NB + ACC_M(mt)];
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) xn[nt] = *reinterpret_cast<const double2*>(zc + d * TILE_N + wn * 32 + nt * 8 + 2 * q);
+          for (int nt = 0; nt < 4; ++nt) { xn[nt][0] = zc[d * TILE_N + ACC_N(nt, 0)]; xn[nt][1] = zc[d * TILE_N + ACC_N(nt, 1)]; }
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-              const double d0 = xm[mt] - xn[nt].x, d1 = xm[mt] - xn[nt].y;
+              const double d0 = xm[mt] - xn[nt][0], d1 = xm[mt] - xn[nt][1];
               r2[mt][nt][0] = fma(d0, d0, r2[mt][nt][0]);
               r2[mt][nt][1] = fma(d1, d1, r2[mt][nt][1]);
             }
         }
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-          const int m = wm * 32 + mt * 8 + g;
+          const int m = ACC_M(mt);
           const bool live = ib * NB + m < a.N;
           const double al = alb[m];
 #pragma unroll
@@ -212,33 +306,30 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
             }
         }
       }
-      gemm_mainloop<AQ_BM, AQ_BN, 4, 4, AQ_STAGES, AQ_THREADS, false>(acc, a.L + (int64_t)ib * NB * a.ld + (int64_t)ib0 * NB, a.ld,
-                                                                     Vs + (int64_t)ib0 * NB, a.ld, (ib - ib0) * (NB / KC), stages, nullptr, 0,
-                                                                     wm, wn, lane, tid, 0, (ib - ib0) * (NB / KC));
+      consume(acc, (ib - ib0) * CH, false, 0, (ib - ib0) * CH);
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
-            Rb[tile_off(n, m, RB_STRIDE)] = -acc[mt][nt][e];
+            Rb[toff(ACC_N(nt, e), ACC_M(mt), RB_STRIDE)] = -acc[mt][nt][e];
             acc[mt][nt][e] = 0.0;
           }
-      __syncthreads();
-      gemm_mainloop<AQ_BM, AQ_BN, 4, 4, AQ_STAGES, AQ_THREADS, true>(acc, a.Linv + (int64_t)ib * NB * NB, NB, nullptr, 0, NB / KC, stages, Rb,
-                                                                    RB_STRIDE, wm, wn, lane, tid, 0, 2 * wm + 2);
+      consumer_sync<AQ_CONSUMERS>();
+      consume(acc, CH, true, 0, 2 * wm + 2);
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
             const double v = acc[mt][nt][e];
-            Vs[(int64_t)n * a.ld + ib * NB + m] = v;
+            Vs[(int64_t)ACC_N(nt, e) * a.ld + ib * NB + ACC_M(mt)] = v;
             ss_p[nt][e] = fma(v, v, ss_p[nt][e]);
           }
+      fence_proxy_async_global();
+      mbar_arrive(vready);
     }
     // ---- per-candidate reductions: over g (shuffles), then over the 4 warp rows (fixed order) ----
 #pragma unroll
@@ -252,12 +343,11 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
           s_ += __shfl_xor_sync(0xffffffffu, s_, o);
         }
         if (g == 0) {
-          const int n = wn * 32 + nt * 8 + 2 * q + e;
-          red[(0 * 4 + wm) * TILE_N + n] = m_;
-          red[(1 * 4 + wm) * TILE_N + n] = s_;
+          red[(0 * 4 + wm) * TILE_N + ACC_N(nt, e)] = m_;
+          red[(1 * 4 + wm) * TILE_N + ACC_N(nt, e)] = s_;
         }
       }
-    __syncthreads();
+    consumer_sync<AQ_CONSUMERS>();
     if (MODE == 0 && tid < TILE_N) {
       const int n = tid;
       const int64_t gi = c0 + n;
@@ -276,7 +366,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
         if (a.values) a.values[gi] = val;
       }
     }
-    __syncthreads();
+    consumer_sync<AQ_CONSUMERS>();
     if (MODE == 0 && tid == 0 && a.acq >= 0) {   // tile arg-max in index order: first strict maximum, NaN never wins
       double bv = best_v; long long bi = best_i;
       for (int n = 0; n < TILE_N; ++n) {
@@ -293,9 +383,9 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
 #pragma unroll
       for (int k = 0; k < 8; ++k) gacc[k] = 0.0;
       for (int ib = a.nblk - 1; ib >= 0; --ib) {
-        __syncthreads();
+        consumer_sync<AQ_CONSUMERS>();
         if (MODE == 0) {
-          for (int e = tid; e < NB * D; e += AQ_THREADS) {
+          for (int e = tid; e < NB * D; e += AQ_CONSUMERS) {
             const int m = e / D, d = e - m * D;
             zx[d * NB + m] = a.Z[((int64_t)ib * NB + m) * D + d];
           }
@@ -307,27 +397,20 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
-              acc[mt][nt][e] = -__ldcg(Vs + (int64_t)n * a.ld + ib * NB + m);
-            }
-        const int nch = (a.nblk - 1 - ib) * (NB / KC);
-        gemm_mainloop<AQ_BM, AQ_BN, 4, 4, AQ_STAGES, AQ_THREADS, false>(acc, a.L + (int64_t)ib * NB * a.ld + (int64_t)(ib + 1) * NB, a.ld,
-                                                                       Vs + (int64_t)(ib + 1) * NB, a.ld, nch, stages, nullptr, 0, wm, wn, lane,
-                                                                       tid, 0, nch);
+            for (int e = 0; e < 2; ++e) acc[mt][nt][e] = -__ldcg(Vs + (int64_t)ACC_N(nt, e) * a.ld + ib * NB + ACC_M(mt));
+        const int nch = (a.nblk - 1 - ib) * CH;
+        consume(acc, nch, false, 0, nch);
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
-              Rb[tile_off(n, m, RB_STRIDE)] = -acc[mt][nt][e];
+              Rb[toff(ACC_N(nt, e), ACC_M(mt), RB_STRIDE)] = -acc[mt][nt][e];
               acc[mt][nt][e] = 0.0;
             }
-        __syncthreads();
-        gemm_mainloop<AQ_BM, AQ_BN, 4, 4, AQ_STAGES, AQ_THREADS, true>(acc, a.LinvT + (int64_t)ib * NB * NB, NB, nullptr, 0, NB / KC, stages, Rb,
-                                                                      RB_STRIDE, wm, wn, lane, tid, 2 * wm, NB / KC);
+        consumer_sync<AQ_CONSUMERS>();
+        consume(acc, CH, true, 2 * wm, CH);
         // W_i -> panel (overwrites V_i), and G = (a_mu alpha - 2 a_s2 W) * sf2 psi(r2) -> Rb
         if (MODE == 1) {
 #pragma unroll
@@ -335,12 +418,20 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q + e;
-                Vs[(int64_t)n * a.ld + ib * NB + m] = acc[mt][nt][e];
-              }
+              for (int e = 0; e < 2; ++e) Vs[(int64_t)ACC_N(nt, e) * a.ld + ib * NB + ACC_M(mt)] = acc[mt][nt][e];
+          fence_proxy_async_global();
+          mbar_arrive(vready);
           continue;
         }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Vs[(int64_t)ACC_N(nt, e) * a.ld + ib * NB + ACC_M(mt)] = acc[mt][nt][e];
+        fence_proxy_async_global();
+        mbar_arrive(vready);
+        consumer_sync<AQ_CONSUMERS>();           // every warp is done reading Rb (diagonal GEMM) before G overwrites it
         {
           double r2[4][4][2];
 #pragma unroll
@@ -348,43 +439,40 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) r2[mt][nt][0] = r2[mt][nt][1] = 0.0;
           for (int d = 0; d < D; ++d) {
-            double xm[4];
-            double2 xn[4];
+            double xm[4], xn[4][2];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) xm[mt] = zx[d * NB + wm * 32 + mt * 8 + g];
+            for (int mt = 0; mt < 4; ++mt) xm[mt] = zx[d * NB + ACC_M(mt)];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) xn[nt] = *reinterpret_cast<const double2*>(zc + d * TILE_N + wn * 32 + nt * 8 + 2 * q);
+            for (int nt = 0; nt < 4; ++nt) { xn[nt][0] = zc[d * TILE_N + ACC_N(nt, 0)]; xn[nt][1] = zc[d * TILE_N + ACC_N(nt, 1)]; }
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
               for (int nt = 0; nt < 4; ++nt) {
-                const double d0 = xm[mt] - xn[nt].x, d1 = xm[mt] - xn[nt].y;
+                const double d0 = xm[mt] - xn[nt][0], d1 = xm[mt] - xn[nt][1];
                 r2[mt][nt][0] = fma(d0, d0, r2[mt][nt][0]);
                 r2[mt][nt][1] = fma(d1, d1, r2[mt][nt][1]);
               }
           }
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt) {
-            const int m = wm * 32 + mt * 8 + g;
+            const int m = ACC_M(mt);
             const bool live = ib * NB + m < a.N;
             const double al = alb[m];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int n = wn * 32 + nt * 8 + 2 * q + e;
-                const double w = acc[mt][nt][e];
-                Vs[(int64_t)n * a.ld + ib * NB + m] = w;
+                const int n = ACC_N(nt, e);
                 double phi, psi;
                 kern_phi_psi<FAM>(r2[mt][nt][e], phi, psi);
-                const double c = fma(c_amu[n], al, -2.0 * c_as2[n] * w);
-                Rb[tile_off(n, m, RB_STRIDE)] = live ? c * a.sf2 * psi : 0.0;
+                const double c = fma(c_amu[n], al, -2.0 * c_as2[n] * acc[mt][nt][e]);
+                Rb[toff(n, m, RB_STRIDE)] = live ? c * a.sf2 * psi : 0.0;
               }
           }
         }
-        __syncthreads();
+        consumer_sync<AQ_CONSUMERS>();
         for (int m = 0; m < NB; ++m) {
-          const double gv = Rb[tile_off(gn, m, RB_STRIDE)];
+          const double gv = Rb[toff(gn, m, RB_STRIDE)];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int d = gd + 4 * k;
@@ -402,7 +490,9 @@ __global__ void __launch_bounds__(AQ_THREADS, 1) acq_fused_kernel(const AcqArgs 
       }
     }
   }
-  __syncthreads();
+#undef ACC_M
+#undef ACC_N
+  consumer_sync<AQ_CONSUMERS>();
   if (tid == 0) { a.cta_best[blockIdx.x].value = best_v; a.cta_best[blockIdx.x].index = best_i; }
 }
 
@@ -420,8 +510,8 @@ __global__ void argmax_reduce_kernel(const b200bo_best_t* __restrict__ cta_best,
 
 size_t acq_smem_bytes(int D) {
   const size_t dbl = (size_t)AQ_STAGES * (AQ_BM + AQ_BN) * KC + (size_t)TILE_N * RB_STRIDE + (size_t)D * NB + (size_t)D * TILE_N + NB +
-                     2 * 4 * TILE_N + 5 * TILE_N + D;
-  return dbl * sizeof(double);
+                     2 * 4 * TILE_N + 5 * TILE_N + ((D + 1) & ~1) + 2 * AQ_STAGES + 2;
+  return dbl * sizeof(double) + 1024;   // + slack to align the TMA tiles to 1024 B
 }
 
 cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& l) {
@@ -438,10 +528,12 @@ cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& l) {
   if (a.ntiles == 0) return cudaSuccess;
   const int grid = (int)(a.ntiles < h->nslots ? a.ntiles : h->nslots);
   const size_t smem = acq_smem_bytes(h->D);
+  AcqMaps maps;
+  maps.L = h->tmL; maps.V = h->tmV; maps.Linv = h->tmLinv; maps.LinvT = h->tmLinvT;
 #define B200BO_ACQ(F)                                                                                   \
   do {                                                                                                  \
     cudaFuncSetAttribute(acq_fused_kernel<F, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    acq_fused_kernel<F, 0><<<grid, AQ_THREADS, smem, h->stream>>>(a);                                   \
+    acq_fused_kernel<F, 0><<<grid, AQ_THREADS, smem, h->stream>>>(a, maps);                                  \
   } while (0)
   switch (h->fam) {
     case FAM_SE: B200BO_ACQ(FAM_SE); break;
@@ -473,7 +565,9 @@ cudaError_t launch_kinv(b200bo_handle_s* h) {
   if (a.ntiles > h->nslots) return cudaErrorInvalidValue;
   const size_t smem = acq_smem_bytes(0);
   cudaFuncSetAttribute(acq_fused_kernel<FAM_SE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  acq_fused_kernel<FAM_SE, 1><<<a.ntiles, AQ_THREADS, smem, h->stream>>>(a);
+  AcqMaps maps;
+  maps.L = h->tmL; maps.V = h->tmV; maps.Linv = h->tmLinv; maps.LinvT = h->tmLinvT;
+  acq_fused_kernel<FAM_SE, 1><<<a.ntiles, AQ_THREADS, smem, h->stream>>>(a, maps);
   h->launches++;
   return cudaGetLastError();
 }

@@ -68,6 +68,7 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   CU(cudaMemsetAsync(h->dZ, 0, sizeof(double) * cap * h->D, h->stream));
   CU(cudaMemsetAsync(h->dalpha, 0, sizeof(double) * cap, h->stream));
   CU(cudaMemsetAsync(h->dy, 0, sizeof(double) * cap, h->stream));
+  CU(make_tensor_maps(h));
   return B200BO_OK;
 }
 

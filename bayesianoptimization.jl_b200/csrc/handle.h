@@ -1,5 +1,6 @@
 // handle.h -- host-side state of one GP model resident on one B200, and the launcher prototypes of the kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -43,6 +44,8 @@ struct b200bo_handle_s {
   b200bo_best_t* dcta_best = nullptr;   // [grid]
   b200bo_best_t* dbest = nullptr;
   double* dpart = nullptr;   // partial sums for the mll gradient
+  // TMA descriptors (128B-swizzled 16-double-wide boxes) over the factor, the solve panels and the inverted diagonal blocks
+  CUtensorMap tmL, tmV, tmLinv, tmLinvT;
   double* dio = nullptr;     // staging for host-pointer entry points
   int64_t dio_bytes = 0;
   cudaStream_t stream = nullptr;
@@ -60,6 +63,8 @@ struct b200bo_handle_s {
 
 namespace b200bo {
 
+// tmap.cu
+cudaError_t make_tensor_maps(b200bo_handle_s* h);
 // kmat.cu
 cudaError_t launch_scale_inputs(b200bo_handle_s* h, int64_t n0, int64_t n1);
 cudaError_t launch_kmat(b200bo_handle_s* h, double* dK, int64_t ld, int64_t N, int64_t Np, double noise, bool pad_identity);
