@@ -130,8 +130,8 @@ __device__ __forceinline__ void produce_chunk(PipeState& p, double* stages, uint
 
 template <int FAM, int MODE>
 __global__ void __launch_bounds__(384, 1) acq_fused_kernel(const AcqArgs a, const __grid_constant__ AcqMaps maps) {
-  extern __shared__ uint8_t smem_raw[];
-  double* stages = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];              // TMA 128B-swizzle tiles need 1024-byte alignment
+  double* stages = reinterpret_cast<double*>(smem_raw);
   const int D = a.D;
   double* Rb = stages + AQ_STAGES * STAGE_DBL;                       // [64][128] swizzled (1024-B aligned)
   double* zx = Rb + TILE_N * RB_STRIDE;                             // [D][128]
@@ -147,8 +147,9 @@ __global__ void __launch_bounds__(384, 1) acq_fused_kernel(const AcqArgs a, cons
   uint64_t* full = reinterpret_cast<uint64_t*>(ie + ((D + 1) & ~1));
   uint64_t* empty = full + AQ_STAGES;
   uint64_t* vready = empty + AQ_STAGES;
-  __shared__ double best_v;
-  __shared__ long long best_i;
+  double& best_v = *reinterpret_cast<double*>(vready + 1);
+  long long& best_i = *reinterpret_cast<long long*>(vready + 2);
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -206,6 +207,10 @@ __global__ void __launch_bounds__(384, 1) acq_fused_kernel(const AcqArgs a, cons
   const int g = lane >> 2, q = lane & 3;
   const int rg = rho(g);
   PipeState p;
+  const FragAddr fa(rg, q);
+  const uint32_t stage0 = smem_u32(stages);
+  const uint32_t a_row = (uint32_t)(wm * 32 + rg) * 128u, b_row = (uint32_t)(wn * 32 + rg) * 128u;      // ring tiles: 128-B rows
+  const uint32_t rb_row = smem_u32(Rb) + (uint32_t)(wn * 32 + rg) * 1024u;                                  // resident tile: 1024-B rows
   for (int d = tid; d < D; d += AQ_CONSUMERS) ie[d] = a.inv_ell[d];
 
   // acc[mt][nt][e]  <->  (m, n) = (wm*32 + mt*8 + rg,  wn*32 + nt*8 + q + 4e)
@@ -218,9 +223,9 @@ __global__ void __launch_bounds__(384, 1) acq_fused_kernel(const AcqArgs a, cons
     for (int c = 0; c < nch; ++c) {
       mbar_wait(&full[p.s], p.ph);
       if (c >= klo && c < khi) {
-        const double* st = stages + p.s * STAGE_DBL;
-        if (b_res) warp_mma_chunk_t<4, 4>(acc, st, KC, 0, wm * 32, Rb, RB_STRIDE, c * KC, wn * 32, rg, q);
-        else warp_mma_chunk_t<4, 4>(acc, st, KC, 0, wm * 32, st + AQ_BM * KC, KC, 0, wn * 32, rg, q);
+        const uint32_t st = stage0 + (uint32_t)p.s * (STAGE_DBL * 8);
+        if (b_res) warp_mma_chunk_t<4, 4, 128, 1024>(acc, st + a_row, rb_row + (uint32_t)c * (KC * 8), fa);
+        else warp_mma_chunk_t<4, 4, 128, 128>(acc, st + a_row, st + AQ_BM * KC * 8 + b_row, fa);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[p.s]);
@@ -510,8 +515,8 @@ __global__ void argmax_reduce_kernel(const b200bo_best_t* __restrict__ cta_best,
 
 size_t acq_smem_bytes(int D) {
   const size_t dbl = (size_t)AQ_STAGES * (AQ_BM + AQ_BN) * KC + (size_t)TILE_N * RB_STRIDE + (size_t)D * NB + (size_t)D * TILE_N + NB +
-                     2 * 4 * TILE_N + 5 * TILE_N + ((D + 1) & ~1) + 2 * AQ_STAGES + 2;
-  return dbl * sizeof(double) + 1024;   // + slack to align the TMA tiles to 1024 B
+                     2 * 4 * TILE_N + 5 * TILE_N + ((D + 1) & ~1) + 2 * AQ_STAGES + 4;
+  return dbl * sizeof(double);
 }
 
 cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& l) {

@@ -64,16 +64,31 @@ __device__ __forceinline__ int toff(int row, int k, int stride) { return row * s
 //     row = warp_row0 + 8 mt + rho(g),   col = warp_col0 + 8 nt + (e ? q + 4 : q)          (rho(2q) = q, rho(2q+1) = q + 4)
 __device__ __forceinline__ int rho(int g) { return (g >> 1) | ((g & 1) << 2); }
 
-template <int MT, int NT>
-__device__ __forceinline__ void warp_mma_chunk_t(double (&acc)[MT][NT][2], const double* sA, int astride, int ak0, int arow0,
-                                                 const double* sB, int bstride, int bk0, int brow0, int rg, int q) {
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+// Per-thread fragment addressing, hoisted out of the chunk loop.  For a tile whose rows are `row_bytes` apart, lane (g, q) of
+// a warp whose first row is row0 reads, for k-half kk (0/1) of a 16-wide chunk at chunk-aligned k offset kb (bytes):
+//     base + (row0 + 8 t + rho(g)) * row_bytes + kb + xk[kk],      xk[kk] = ((4 kk + q) ^ (rho(g) & 7)) * 16
+struct FragAddr {
+  uint32_t xk[2];
+  __device__ __forceinline__ FragAddr(int rg, int q) { xk[0] = (uint32_t)((q ^ (rg & 7)) << 4); xk[1] = (uint32_t)(((4 + q) ^ (rg & 7)) << 4); }
+};
+
+// acc += A(MT*8 rows x 16 k) * B(NT*8 rows x 16 k)^T for one warp.  aaddr/baddr: shared-space byte address of this lane's row
+// in the first row tile, INCLUDING the chunk's k offset; consecutive row tiles are 8 * row_bytes apart.
+template <int MT, int NT, int A_ROW_BYTES, int B_ROW_BYTES>
+__device__ __forceinline__ void warp_mma_chunk_t(double (&acc)[MT][NT][2], uint32_t aaddr, uint32_t baddr, const FragAddr& f) {
 #pragma unroll
   for (int kk = 0; kk < KC / 8; ++kk) {
     double2 a[MT], b[NT];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) a[mt] = *reinterpret_cast<const double2*>(sA + toff(arow0 + mt * 8 + rg, ak0 + kk * 8 + 2 * q, astride));
+    for (int mt = 0; mt < MT; ++mt) a[mt] = lds128(aaddr + f.xk[kk] + mt * 8 * A_ROW_BYTES);
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) b[nt] = *reinterpret_cast<const double2*>(sB + toff(brow0 + nt * 8 + rg, bk0 + kk * 8 + 2 * q, bstride));
+    for (int nt = 0; nt < NT; ++nt) b[nt] = lds128(baddr + f.xk[kk] + nt * 8 * B_ROW_BYTES);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
