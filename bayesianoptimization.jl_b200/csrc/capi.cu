@@ -186,7 +186,13 @@ B200BO_API int32_t b200bo_create(b200bo_handle_t* out, int32_t device, int32_t D
   h->num_sms = prop.multiProcessorCount;
   h->hp.ll.assign(h->iso ? 1 : D, 0.0);
   cudaSetDevice(device);
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, B200BO_ERR_CUDA, "stream create failed"); }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, B200BO_ERR_CUDA, "stream create failed");
+  }
   for (auto& e : h->ev) cudaEventCreate(&e);
   int32_t rc = alloc_device(h, capacity);
   if (rc != B200BO_OK) { g_err = h->err; free_device(h); cudaStreamDestroy(h->stream); delete h; return rc; }
@@ -203,6 +209,8 @@ B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
   if (h->dio) cudaFree(h->dio);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->syrk_ev) cudaEventDestroy(e);
+  for (auto& e : h->la_ev) cudaEventDestroy(e);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return B200BO_OK;

@@ -5,190 +5,329 @@
 // Sigma = U'U in column-major storage; that is byte-identical to the row-major lower L = U' kept here.
 //
 //   for each 128-wide panel k:
-//     K2 potrf_diag   : L_kk = chol(A_kk) by one warp-cooperative CTA; the same sweep also produces L_kk^-1
-//                       (forward substitution on I carried along the column loop) for the GEMM-shaped solves.
-//     K3 trsm_panel   : A_ik <- A_ik L_kk^-T  = A_ik (L_kk^-1)^T          (DMMA GEMM, K = 128)
-//     K4 syrk_trailing: A_ij <- A_ij - L_ik L_jk^T  for i >= j > k        (DMMA GEMM: the dense contraction)
-//   The upper triangle of h->dL receives L^T ("mirrored factor") so the backward solve L^T w = v reads the
-//   same k-major rows as the forward one.
-#include "common.cuh"
+//     K2 potrf_diag   : L_kk = chol(A_kk) by ONE 1024-thread CTA, one barrier per column; the same sweep carries the
+//                       forward substitution on I, so L_kk^-1 (needed by every GEMM-shaped solve) costs no extra pass.
+//     K3 trsm_panel   : A_ik <- A_ik L_kk^-T = (L_kk^-1 A_ik^T)^T                (TMA + DMMA tile GEMM, K = 128)
+//     K4 syrk_trailing: A_ij <- A_ij - L_ik L_jk^T  for i >= j > k              (TMA + DMMA tile GEMM: the dense contraction)
+//   The upper triangle of h->dL receives L^T ("mirrored factor") so the backward solve L^T w = v reads the same
+//   k-major rows as the forward one.
+//   Look-ahead: panel k+1 (its column of the trailing update, potrf, trsm) runs on the handle's stream while the
+//   rest of trailing update k runs on a second stream.
+#include "tma.cuh"
 #include "handle.h"
 
 namespace b200bo {
 
 // ------------------------------------------------------------------------------------------------------------
-// K2: diagonal block.  S (128 x 129 doubles in smem): lower triangle = working matrix, later B (forward
-// substitution applied to I); strict upper triangle receives L^T as columns are finished.
+// K2: diagonal block, register resident.  One thread per 4 x 4 tile of the lower triangle (528 of 544 threads); thread (ti, tk) keeps the 4 x 4 tile rows 4 ti + b, cols 4 tk + a in
+// registers: on and below the diagonal it starts as A and, column by column, turns into B = the forward substitution
+// applied to I (L^-1 with unscaled rows).  Per column j only the pivot column (unscaled a_ij) and row j-1 of B travel
+// through shared memory (double buffered), so there is ONE barrier per column and no shared-memory read-modify-write:
+//   phase 1 (cols k > j, rows i >= k):  r -= a_ij a_kj / a_jj
+//   phase 2 (cols k < j, rows i > j-1): r  = r - (l_{i,j-1}/l_{j-1,j-1}) B[j-1][k]     (B[j-1][j-1] = 1)
+// Consecutive threads walk along a tile row, so the row vector is a broadcast and the column vector is contiguous.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PS = NB + 1;
+constexpr int PD_THREADS = 544;   // 17 warps >= 32*33/2 = 528 lower-triangle tiles
 
-__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, int kb, double* __restrict__ Linv,
-                                                            double* __restrict__ LinvT, int* __restrict__ info) {
-  extern __shared__ double sm[];
-  double* S = sm;             // [NB][PS]
-  double* dg = sm + NB * PS;  // [NB] diag(L)
+__global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, int kb, double* __restrict__ Linv,
+                                                             double* __restrict__ LinvT, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double* Lf = sm;                       // [NB][PS] finished columns of L (for the coalesced write-back)
+  double* colbuf = Lf + NB * PS;         // [2][NB] pivot column, unscaled (NB*PS is even: 16-byte aligned)
+  double* rowbuf = colbuf + 2 * NB;      // [2][NB] row j-1 of B
+  double* scal = rowbuf + 2 * NB;        // [2][2]  {1/a_jj, 1/sqrt(a_jj)}
+  double* dg = scal + 4;                 // [NB] diag(L)
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  int ti = (int)((sqrt(8.0 * (double)tid + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
+  while (ti * (ti + 1) / 2 > tid) --ti;
+  int tk = tid - ti * (ti + 1) / 2;
+  const bool active = tid < 528;                     // tile (ti, tk), tk <= ti, of the lower triangle
+  if (!active) { ti = 64; tk = 64; }                 // matches no column / row: idle threads only join the barriers
   double* Ab = A + ((int64_t)kb * NB) * ld + (int64_t)kb * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e >> 7, c = e & 127;
-    if (c <= i) S[i * PS + c] = Ab[(int64_t)i * ld + c];
-  }
-  for (int j = 0; j <= NB; ++j) {
-    __syncthreads();
-    if (j < NB) {
-      // ---- phase 1 of column j: pivot, L^T row j into the upper triangle, trailing rank-1 update ----
-      double d = S[j * PS + j];
-      if (!(d > 0.0)) {
-        if (tid == 0) atomicCAS(info, 0, kb * NB + j + 1);
-        d = 1.0;
-      }
-      const double piv = sqrt(d);
-      const double rinv = 1.0 / piv;
-      if (tid == 0) dg[j] = piv;
-      for (int i = j + 1 + tid; i < NB; i += 256) S[j * PS + i] = S[i * PS + j] * rinv;
-      for (int i = j + 1 + ty; i < NB; i += 16) {
-        const double li = S[i * PS + j] * rinv;
-        for (int k = j + 1 + tx; k <= i; k += 16) {
-          const double lk = S[k * PS + j] * rinv;
-          S[i * PS + k] = fma(-li, lk, S[i * PS + k]);
-        }
-      }
+  double r[4][4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = 4 * ti + b, k = 4 * tk + a;
+      r[b][a] = (active && k <= i) ? Ab[(int64_t)i * ld + k] : 0.0;
     }
-    if (j > 0) {
-      // ---- phase 2 of column jj = j-1: B[i][c] -= l_{i,jj} * B[jj][c] / l_{jj,jj},  i > jj, c <= jj  (B diag = 1) ----
-      const int jj = j - 1;
-      const double inv = 1.0 / dg[jj];
-      for (int i = jj + 1 + ty; i < NB; i += 16) {
-        const double lij = S[jj * PS + i] * inv;      // l_{i,jj} / l_{jj,jj}
-        for (int c = tx; c <= jj; c += 16) {
-          if (c == jj) S[i * PS + c] = -lij;
-          else S[i * PS + c] = fma(-lij, S[jj * PS + c], S[i * PS + c]);
+  double lprev[4] = {0.0, 0.0, 0.0, 0.0};
+  double rinv2_prev = 0.0;
+  // Branch-free inner step: both updates are plain FMAs over the whole tile.  Masks live in the broadcast vectors
+  // (lk = 0 for k <= j, lf = 0 for i <= jj, rowbuf = 0 for k > jj); the pivot column is zeroed by its owners after it
+  // is broadcast, so "B[i][jj] = -lf_i" is the same accumulate as every other column.  Positions above the diagonal
+  // collect garbage and are never read.  The column loop is unrolled by 4 so that every register index is static.
+#pragma unroll 1
+  for (int j4 = 0; j4 < NB / 4; ++j4) {
+#pragma unroll
+    for (int a0 = 0; a0 < 4; ++a0) {
+      const int j = 4 * j4 + a0, cur = a0 & 1, jj = j - 1;
+      const int bb = (a0 + 3) & 3, jj4 = a0 > 0 ? j4 : j4 - 1;       // row jj = 4 jj4 + bb
+      // ---- writers: pivot column j (unscaled), 1/a_jj, and row jj of B ----
+      if (tk == j4) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) colbuf[cur * NB + 4 * ti + b] = r[b][a0];
+        if (ti == j4) {
+          double d = r[a0][a0];
+          if (!(d > 0.0)) { atomicCAS(info, 0, kb * NB + j + 1); d = 1.0; }
+          const double rs = rsqrt(d);
+          *reinterpret_cast<double2*>(scal + cur * 2) = make_double2(rs * rs, rs);
+          dg[j] = d;                                            // sqrt is taken after the sweep, off the critical path
         }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) r[b][a0] = 0.0;
+      }
+      if (ti == jj4) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int k = 4 * tk + a;
+          rowbuf[cur * NB + k] = (k < jj) ? r[bb][a] : (k == jj ? 1.0 : 0.0);
+        }
+      }
+      __syncthreads();
+      if (active) {
+        const double2 sc = *reinterpret_cast<const double2*>(scal + cur * 2);
+        const double rinv2 = sc.x, rinv = sc.y;
+        double li[4];
+        {
+          const double2 u = *reinterpret_cast<const double2*>(colbuf + cur * NB + 4 * ti);
+          const double2 v = *reinterpret_cast<const double2*>(colbuf + cur * NB + 4 * ti + 2);
+          li[0] = u.x; li[1] = u.y; li[2] = v.x; li[3] = v.y;
+        }
+        if (tk == j4) {                                         // finished column j of L
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (4 * ti + b > j) Lf[(4 * ti + b) * PS + j] = li[b] * rinv;
+        }
+        if (tk > j4 || (tk == j4 && a0 < 3)) {                  // Cholesky rank-1 update of the columns k > j
+          const double2 u = *reinterpret_cast<const double2*>(colbuf + cur * NB + 4 * tk);
+          const double2 v = *reinterpret_cast<const double2*>(colbuf + cur * NB + 4 * tk + 2);
+          double lk[4] = {u.x * rinv2, u.y * rinv2, v.x * rinv2, v.y * rinv2};
+#pragma unroll
+          for (int a = 0; a < 4; ++a) lk[a] = (tk > j4 || a > a0) ? lk[a] : 0.0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) r[b][a] = fma(-li[b], lk[a], r[b][a]);
+        }
+        if (tk <= jj4 && (ti > jj4 || (ti == jj4 && bb < 3))) { // forward substitution on I with column jj
+          const double2 w = *reinterpret_cast<const double2*>(rowbuf + cur * NB + 4 * tk);
+          const double2 x = *reinterpret_cast<const double2*>(rowbuf + cur * NB + 4 * tk + 2);
+          const double bj[4] = {w.x, w.y, x.x, x.y};
+          double lf[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) lf[b] = (ti > jj4 || b > bb) ? lprev[b] * rinv2_prev : 0.0;   // l_{i,jj} / l_{jj,jj}
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) r[b][a] = fma(-lf[b], bj[a], r[b][a]);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) lprev[b] = li[b];
+        rinv2_prev = rinv2;
       }
     }
   }
   __syncthreads();
-  // write back: mirrored factor block, L^-1 and its transpose
+  if (tid < NB) dg[tid] = sqrt(dg[tid]);
+  // the last column (jj = NB - 1) has no rows below it: nothing left for phase 2
+  __syncthreads();
+  // ---- L^-1 and its transpose straight from the registers: Linv[i][k] = B[i][k] / l_ii ----
   double* Li = Linv + (int64_t)kb * NB * NB;
   double* LiT = LinvT + (int64_t)kb * NB * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e >> 7, c = e & 127;
-    const int lo = i < c ? i : c, hi = i < c ? c : i;
-    Ab[(int64_t)i * ld + c] = (i == c) ? dg[i] : S[lo * PS + hi];
-    const double inv_i = 1.0 / dg[i];
-    const double y = (c < i) ? S[i * PS + c] * inv_i : (c == i ? inv_i : 0.0);   // Linv[i][c]
-    Li[i * NB + c] = y;
-  }
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int c = e >> 7, i = e & 127;      // LinvT[c][i] = Linv[i][c]
-    const double inv_i = 1.0 / dg[i];
-    const double y = (c < i) ? S[i * PS + c] * inv_i : (c == i ? inv_i : 0.0);
-    LiT[c * NB + i] = y;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K3: panel solve.  One CTA per 64 rows below the diagonal block:  C = A_rows,k * Linv_kk^T  (in place),
-// plus the mirrored copy into the upper triangle.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int TR_BM = 64, TR_BN = 128, TR_STAGES = 3, TR_THREADS = 256;
-
-__global__ void __launch_bounds__(TR_THREADS, 1) trsm_panel_kernel(double* __restrict__ A, int64_t ld, int kb,
-                                                                   const double* __restrict__ Linv) {
-  extern __shared__ __align__(16) double sm[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;   // 2 x 4 warps, warp tile 32 x 32
-  const int64_t row0 = (int64_t)(kb + 1) * NB + (int64_t)blockIdx.x * TR_BM;
-  double* Arow = A + row0 * ld + (int64_t)kb * NB;
-  const double* Li = Linv + (int64_t)kb * NB * NB;
-  double acc[4][4][2];
+  if (active) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      const int i = 4 * ti + b;
+      const double inv_i = 1.0 / dg[i];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  gemm_mainloop<TR_BM, TR_BN, 4, 4, TR_STAGES, TR_THREADS, false>(acc, Arow, ld, Li, NB, NB / KC, sm, nullptr, 0, wm, wn, lane, tid,
-                                                                 0, NB / KC);
-  const int g = lane >> 2, q = lane & 3;
-  double* Aup = A + ((int64_t)kb * NB) * ld + row0;    // mirrored block: rows = panel cols, cols = these rows
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q;
-      *reinterpret_cast<double2*>(Arow + (int64_t)m * ld + n) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-      Aup[(int64_t)n * ld + m] = acc[mt][nt][0];
-      Aup[(int64_t)(n + 1) * ld + m] = acc[mt][nt][1];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K4: trailing update (the dense contraction).  One CTA per 128 x 128 tile (bi >= bj > kb) of the trailing
-// lower triangle:  A_ij -= L_ik L_jk^T, K = 128.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int SY_BM = 128, SY_BN = 128, SY_STAGES = 3, SY_THREADS = 512;
-
-__global__ void __launch_bounds__(SY_THREADS, 1) syrk_trailing_kernel(double* __restrict__ A, int64_t ld, int kb) {
-  extern __shared__ __align__(16) double sm[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;   // 4 x 4 warps, warp tile 32 x 32
-  const int t = blockIdx.x;
-  int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-  while (ti * (ti + 1) / 2 > t) --ti;
-  const int tj = t - ti * (ti + 1) / 2;
-  const int bi = kb + 1 + ti, bj = kb + 1 + tj;
-  const double* Ai = A + ((int64_t)bi * NB) * ld + (int64_t)kb * NB;
-  const double* Aj = A + ((int64_t)bj * NB) * ld + (int64_t)kb * NB;
-  double acc[4][4][2];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  gemm_mainloop<SY_BM, SY_BN, 4, 4, SY_STAGES, SY_THREADS, false>(acc, Ai, ld, Aj, ld, NB / KC, sm, nullptr, 0, wm, wn, lane, tid, 0,
-                                                                 NB / KC);
-  const int g = lane >> 2, q = lane & 3;
-  double* C = A + ((int64_t)bi * NB) * ld + (int64_t)bj * NB;
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int m = wm * 32 + mt * 8 + g, n = wn * 32 + nt * 8 + 2 * q;
-      if (bi != bj || n + 1 <= m) {
-        double2* p = reinterpret_cast<double2*>(C + (int64_t)m * ld + n);
-        double2 c = *p;
-        c.x -= acc[mt][nt][0];
-        c.y -= acc[mt][nt][1];
-        *p = c;
-      } else if (n == m) {
-        C[(int64_t)m * ld + n] -= acc[mt][nt][0];
+      for (int a = 0; a < 4; ++a) {
+        const int k = 4 * tk + a;
+        const double y = (k < i) ? r[b][a] * inv_i : (k == i ? inv_i : 0.0);
+        Li[i * NB + k] = y;
+        LiT[k * NB + i] = y;
+        if (ti != tk) { Li[k * NB + i] = 0.0; LiT[i * NB + k] = 0.0; }     // the strictly upper tile of L^-1 is zero
       }
     }
+  }
+  // ---- mirrored factor block ----
+  for (int e = tid; e < NB * NB; e += PD_THREADS) {
+    const int i = e >> 7, c = e & 127;
+    const int lo = i < c ? i : c, hi = i < c ? c : i;
+    Ab[(int64_t)i * ld + c] = (i == c) ? dg[i] : Lf[hi * PS + lo];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Tile GEMM core shared by K3 and K4:  acc(128 x 64) = A(128 rows x 128 k) * B(64 rows x 128 k)^T, operands k-major in
+// global memory, staged by TMA (128B swizzle) through a 4-deep ring refilled once; 8 warps of DMMA.8x8x4.
+// acc[mt][nt][e] <-> (A row wm*32 + 8 mt + rho(g),  B row wn*32 + 8 nt + q + 4 e).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TG_STAGES = 4, TG_THREADS = 256, TG_BM = 128, TG_BN = 64;
+constexpr int TG_STAGE_DBL = (TG_BM + TG_BN) * KC;
+constexpr uint32_t TG_A_BYTES = TG_BM * KC * 8, TG_B_BYTES = TG_BN * KC * 8;
+constexpr size_t TG_SMEM = (size_t)TG_STAGES * TG_STAGE_DBL * 8 + 64;
+
+__device__ __forceinline__ void tile_gemm_k128(double (&acc)[4][4][2], const CUtensorMap* mapA, int ak0, int arow, const CUtensorMap* mapB,
+                                               int bk0, int brow, uint8_t* smem_raw) {
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + TG_STAGES * TG_STAGE_DBL);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3, rg = rho(g);
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < TG_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  constexpr int NCH = NB / KC;
+  if (tid == 0) {
+    for (int c = 0; c < TG_STAGES; ++c) {
+      mbar_arrive_expect_tx(&full[c], TG_A_BYTES + TG_B_BYTES);
+      tma_load_2d(stages + c * TG_STAGE_DBL, mapA, &full[c], ak0 + c * KC, arow);
+      tma_load_2d(stages + c * TG_STAGE_DBL + TG_BM * KC, mapB, &full[c], bk0 + c * KC, brow);
+    }
+  }
+  const FragAddr fa(rg, q);
+  const uint32_t stage0 = smem_u32(stages);
+  const uint32_t a_row = (uint32_t)(wm * 32 + rg) * 128u, b_row = (uint32_t)(wn * 32 + rg) * 128u;
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    const int s = c & (TG_STAGES - 1);
+    mbar_wait(&full[s], (uint32_t)(c / TG_STAGES) & 1u);
+    const uint32_t st = stage0 + (uint32_t)s * (TG_STAGE_DBL * 8);
+    warp_mma_chunk_t<4, 4, 128, 128>(acc, st + a_row, st + TG_BM * KC * 8 + b_row, fa);
+    if (c + TG_STAGES < NCH) {
+      __syncthreads();                               // every warp is done with stage s before it is refilled
+      if (tid == 0) {
+        const int cn = c + TG_STAGES;
+        mbar_arrive_expect_tx(&full[s], TG_A_BYTES + TG_B_BYTES);
+        tma_load_2d(stages + s * TG_STAGE_DBL, mapA, &full[s], ak0 + cn * KC, arow);
+        tma_load_2d(stages + s * TG_STAGE_DBL + TG_BM * KC, mapB, &full[s], bk0 + cn * KC, brow);
+      }
+    }
+  }
+}
+
+struct CholMaps { CUtensorMap L128, L64, Linv; };
+
+// K3: one CTA per 64 rows below the diagonal block.  acc[n_panel][row] = sum_l Linv[n_panel][l] * A[row][l]  = L[row][n_panel].
+__global__ void __launch_bounds__(TG_THREADS, 2) trsm_panel_kernel(double* __restrict__ A, int64_t ld, int kb,
+                                                                   const __grid_constant__ CholMaps maps) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int row0 = (kb + 1) * NB + blockIdx.x * TG_BN;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  tile_gemm_k128(acc, &maps.Linv, 0, kb * NB, &maps.L64, kb * NB, row0, smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3, rg = rho(g);
+  double* Alo = A + (int64_t)row0 * ld + (int64_t)kb * NB;          // [row][panel col]
+  double* Aup = A + ((int64_t)kb * NB) * ld + row0;                 // mirrored: [panel col][row]
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int pc = wm * 32 + mt * 8 + rg, r = wn * 32 + nt * 8 + q + 4 * e;
+        Alo[(int64_t)r * ld + pc] = acc[mt][nt][e];
+        Aup[(int64_t)pc * ld + r] = acc[mt][nt][e];
+      }
+}
+
+// K4: one CTA per 128 x 64 tile (row block bi, 64-wide column block bj2) of the trailing lower triangle:
+//     A_ij -= L_ik L_jk^T.  jlo/jhi select the 64-wide column blocks handled by this launch (look-ahead split).
+__global__ void __launch_bounds__(TG_THREADS, 2) syrk_trailing_kernel(double* __restrict__ A, int64_t ld, int kb, int col2_lo, int col2_hi,
+                                                                      int nblk, const __grid_constant__ CholMaps maps) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // tiles: for row block bi in (kb, nblk): column blocks c2 in [max(col2_lo, 2(kb+1)), min(col2_hi, 2 bi + 2))
+  int t = blockIdx.x, bi = kb + 1, c2 = 0;
+  const int base = 2 * (kb + 1) > col2_lo ? 2 * (kb + 1) : col2_lo;
+  for (; bi < nblk; ++bi) {
+    const int hi = (2 * bi + 2 < col2_hi) ? 2 * bi + 2 : col2_hi;
+    const int cnt = hi - base;
+    if (cnt > 0) { if (t < cnt) { c2 = base + t; break; } t -= cnt; }
+  }
+  if (bi >= nblk) return;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  tile_gemm_k128(acc, &maps.L128, kb * NB, bi * NB, &maps.L64, kb * NB, c2 * TG_BN, smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3, rg = rho(g);
+  double* C = A + ((int64_t)bi * NB) * ld + (int64_t)c2 * TG_BN;
+  const int diag_off = bi * NB - c2 * TG_BN;      // element (m, n) is on/below the diagonal iff n <= m + diag_off
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int m = wm * 32 + mt * 8 + rg, n = wn * 32 + nt * 8 + q + 4 * e;
+        if (n <= m + diag_off) C[(int64_t)m * ld + n] -= acc[mt][nt][e];
+      }
+}
+
+static int syrk_tiles(int kb, int nblk, int col2_lo, int col2_hi) {
+  int n = 0;
+  const int base = 2 * (kb + 1) > col2_lo ? 2 * (kb + 1) : col2_lo;
+  for (int bi = kb + 1; bi < nblk; ++bi) {
+    const int hi = (2 * bi + 2 < col2_hi) ? 2 * bi + 2 : col2_hi;
+    if (hi > base) n += hi - base;
+  }
+  return n;
 }
 
 cudaError_t launch_cholesky(b200bo_handle_s* h) {
   const int nblk = (int)(h->Np / NB);
-  const size_t sm_potrf = (size_t)(NB * PS + NB) * sizeof(double);
-  const size_t sm_trsm = (size_t)TR_STAGES * (TR_BM + TR_BN) * KC * sizeof(double);
-  const size_t sm_syrk = (size_t)SY_STAGES * (SY_BM + SY_BN) * KC * sizeof(double);
+  const size_t sm_potrf = (size_t)(NB * PS + 1 + 2 * NB + 2 * NB + 4 + NB) * sizeof(double);
   cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf);
-  cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trsm);
-  cudaFuncSetAttribute(syrk_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_syrk);
-  cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream);
+  cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
+  cudaFuncSetAttribute(syrk_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
+  CholMaps maps;
+  maps.L128 = h->tmL; maps.L64 = h->tmL64; maps.Linv = h->tmLinv;
+  cudaStream_t sa = h->stream, sb = h->stream2;
+  cudaMemsetAsync(h->dinfo, 0, sizeof(int), sa);
   while ((int)h->syrk_ev.size() < 2 * nblk) { cudaEvent_t e; cudaEventCreate(&e); h->syrk_ev.push_back(e); }
+  while ((int)h->la_ev.size() < 2 * nblk + 2) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->la_ev.push_back(e); }
   h->syrk_ev_used = 0;
+  const int big = 1 << 30;
+  // stream A (handle stream): potrf(k), trsm(k), [wait rest(k-1)], syrk column k+1 of step k, potrf(k+1), ...
+  // stream B: [wait trsm(k)], rest of syrk step k (columns >= k+2)
   for (int k = 0; k < nblk; ++k) {
-    potrf_diag_kernel<<<1, 256, sm_potrf, h->stream>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
+    potrf_diag_kernel<<<1, PD_THREADS, sm_potrf, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
     h->launches++;
     const int rem = nblk - k - 1;
-    if (rem > 0) {
-      trsm_panel_kernel<<<rem * (NB / TR_BM), TR_THREADS, sm_trsm, h->stream>>>(h->dL, h->ld, k, h->dLinv);
-      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], h->stream);
-      syrk_trailing_kernel<<<rem * (rem + 1) / 2, SY_THREADS, sm_syrk, h->stream>>>(h->dL, h->ld, k);
-      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], h->stream);
-      h->launches += 2;
+    if (rem <= 0) break;
+    trsm_panel_kernel<<<rem * (NB / TG_BN), TG_THREADS, TG_SMEM, sa>>>(h->dL, h->ld, k, maps);
+    h->launches++;
+    cudaEvent_t Pk = h->la_ev[2 * k], Rk = h->la_ev[2 * k + 1];
+    const int rest = syrk_tiles(k, nblk, 2 * (k + 2), big);
+    if (rest > 0) {
+      cudaEventRecord(Pk, sa);
+      cudaStreamWaitEvent(sb, Pk, 0);
+      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
+      syrk_trailing_kernel<<<rest, TG_THREADS, TG_SMEM, sb>>>(h->dL, h->ld, k, 2 * (k + 2), big, nblk, maps);
+      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
+      cudaEventRecord(Rk, sb);
+      h->launches++;
     }
+    if (k > 0 && syrk_tiles(k - 1, nblk, 2 * (k + 1), big) > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (k - 1) + 1], 0);   // rest(k-1) touched column k+1
+    const int col = syrk_tiles(k, nblk, 0, 2 * (k + 2));
+    syrk_trailing_kernel<<<col, TG_THREADS, TG_SMEM, sa>>>(h->dL, h->ld, k, 0, 2 * (k + 2), nblk, maps);
+    h->launches++;
+    if (rest > 0 && k == nblk - 2) cudaStreamWaitEvent(sa, Rk, 0);
   }
+  // join: everything of stream B must be visible on the handle stream
+  if (nblk >= 3) cudaStreamWaitEvent(sa, h->la_ev[2 * (nblk - 3) + 1], 0);
   return cudaGetLastError();
 }
 

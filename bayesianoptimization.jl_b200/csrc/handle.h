@@ -45,11 +45,13 @@ struct b200bo_handle_s {
   b200bo_best_t* dbest = nullptr;
   double* dpart = nullptr;   // partial sums for the mll gradient
   // TMA descriptors (128B-swizzled 16-double-wide boxes) over the factor, the solve panels and the inverted diagonal blocks
-  CUtensorMap tmL, tmV, tmLinv, tmLinvT;
+  CUtensorMap tmL, tmL64, tmV, tmLinv, tmLinvT;
   double* dio = nullptr;     // staging for host-pointer entry points
   int64_t dio_bytes = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t stream2 = nullptr;     // look-ahead stream of the factorisation (trailing update k overlaps panel k+1)
+  std::vector<cudaEvent_t> la_ev;     // look-ahead dependencies
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> syrk_ev;   // start/stop pairs around every trailing-update launch of the last factorisation
   int syrk_ev_used = 0;

@@ -15,15 +15,25 @@ __global__ void residual_kernel(const double* __restrict__ y, double beta, doubl
   if (i < Np) w[i] = i < N ? y[i] - beta : 0.0;
 }
 
-// z_blk = M * w_blk with M given TRANSPOSED (MT[c][m]) so that threads m read coalesced.
+// z_blk = M * w_blk with M given TRANSPOSED (MT[c][m]) so that threads m read coalesced.  256 threads: two halves of the
+// c range, 16 independent loads in flight per thread, fixed combine order (deterministic).
 __device__ __forceinline__ void diag_apply(const double* __restrict__ MT, const double* wblk, double* out, double* sh, int tid) {
+  __shared__ double dpart[2][NB];
   if (tid < NB) sh[tid] = wblk[tid];
   __syncthreads();
-  if (tid < NB) {
-    double s = 0.0;
-    for (int c = 0; c < NB; ++c) s = fma(MT[c * NB + tid], sh[c], s);
-    out[tid] = s;
+  const int m = tid & (NB - 1), half = tid >> 7;
+  double s = 0.0;
+#pragma unroll 1
+  for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldg(MT + (c0 + u) * NB + m);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s = fma(v[u], sh[c0 + u], s);
   }
+  dpart[half][m] = s;
+  __syncthreads();
+  if (tid < NB) out[tid] = dpart[0][tid] + dpart[1][tid];
 }
 
 // forward step i (i = -1: only the first diagonal solve).  grid = nblk - i - 1 CTAs (min 1), 256 threads.

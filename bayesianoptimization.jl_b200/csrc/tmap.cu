@@ -35,6 +35,7 @@ static bool make2d(CUtensorMap* m, double* base, uint64_t rows, uint64_t cols, u
 cudaError_t make_tensor_maps(b200bo_handle_s* h) {
   const uint64_t cap = (uint64_t)h->cap, nb = cap / NB;
   bool ok = make2d(&h->tmL, h->dL, cap, cap, cap, NB);
+  ok = ok && make2d(&h->tmL64, h->dL, cap, cap, cap, TILE_N);
   ok = ok && make2d(&h->tmV, h->dV, (uint64_t)h->nslots * TILE_N, cap, cap, TILE_N);
   ok = ok && make2d(&h->tmLinv, h->dLinv, nb * NB, NB, NB, NB);
   ok = ok && make2d(&h->tmLinvT, h->dLinvT, nb * NB, NB, NB, NB);
