@@ -5,7 +5,7 @@
 //
 // One CTA per 64x64 tile of the LOWER triangle of tiles; the tile is computed once and stored twice (tile and
 // its transpose, the latter through shared memory) so the output is exactly symmetric and every global store is
-// a full 512-byte row segment written with 16-byte vector stores.  Algorithmic bytes: 8 N^2 written + 8 N D read.
+// written as full 32-byte sectors with 16-byte vector stores (the mirror is the thread's 4x4 block transposed in registers).  Algorithmic bytes: 8 N^2 written + 8 N D read.
 #include "common.cuh"
 #include "handle.h"
 
@@ -20,12 +20,11 @@ __global__ void scale_inputs_kernel(const double* __restrict__ X, const double* 
 }
 
 template <int FAM>
-__global__ void __launch_bounds__(256) kmat_kernel(const double* __restrict__ Z, int N, int Np, int D, double sf2, double noise,
-                                                   int pad_identity, double* __restrict__ K, int64_t ld) {
+__global__ void __launch_bounds__(256, 4) kmat_kernel(const double* __restrict__ Z, int N, int Np, int D, double sf2, double noise,
+                                                      int pad_identity, double* __restrict__ K, int64_t ld) {
   extern __shared__ double sm[];
   double* za = sm;                 // [D][KT]  rows of the tile (points bi*KT..)
   double* zb = sm + D * KT;        // [D][KT]  cols of the tile (points bj*KT..)
-  double* tr = zb + D * KT;        // [KT][KT+1] transpose staging
   // linear lower-triangle tile index -> (bi >= bj)
   const int t = blockIdx.x;
   int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
@@ -47,17 +46,43 @@ __global__ void __launch_bounds__(256) kmat_kernel(const double* __restrict__ Z,
 #pragma unroll
     for (int b = 0; b < 4; ++b) r2[a][b] = 0.0;
   for (int d = 0; d < D; ++d) {
-    double xa[4], xb[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) xa[a] = za[d * KT + 4 * ty + a];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) xb[b] = zb[d * KT + 4 * tx + b];
+    const double2 xa0 = *reinterpret_cast<const double2*>(za + d * KT + 4 * ty), xa1 = *reinterpret_cast<const double2*>(za + d * KT + 4 * ty + 2);
+    const double2 xb0 = *reinterpret_cast<const double2*>(zb + d * KT + 4 * tx), xb1 = *reinterpret_cast<const double2*>(zb + d * KT + 4 * tx + 2);
+    const double xa[4] = {xa0.x, xa0.y, xa1.x, xa1.y}, xb[4] = {xb0.x, xb0.y, xb1.x, xb1.y};
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) { const double df = xa[a] - xb[b]; r2[a][b] = fma(df, df, r2[a][b]); }
   }
+  const int lim = pad_identity ? Np : N;
   double v[4][4];
+  if ((bi + 1) * KT <= N) {
+    // ---- interior tile (the common case): no bounds logic at all ----
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[a][b] = sf2 * kern_phi<FAM>(r2[a][b]);
+    if (bi == bj && ty == tx) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) v[a][a] += noise;
+    }
+    double* p = K + (int64_t)(bi * KT + 4 * ty) * ld + bj * KT + 4 * tx;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      *reinterpret_cast<double2*>(p + (int64_t)a * ld) = make_double2(v[a][0], v[a][1]);
+      *reinterpret_cast<double2*>(p + (int64_t)a * ld + 2) = make_double2(v[a][2], v[a][3]);
+    }
+    if (bi != bj) {   // mirrored tile: the thread's 4 x 4 block transposed in registers, full 32-byte sectors, no staging
+      double* m = K + (int64_t)(bj * KT + 4 * tx) * ld + bi * KT + 4 * ty;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        *reinterpret_cast<double2*>(m + (int64_t)b * ld) = make_double2(v[0][b], v[1][b]);
+        *reinterpret_cast<double2*>(m + (int64_t)b * ld + 2) = make_double2(v[2][b], v[3][b]);
+      }
+    }
+    return;
+  }
+  // ---- edge tile: ragged N and the identity padding ----
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int gi = bi * KT + 4 * ty + a;
@@ -74,11 +99,9 @@ __global__ void __launch_bounds__(256) kmat_kernel(const double* __restrict__ Z,
       v[a][b] = val;
     }
   }
-  const int lim = pad_identity ? Np : N;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int gi = bi * KT + 4 * ty + a;
-    const int gj = bj * KT + 4 * tx;
+    const int gi = bi * KT + 4 * ty + a, gj = bj * KT + 4 * tx;
     if (gi < lim) {
       double* p = K + (int64_t)gi * ld + gj;
       if (gj + 3 < lim) {
@@ -92,23 +115,16 @@ __global__ void __launch_bounds__(256) kmat_kernel(const double* __restrict__ Z,
   }
   if (bi != bj) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) tr[(4 * tx + b) * (KT + 1) + 4 * ty + a] = v[a][b];
-    __syncthreads();
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int gi = bj * KT + 4 * ty + a;     // row of the mirrored tile
-      const int gj = bi * KT + 4 * tx;
+    for (int b = 0; b < 4; ++b) {
+      const int gi = bj * KT + 4 * tx + b, gj = bi * KT + 4 * ty;
       if (gi < lim) {
-        const double* s = tr + (4 * ty + a) * (KT + 1) + 4 * tx;
         double* p = K + (int64_t)gi * ld + gj;
         if (gj + 3 < lim) {
-          *reinterpret_cast<double2*>(p) = make_double2(s[0], s[1]);
-          *reinterpret_cast<double2*>(p + 2) = make_double2(s[2], s[3]);
+          *reinterpret_cast<double2*>(p) = make_double2(v[0][b], v[1][b]);
+          *reinterpret_cast<double2*>(p + 2) = make_double2(v[2][b], v[3][b]);
         } else {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) if (gj + b < lim) p[b] = s[b];
+          for (int a = 0; a < 4; ++a) if (gj + a < lim) p[a] = v[a][b];
         }
       }
     }
@@ -129,7 +145,7 @@ cudaError_t launch_kmat(b200bo_handle_s* h, double* dK, int64_t ld, int64_t N, i
   const int T = (int)((lim + KT - 1) / KT);
   const int ntiles = T * (T + 1) / 2;
   if (ntiles == 0) return cudaSuccess;
-  const size_t smem = (size_t)(2 * h->D * KT + KT * (KT + 1)) * sizeof(double);
+  const size_t smem = (size_t)(2 * h->D * KT) * sizeof(double);
   const double sf2 = exp(2.0 * h->hp.lsigma);
 #define B200BO_KMAT(F)                                                                                       \
   do {                                                                                                       \
