@@ -1,0 +1,158 @@
+# B200BayesOpt.jl -- the reference-side binding of libb200bo.so (include/b200bo.h).
+#
+# NOT EXECUTED in this repository's environment (no julia binary in the image; SURVEY.md 0.3).  Every ccall below is
+# mirrored one-to-one by the ctypes calls in ../_lib.py / ../gp.py, which ARE exercised by tests/ on a B200.
+#
+# Drop-in: a `B200GPE` stands where a reference script uses `ElasticGPE(D; mean, kernel, logNoise, capacity)`
+# (README.md:22-26).  It implements the generic functions BayesianOptimization.jl dispatches on
+# (src/models/gp.jl:2-18,42-77 and src/acquisition.jl:4-9,20-68); the acquisition types, `BOpt`, `boptimize!` stay the
+# reference's own Julia code.
+module B200BayesOpt
+
+import BayesianOptimization
+const BO = BayesianOptimization
+import BayesianOptimization: mean_var, myrand, dims, maxy, update!, optimizemodel!, defaultoptions, nlopt_setup,
+                             acquire_max, acquisitionfunction, setparams!, AbstractAcquisition, MAPGPOptimizer,
+                             ProbabilityOfImprovement, ExpectedImprovement, UpperConfidenceBound,
+                             ThompsonSamplingSimple, MutualInformation, MaxMean, ScaledLHSIterator
+
+const LIB = get(ENV, "B200BO_LIB", joinpath(@__DIR__, "..", "csrc", "libb200bo.so"))
+
+struct Best
+    value::Float64
+    index::Int64
+end
+
+const KERNELS = Dict(:SEIso => 0, :SEArd => 1, :Mat12Iso => 2, :Mat12Ard => 3, :Mat32Iso => 4, :Mat32Ard => 5,
+                     :Mat52Iso => 6, :Mat52Ard => 7)
+acqkind(::ProbabilityOfImprovement) = Int32(0); acqparams(a::ProbabilityOfImprovement) = [a.τ]
+acqkind(::ExpectedImprovement) = Int32(1);      acqparams(a::ExpectedImprovement) = [a.τ]
+acqkind(::UpperConfidenceBound) = Int32(2);     acqparams(a::UpperConfidenceBound) = [a.βt]
+acqkind(::ThompsonSamplingSimple) = Int32(3);   acqparams(::ThompsonSamplingSimple) = Float64[]
+acqkind(::MutualInformation) = Int32(4);        acqparams(a::MutualInformation) = [a.sqrtα, a.γ̂]
+acqkind(::MaxMean) = Int32(5);                  acqparams(::MaxMean) = Float64[]
+
+lasterror(h) = unsafe_string(ccall((:b200bo_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+check(rc, h = C_NULL) = rc == 0 ? nothing : error("libb200bo error $rc: $(lasterror(h))")
+
+mutable struct B200GPE
+    h::Ptr{Cvoid}
+    dim::Int
+    function B200GPE(D::Integer; kernel::Symbol = :SEArd, meanconst::Union{Nothing, Real} = nothing,
+                     ll = zeros(kernel in (:SEIso, :Mat12Iso, :Mat32Iso, :Mat52Iso) ? 1 : D), lσ = 0.0,
+                     logNoise = -2.0, capacity = 3000, device = 0)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:b200bo_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Int32, Int64, Int32, Int32),
+                    ref, device, D, capacity, KERNELS[kernel], meanconst === nothing ? 0 : 1))
+        m = new(ref[], D)
+        finalizer(x -> ccall((:b200bo_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), m)
+        θ = Float64[logNoise; (meanconst === nothing ? Float64[] : [Float64(meanconst)]); ll; lσ]
+        check(ccall((:b200bo_set_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), m.h, θ, length(θ)), m.h)
+        m
+    end
+end
+
+# ---- model plugin API (src/models/gp.jl) -------------------------------------------------------------------------
+function dims(m::B200GPE)                                             # gp.jl:9
+    D = Ref{Int32}(0); N = Ref{Int64}(0)
+    check(ccall((:b200bo_dims, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}, Ref{Int64}), m.h, D, N), m.h)
+    (Int(D[]), Int(N[]))
+end
+function maxy(m::B200GPE)                                             # gp.jl:10
+    v = Ref{Float64}(0.0)
+    check(ccall((:b200bo_maxy, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}), m.h, v), m.h)
+    v[]
+end
+function Base.getproperty(m::B200GPE, s::Symbol)                      # model.x / model.y (BayesianOptimization.jl:117-119)
+    if s === :x || s === :y
+        D, N = dims(m)
+        X = Matrix{Float64}(undef, D, N); y = Vector{Float64}(undef, N)
+        check(ccall((:b200bo_get_data, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), getfield(m, :h), X, y), getfield(m, :h))
+        return s === :x ? X : y
+    end
+    getfield(m, s)
+end
+function mean_var(m::B200GPE, X::AbstractMatrix)                      # gp.jl:8
+    Xs = Matrix{Float64}(X); M = size(Xs, 2)
+    μ = Vector{Float64}(undef, M); σ² = similar(μ)
+    GC.@preserve Xs μ σ² check(ccall((:b200bo_predict, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                                     m.h, Xs, M, μ, σ²), m.h)
+    μ, σ²
+end
+function mean_var(m::B200GPE, x::AbstractVector)                      # gp.jl:2-5
+    μ, σ² = mean_var(m, reshape(x, :, 1))
+    μ[1], σ²[1]
+end
+function update!(m::B200GPE, x, y)                                    # gp.jl:11-18
+    if isempty(y)
+        check(ccall((:b200bo_refit, LIB), Int32, (Ptr{Cvoid},), m.h), m.h)
+    else
+        X = Matrix{Float64}(reshape(x, m.dim, :)); yy = Vector{Float64}(y)
+        GC.@preserve X yy check(ccall((:b200bo_append, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64),
+                                      m.h, X, yy, length(yy)), m.h)
+    end
+    m
+end
+
+# one fused launch over the columns of X: values, optional gradient, first-strict-max (acquisition.jl:54-68)
+function acquire(m::B200GPE, a::AbstractAcquisition, X::AbstractMatrix; seed = 0, offset = 0, grad = false)
+    Xs = Matrix{Float64}(X); M = size(Xs, 2); p = acqparams(a)
+    vals = Vector{Float64}(undef, M); g = grad ? Matrix{Float64}(undef, m.dim, M) : nothing
+    best = Ref(Best(-Inf, -1)); bx = fill(NaN, m.dim)
+    GC.@preserve Xs p vals g bx check(ccall((:b200bo_acquire, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Int64, UInt64, Int64, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ref{Best}, Ptr{Float64}),
+        m.h, acqkind(a), isempty(p) ? C_NULL : pointer(p), length(p), Xs, M, seed, offset, vals,
+        g === nothing ? C_NULL : pointer(g), C_NULL, C_NULL, best, bx), m.h)
+    (values = vals, grad = g, best = best[], best_x = bx)
+end
+myrand(m::B200GPE, x::AbstractVector) = acquire(m, ThompsonSamplingSimple(), reshape(x, :, 1); seed = rand(UInt64)).values[1]   # gp.jl:6
+myrand(m::B200GPE, X::AbstractMatrix) = acquire(m, ThompsonSamplingSimple(), X; seed = rand(UInt64)).values                    # gp.jl:7 (independent, quirk 9)
+
+# acquisitionfunction(a, model) (acquisitionfunctions.jl:4-9,108,111): vector -> scalar, matrix -> vector
+acquisitionfunction(a::AbstractAcquisition, m::B200GPE) =
+    x -> x isa AbstractVector ? acquire(m, a, reshape(x, :, 1)).values[1] : acquire(m, a, x).values
+
+# ---- acquisition search (src/acquisition.jl): restarts == number of candidate columns of ONE launch -----------------
+defaultoptions(::Type{B200GPE}, ::Type{<:AbstractAcquisition}) = (method = :LD_LBFGS, restarts = 16384, maxeval = 2000)
+defaultoptions(::Type{B200GPE}, ::Type{ThompsonSamplingSimple}) = (method = :GN_DIRECT_L, restarts = 16384, maxeval = 2000)
+
+struct B200Search{A, O}             # stands where BOpt.opt holds an NLopt.Opt (BayesianOptimization.jl:74,134)
+    acquisition::A
+    model::B200GPE
+    options::O
+end
+Base.getproperty(s::B200Search, k::Symbol) = k in (:acquisition, :model, :options) ? getfield(s, k) : getproperty(getfield(s, :options), k)
+function nlopt_setup(a::AbstractAcquisition, m::B200GPE, lb, ub, options)                    # acquisition.jl:20-38
+    setparams!(a, m)
+    B200Search(a, m, options)
+end
+function acquire_max(s::B200Search, lb, ub, restarts)                                        # acquisition.jl:54-68
+    seq = ScaledLHSIterator(lb, ub, restarts)
+    r = acquire(s.model, s.acquisition, seq.data; seed = rand(UInt64))
+    r.best.index < 0 ? (-Inf, lb) : (r.best.value, r.best_x)
+end
+
+# ---- MAP objective (gp.jl:54-77): the closure f(θ, g) of optimizemodel! is one b200bo_mll_sweep call ----------------
+function mll_and_grad!(g::Vector{Float64}, m::B200GPE, θ::Vector{Float64}; noise = true, domean = true, kern = true)
+    mll = Ref{Float64}(0.0)
+    mask = Int32((noise ? 1 : 0) | (domean ? 2 : 0) | (kern ? 4 : 0))
+    GC.@preserve θ g check(ccall((:b200bo_mll_sweep, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Int32, Ref{Float64}, Ptr{Float64}), m.h, θ, length(θ), 1, mask, mll, g), m.h)
+    mll[]
+end
+function optimizemodel!(o::MAPGPOptimizer, m::B200GPE)                                       # gp.jl:42-47
+    if o.i % o.every == 0
+        P = Ref{Int32}(0); ccall((:b200bo_num_params, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), m.h, P)
+        θ0 = Vector{Float64}(undef, P[]); ccall((:b200bo_get_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), m.h, θ0, P[])
+        opt = BO.NLopt.Opt(o.options.method, length(θ0))                                     # same NLopt driver as gp.jl:69-74
+        BO.NLopt.maxeval!(opt, o.options.maxeval)
+        BO.NLopt.max_objective!(opt, (θ, g) -> mll_and_grad!(g, m, θ))
+        _, θ, _ = BO.NLopt.optimize(opt, θ0)
+        check(ccall((:b200bo_set_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), m.h, θ, length(θ)), m.h)
+    end
+    o.i += 1
+end
+
+export B200GPE
+end # module
