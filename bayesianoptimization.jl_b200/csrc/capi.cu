@@ -60,7 +60,8 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   CU(cudaMalloc(&h->dLinvT, sizeof(double) * nb * NB * NB));
   CU(cudaMalloc(&h->dV, sizeof(double) * h->nslots * TILE_N * cap));
   CU(cudaMalloc(&h->dscal, sizeof(double) * 64));
-  CU(cudaMalloc(&h->dinfo, sizeof(int)));
+  CU(cudaMalloc(&h->dinfo, 4 * sizeof(int)));
+  CU(cudaMemsetAsync(h->dinfo, 0, 4 * sizeof(int), h->stream));
   CU(cudaMalloc(&h->dcta_best, sizeof(b200bo_best_t) * h->nslots));
   CU(cudaMalloc(&h->dbest, sizeof(b200bo_best_t)));
   CU(cudaMalloc(&h->dpart, sizeof(double) * T * T * 35));
