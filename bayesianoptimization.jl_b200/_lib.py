@@ -64,6 +64,11 @@ PROTOTYPES = {
     "b200bo_predict_dev": [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
     "b200bo_acquire_dev": [_H, C.c_int32, _dp, C.c_int32, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p,
                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "b200bo_lhs": [_H, _dp, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, _dp],
+    "b200bo_acquire_lhs": [_H, C.c_int32, _dp, C.c_int32, _dp, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, _dp,
+                           C.POINTER(Best), _dp],
+    "b200bo_acquire_ascent": [_H, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, _dp, _dp, C.c_int32, C.c_double, C.c_int64, _dp, _dp,
+                              C.POINTER(Best), _dp],
     "b200bo_kmat": [_H, _dp],
     "b200bo_last_timing_ms": [_H, C.c_int32, C.POINTER(C.c_float)],
     "b200bo_launch_count": [_H, C.POINTER(C.c_int64)],

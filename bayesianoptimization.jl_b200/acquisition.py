@@ -37,6 +37,9 @@ class AcquisitionSearch:
         self.maxeval, self.maxtime = 0, 0.0
         self.ftol_abs = self.ftol_rel = self.xtol_abs = self.xtol_rel = 0.0
         self.polish = True
+        self.device_lhs = False          # candidates generated in HBM (b200bo_acquire_lhs) instead of on the host
+        self.ascent_steps = 0            # > 0: refine the `ascent_top` best candidates by batched ascent on the device
+        self.ascent_top = 256
         self.seed = 0
         self.rng = None
         for k, v in options.items():                 # acquisition.jl:24-27: every key but method/restarts is set
@@ -85,9 +88,19 @@ def acquire_max(opt, lowerbounds=None, upperbounds=None, restarts=None, options=
         return acquire_max(o, lb, ub, options["restarts"])
     lb = np.asarray(lowerbounds, float); ub = np.asarray(upperbounds, float)
     a, model = opt.acquisition, opt.model
-    seq = ScaledLHSIterator(lb, ub, int(restarts), opt.rng)        # :57
     derivative_free = isinstance(a, ThompsonSamplingSimple) or not opt.gradient
-    r = model.acquire(a.kind, a.params(), seq.data, seed=opt.seed, want_values=False)
+    refine = opt.ascent_steps > 0 and not derivative_free
+    if opt.device_lhs and not refine:
+        r = model.acquire_lhs(a.kind, a.params(), lb, ub, int(restarts), lhs_seed=opt.seed, ts_seed=opt.seed)
+    else:
+        data = model.lhs(lb, ub, int(restarts), seed=opt.seed) if opt.device_lhs else ScaledLHSIterator(lb, ub, int(restarts), opt.rng).data  # :57
+        r = model.acquire(a.kind, a.params(), data, seed=opt.seed, want_values=refine)
+        if refine and r["best_index"] >= 0:
+            v = np.where(np.isnan(r["values"]), -np.inf, r["values"])
+            top = np.argsort(-v, kind="stable")[:max(1, min(int(opt.ascent_top), v.size))]
+            r2 = model.acquire_ascent(a.kind, a.params(), data[:, top], lb, ub, steps=int(opt.ascent_steps))
+            if r2["best_index"] >= 0 and r2["best_value"] > r["best_value"]:
+                r = dict(r, best_value=r2["best_value"], best_x=r2["best_x"])
     opt.seed += 1
     opt.last = r
     if r["best_index"] < 0:

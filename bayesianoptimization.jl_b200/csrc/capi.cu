@@ -208,6 +208,7 @@ B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
   cudaStreamSynchronize(h->stream);
   free_device(h);
   if (h->dio) cudaFree(h->dio);
+  if (h->dlbub) cudaFree(h->dlbub);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->syrk_ev) cudaEventDestroy(e);
   for (auto& e : h->la_ev) cudaEventDestroy(e);
@@ -452,6 +453,104 @@ B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t kind, const double*
   cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
   if (best) *best = hb;
   if (best_x && hb.index >= 0) memcpy(best_x, Xs + (hb.index - idx_offset) * D, sizeof(double) * D);
+  return B200BO_OK;
+}
+
+static int32_t upload_bounds(b200bo_handle_t h, const double* lb, const double* ub) {
+  if (!lb || !ub) return fail(h, B200BO_ERR_ARG, "null bounds");
+  for (int d = 0; d < h->D; ++d)
+    if (!(lb[d] <= ub[d])) return fail(h, B200BO_ERR_ARG, "mins[i] should not exceed maxs[i]");      // utils.jl:106-107
+  if (!h->dlbub) CU(cudaMalloc(&h->dlbub, sizeof(double) * 2 * h->D));
+  std::vector<double> b(lb, lb + h->D);
+  b.insert(b.end(), ub, ub + h->D);
+  CU(cudaMemcpyAsync(h->dlbub, b.data(), sizeof(double) * 2 * h->D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_lhs(b200bo_handle_t h, const double* lb, const double* ub, int64_t n_total, int64_t offset, int64_t n_local,
+                              uint64_t seed, double* Xs) {
+  if (!h || n_total < 0 || offset < 0 || n_local < 0 || offset + n_local > n_total || (n_local > 0 && !Xs))
+    return fail(h, B200BO_ERR_ARG, "bad arguments to lhs");
+  cudaSetDevice(h->device);
+  int32_t rc = upload_bounds(h, lb, ub);
+  if (rc) return rc;
+  rc = ensure_io(h, sizeof(double) * (n_local * h->D + 2));
+  if (rc) return rc;
+  CU(launch_lhs(h, h->dio, n_total, offset, n_local, seed, h->dlbub));
+  if (n_local > 0) CU(cudaMemcpyAsync(Xs, h->dio, sizeof(double) * n_local * h->D, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_acquire_lhs(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* lb, const double* ub,
+                                      int64_t n_total, int64_t offset, int64_t n_local, uint64_t lhs_seed, uint64_t ts_seed,
+                                      double* values, b200bo_best_t* best, double* best_x) {
+  if (!h || n_total < 0 || offset < 0 || n_local < 0 || offset + n_local > n_total) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire_lhs");
+  int32_t rc = check_acq(h, kind, np, false);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  rc = upload_bounds(h, lb, ub);
+  if (rc) return rc;
+  const int64_t D = h->D, M = n_local;
+  rc = ensure_io(h, sizeof(double) * (M * D + M + 4));
+  if (rc) return rc;
+  double* dXs = h->dio;
+  double* dval = dXs + M * D;
+  b200bo_best_t* dbest = reinterpret_cast<b200bo_best_t*>(dval + M);
+  CU(launch_lhs(h, dXs, n_total, offset, n_local, lhs_seed, h->dlbub));
+  rc = b200bo_acquire_dev(h, kind, p, np, dXs, M, ts_seed, offset, values ? dval : nullptr, nullptr, nullptr, nullptr, dbest);
+  if (rc) return rc;
+  b200bo_best_t hb = {-INFINITY, -1};
+  if (values && M > 0) CU(cudaMemcpyAsync(values, dval, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(&hb, dbest, sizeof(hb), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
+  if (best) *best = hb;
+  if (best_x && hb.index >= 0) {
+    CU(cudaMemcpyAsync(best_x, dXs + (hb.index - offset) * D, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* Xs, int64_t M,
+                                         const double* lb, const double* ub, int32_t steps, double step0, int64_t idx_offset,
+                                         double* Xout, double* values, b200bo_best_t* best, double* best_x) {
+  if (!h || M < 0 || (M > 0 && !Xs) || steps < 0 || !(step0 > 0.0)) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire_ascent");
+  int32_t rc = check_acq(h, kind, np, true);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  rc = upload_bounds(h, lb, ub);
+  if (rc) return rc;
+  rc = ensure_fitted(h);
+  if (rc) return rc;
+  const int64_t D = h->D;
+  rc = ensure_io(h, sizeof(double) * (M * D * 4 + M * 4 + 4));
+  if (rc) return rc;
+  double* dX = h->dio;
+  double* dwork = dX + M * D;                                       // val, grad, Xb, Gb, Fb, S
+  double* dFb = dwork + M + 3 * M * D;
+  b200bo_best_t* dbest = reinterpret_cast<b200bo_best_t*>(dwork + 3 * M + 3 * M * D);
+  b200bo_best_t hb = {-INFINITY, -1};
+  if (M > 0) {
+    CU(cudaMemcpyAsync(dX, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, h->stream));
+    AcqLaunch l;
+    l.acq_kind = kind; l.p0 = np > 0 ? p[0] : 0.0; l.p1 = np > 1 ? p[1] : 0.0; l.idx_offset = idx_offset; l.M = M; l.dbest = dbest;
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    CU(launch_ascent(h, l, dX, dwork, h->dlbub, steps, step0));
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    if (Xout) CU(cudaMemcpyAsync(Xout, dX, sizeof(double) * M * D, cudaMemcpyDeviceToHost, h->stream));
+    if (values) CU(cudaMemcpyAsync(values, dFb, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&hb, dbest, sizeof(hb), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
+    if (best_x && hb.index >= 0) {
+      CU(cudaMemcpyAsync(best_x, dX + (hb.index - idx_offset) * D, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+  }
+  if (best) *best = hb;
   return B200BO_OK;
 }
 

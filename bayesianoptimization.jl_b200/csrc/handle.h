@@ -47,6 +47,7 @@ struct b200bo_handle_s {
   // TMA descriptors (128B-swizzled 16-double-wide boxes) over the factor, the solve panels and the inverted diagonal blocks
   CUtensorMap tmL, tmL64, tmV, tmLinv, tmLinvT;
   double* dio = nullptr;     // staging for host-pointer entry points
+  double* dlbub = nullptr;   // [2][D] box bounds of the search
   int64_t dio_bytes = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
@@ -87,6 +88,10 @@ struct AcqLaunch {
 };
 cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& a);
 size_t acq_smem_bytes(int D);
+// search.cu
+cudaError_t launch_lhs(b200bo_handle_s* h, double* dXs, int64_t n_total, int64_t offset, int64_t n_local, unsigned long long seed,
+                       const double* d_lbub);
+cudaError_t launch_ascent(b200bo_handle_s* h, const AcqLaunch& base, double* dX, double* dwork, const double* d_lbub, int steps, double s0);
 // peak.cu
 cudaError_t launch_dmma_peak(b200bo_handle_s* h, double* tflops);
 // mll.cu

@@ -210,6 +210,42 @@ class B200GPE:
                                  C.byref(best), dptr(bx)), self._h)
         return dict(best_value=best.value, best_index=best.index, best_x=bx, values=vals, grad=grad, mu=mu, var=var)
 
+    def lhs(self, lb, ub, n_total: int, seed: int = 0, offset: int = 0, n_local: int = None) -> np.ndarray:
+        """latin_hypercube_sampling(lb, ub, n) (src/utils.jl:101-120) generated on the device: columns
+        [offset, offset + n_local) of one global n_total-point design."""
+        n_local = n_total - offset if n_local is None else n_local
+        lb = np.ascontiguousarray(lb, float); ub = np.ascontiguousarray(ub, float)
+        if lb.size != self.D or ub.size != self.D:
+            raise ValueError("mins and maxs should have the same length")
+        X = np.empty((self.D, n_local), order="F")
+        check(lib.b200bo_lhs(self._h, dptr(lb), dptr(ub), n_total, offset, n_local, seed & 0xFFFFFFFFFFFFFFFF, dptr(X)), self._h)
+        return X
+
+    def acquire_lhs(self, kind: str, params, lb, ub, n_total: int, lhs_seed: int = 0, ts_seed: int = 0, offset: int = 0,
+                    n_local: int = None, want_values=False):
+        """LHS candidates born in HBM + one fused sweep (ScaledLHSIterator + acquire_max's loop, acquisition.jl:57-66)."""
+        n_local = n_total - offset if n_local is None else n_local
+        lb = np.ascontiguousarray(lb, float); ub = np.ascontiguousarray(ub, float)
+        p = np.ascontiguousarray(params, float).ravel()
+        vals = np.empty(n_local) if want_values else None
+        best = _lib.Best(); bx = np.full(self.D, np.nan)
+        check(lib.b200bo_acquire_lhs(self._h, _lib.ACQ_KINDS[kind], dptr(p) if p.size else None, p.size, dptr(lb), dptr(ub), n_total,
+                                     offset, n_local, lhs_seed & 0xFFFFFFFFFFFFFFFF, ts_seed & 0xFFFFFFFFFFFFFFFF, dptr(vals),
+                                     C.byref(best), dptr(bx)), self._h)
+        return dict(best_value=best.value, best_index=best.index, best_x=bx, values=vals)
+
+    def acquire_ascent(self, kind: str, params, X, lb, ub, steps: int = 20, step0: float = 0.05, idx_offset: int = 0):
+        """M box-constrained gradient ascents in lock-step on the fused value+gradient kernel (acquisition.jl:59)."""
+        Xs = self._cands(X)
+        M = Xs.shape[1]
+        lb = np.ascontiguousarray(lb, float); ub = np.ascontiguousarray(ub, float)
+        p = np.ascontiguousarray(params, float).ravel()
+        Xout = np.empty((self.D, M), order="F"); vals = np.empty(M)
+        best = _lib.Best(); bx = np.full(self.D, np.nan)
+        check(lib.b200bo_acquire_ascent(self._h, _lib.ACQ_KINDS[kind], dptr(p) if p.size else None, p.size, dptr(Xs), M, dptr(lb),
+                                        dptr(ub), steps, step0, idx_offset, dptr(Xout), dptr(vals), C.byref(best), dptr(bx)), self._h)
+        return dict(best_value=best.value, best_index=best.index, best_x=bx, values=vals, X=Xout)
+
     def mll_sweep(self, Theta, noise=True, domean=True, kern=True, want_grad=True):
         Theta = np.asfortranarray(np.asarray(Theta, float))
         Theta = Theta.reshape(-1, 1) if Theta.ndim == 1 else Theta

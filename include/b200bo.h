@@ -130,6 +130,23 @@ B200BO_API int32_t b200bo_acquire_dev(b200bo_handle_t h, int32_t acq_kind, const
                            double* dvalues, double* dgrad, double* dmu, double* dvar,
                            b200bo_best_t* dbest);
 
+/* -- search helpers that keep the candidates in HBM ------------------------------------------
+ * b200bo_lhs: latin_hypercube_sampling(lb, ub, n) (src/utils.jl:101-120) on device: columns [offset, offset + n_local) of ONE
+ *   global n_total-point design (each stratum used once per dimension; shards of the same (seed, n_total) agree).
+ * b200bo_acquire_lhs: ScaledLHSIterator + acquire_max's sweep (src/acquisition.jl:57-66) without host candidates.
+ * b200bo_acquire_ascent: M box-constrained gradient ascents in lock-step from the columns of Xs (what NLopt LD_LBFGS adds per
+ *   restart, src/acquisition.jl:59), `steps` value+gradient launches; returns refined points / values / best. */
+B200BO_API int32_t b200bo_lhs(b200bo_handle_t h, const double* lb, const double* ub, int64_t n_total, int64_t offset, int64_t n_local,
+                              uint64_t seed, double* Xs /* host, D x n_local */);
+B200BO_API int32_t b200bo_acquire_lhs(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params,
+                                      const double* lb, const double* ub, int64_t n_total, int64_t offset, int64_t n_local,
+                                      uint64_t lhs_seed, uint64_t ts_seed, double* values /*n_local or NULL*/,
+                                      b200bo_best_t* best, double* best_x /*D or NULL*/);
+B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params,
+                                         const double* Xs, int64_t M, const double* lb, const double* ub, int32_t steps, double step0,
+                                         int64_t idx_offset, double* Xout /*D x M or NULL*/, double* values /*M or NULL*/,
+                                         b200bo_best_t* best, double* best_x /*D or NULL*/);
+
 /* -- introspection for benches / tests ----------------------------------------------------------------------- */
 B200BO_API int32_t b200bo_kmat(b200bo_handle_t h, double* K);         /* N x N Sigma = K + (e^{2 logNoise}+eps) I to host */
 B200BO_API int32_t b200bo_last_timing_ms(b200bo_handle_t h, int32_t which, float* ms);

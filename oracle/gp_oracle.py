@@ -426,6 +426,79 @@ def latin_hypercube_sampling(mins, maxs, n: int, rng: np.random.Generator) -> np
 
 
 # --------------------------------------------------------------------------------------------------
+# device-side candidate generation / batched ascent restated (csrc/search.cu).  These are the REPO's own algorithms for
+# the SURVEY 8f-2/8f-3 rows (the reference uses Random.shuffle! and NLopt); the oracle restates them to check the kernels.
+# --------------------------------------------------------------------------------------------------
+def _philox_words(c, k):
+    return philox4x32_10(np.asarray(c, np.uint32).reshape(-1, 4), np.asarray(k, np.uint32).reshape(-1, 2))
+
+
+def _perm_index(x: np.ndarray, n: int, bits: int, key) -> np.ndarray:
+    mask = np.uint64((1 << bits) - 1)
+    sh = np.uint64(bits // 2 + 1)
+    k = [np.uint64(int(v)) for v in key]
+    x = x.astype(np.uint64).copy()
+    todo = np.ones(x.size, bool)
+    with np.errstate(over="ignore"):
+        while todo.any():
+            y = x[todo]
+            y = (y + k[0]) & mask
+            y = (y * (np.uint64(2) * k[1] + np.uint64(1))) & mask
+            y ^= y >> sh
+            y = (y * (np.uint64(2) * k[2] + np.uint64(1))) & mask
+            y ^= y >> sh
+            y = (y + k[3]) & mask
+            x[todo] = y
+            todo[todo] = y >= np.uint64(n)
+    return x
+
+
+def lhs_device(lb, ub, n_total: int, seed: int, offset: int = 0, n_local: int = None) -> np.ndarray:
+    """csrc/search.cu:lhs_kernel restated: stratum = keyed permutation of the global column index, Philox jitter."""
+    lb = np.asarray(lb, float); ub = np.asarray(ub, float)
+    D = lb.size
+    n_local = n_total - offset if n_local is None else n_local
+    bits = 1
+    while bits < 63 and (1 << bits) < n_total:
+        bits += 1
+    j = np.arange(offset, offset + n_local, dtype=np.uint64)
+    s_lo, s_hi = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    out = np.empty((D, n_local))
+    for d in range(D):
+        key = _philox_words([[d, 0x4C485321, 0, 0]], [[s_lo, s_hi]])[0]
+        stratum = _perm_index(j, n_total, bits, key)
+        ctr = np.stack([(j & np.uint64(0xFFFFFFFF)).astype(np.uint32), (j >> np.uint64(32)).astype(np.uint32),
+                        np.full(n_local, d, np.uint32), np.full(n_local, 0x4A495454, np.uint32)], axis=1)
+        u = philox4x32_10(ctr, np.tile(np.array([[s_lo, s_hi]], np.uint32), (n_local, 1))).astype(np.uint64)
+        jit = (((u[:, 0] << np.uint64(32)) | u[:, 1]) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+        step = (ub[d] - lb[d]) / float(n_total)
+        out[d] = lb[d] + step * (stratum.astype(np.float64) + jit)
+    return out
+
+
+def ascent(gp: "GPOracle", kind: str, params, X0, lb, ub, steps: int = 20, step0: float = 0.05):
+    """csrc/search.cu:ascent_step_kernel restated with the oracle's value/gradient."""
+    lb = np.asarray(lb, float); ub = np.asarray(ub, float); rng = ub - lb
+    X = np.array(X0, float).reshape(lb.size, -1).copy()
+    M = X.shape[1]
+    Xb = X.copy(); Fb = np.full(M, -np.inf); Gb = np.zeros_like(X); S = np.full(M, step0)
+    for it in range(steps + 1):
+        v, g = acq_grad(gp, kind, params, X)
+        better = np.ones(M, bool) if it == 0 else (v > Fb)
+        Fb = np.where(better, v, Fb)
+        Xb[:, better] = X[:, better]; Gb[:, better] = g[:, better]
+        if it > 0:
+            S = np.where(better, np.minimum(S * 1.3, 0.5), S * 0.35)
+        if it == steps:
+            return Xb, Fb
+        gu = Gb * rng[:, None]
+        nrm = np.sqrt(np.sum(gu * gu, axis=0))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            stepv = np.where((nrm > 0) & np.isfinite(nrm), rng[:, None] * S * (gu / nrm), 0.0)
+        X = np.clip(Xb + stepv, lb[:, None], ub[:, None])
+
+
+# --------------------------------------------------------------------------------------------------
 # test functions used by the BASELINE configs (test/branin.jl:1-5, examples/branin_hartmann.jl:12-22)
 # --------------------------------------------------------------------------------------------------
 def branin(x1, x2, a=1.0, b=5.1 / (4 * math.pi ** 2), c=5 / math.pi, r=6.0, s=10.0, t=1 / (8 * math.pi)):

@@ -264,3 +264,55 @@ def test_linearity_in_y_large(bo):
         out.append(g.predict(Xs))
     assert np.allclose(out[0][0] + out[1][0], out[2][0], rtol=0, atol=1e-9 * np.abs(out[2][0]).max())
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][1], out[2][1])
+
+
+def test_device_lhs_matches_restatement_and_is_stratified(bo):
+    """src/utils.jl:101-120 on device: every stratum used once per dimension; bit-exact vs the oracle restatement of the
+    keyed permutation; shards of one design agree with the whole."""
+    g = bo.B200GPE(3, mean=bo.MeanZero(), kernel=bo.SEArd(np.zeros(3), 0.0), capacity=8)
+    lb, ub = np.array([-5.0, 0.0, 2.0]), np.array([10.0, 15.0, 2.0])
+    for n, seed in [(1, 0), (7, 3), (64, 1), (1000, 123456789012345), (4097, 7)]:
+        X = g.lhs(lb, ub, n, seed=seed)
+        assert X.shape == (3, n) and np.array_equal(X, orc.lhs_device(lb, ub, n, seed))
+        for d in range(2):
+            strata = np.floor((X[d] - lb[d]) / ((ub[d] - lb[d]) / n)).astype(int)
+            assert sorted(strata) == list(range(n))
+        assert np.all(X[2] == 2.0)
+    whole = g.lhs(lb, ub, 1000, seed=5)
+    parts = [g.lhs(lb, ub, 1000, seed=5, offset=o, n_local=m) for o, m in [(0, 333), (333, 334), (667, 333)]]
+    assert np.array_equal(np.hstack(parts), whole)
+    with pytest.raises(bo._lib.B200BOError):
+        g.lhs(ub + 1, lb, 10)
+
+
+def test_acquire_lhs_equals_host_sweep(bo):
+    rng, o, g, X, y = make_pair(bo, "Mat52Ard", "MeanConst", 4, 300, 31)
+    lb, ub = np.zeros(4), np.ones(4)
+    for kind, par in [("EI", (float(np.quantile(y, 0.9)),)), ("TS", ())]:
+        r = g.acquire_lhs(kind, par, lb, ub, 5000, lhs_seed=11, ts_seed=12, want_values=True)
+        Xs = g.lhs(lb, ub, 5000, seed=11)
+        r0 = g.acquire(kind, par, Xs, seed=12)
+        assert np.array_equal(r["values"], r0["values"]) and r["best_index"] == r0["best_index"] and np.array_equal(r["best_x"], r0["best_x"])
+        a = g.acquire_lhs(kind, par, lb, ub, 5000, lhs_seed=11, ts_seed=12, offset=0, n_local=2500)
+        b = g.acquire_lhs(kind, par, lb, ub, 5000, lhs_seed=11, ts_seed=12, offset=2500, n_local=2500)
+        from b200bo.dist import select_best
+        assert select_best([a["best_value"], b["best_value"]], [a["best_index"], b["best_index"]]) == (r["best_value"], r["best_index"])
+
+
+def test_batched_ascent_against_restatement(bo):
+    rng, o, g, X, y = make_pair(bo, "SEArd", "MeanConst", 3, 120, 41)
+    lb, ub = np.zeros(3), np.ones(3)
+    X0 = rng.random((3, 100))
+    for kind, par in [("UCB", (2.0,)), ("EI", (float(np.quantile(y, 0.8)),)), ("MaxMean", ())]:
+        r = g.acquire_ascent(kind, par, X0, lb, ub, steps=15, step0=0.05)
+        Xo, Fo = orc.ascent(o, kind, par, X0, lb, ub, steps=15, step0=0.05)
+        f0 = g.acquire(kind, par, X0)["values"]
+        assert np.all(r["values"] >= f0) and np.all(r["X"] >= lb[:, None]) and np.all(r["X"] <= ub[:, None])
+        assert np.mean(r["values"] > f0 + 1e-9 * np.abs(f0)) > 0.8                      # ascent actually climbs
+        agree = np.abs(r["values"] - Fo) <= 1e-6 * np.abs(Fo) + 1e-10                    # same trajectories up to accept/reject ties
+        assert agree.mean() > 0.97
+        chk = g.acquire(kind, par, r["X"])["values"]                                     # returned points reproduce the returned values
+        assert close(chk, r["values"], 1e-9)
+        assert r["best_index"] == orc.first_strict_argmax_np(r["values"]) and r["best_value"] == r["values"][r["best_index"]]
+    with pytest.raises(bo._lib.B200BOError):
+        g.acquire_ascent("TS", (), X0, lb, ub)

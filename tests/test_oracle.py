@@ -233,3 +233,23 @@ def test_c_restatement_matches_lapack_oracle(kern):
             assert np.abs(r["grad"] - g).max() / np.abs(g).max() < 1e-9
         assert np.allclose(r["values"], a, rtol=1e-9, atol=1e-13)
         assert r["best_index"] - 7 == orc.first_strict_argmax_np(a)
+
+
+def test_device_lhs_restatement_is_a_latin_hypercube():
+    lb, ub = np.array([-1.0, 3.0]), np.array([2.0, 4.0])
+    for n, seed in [(1, 0), (2, 1), (33, 2), (512, 3)]:
+        X = orc.lhs_device(lb, ub, n, seed)
+        for d in range(2):
+            assert sorted(np.floor((X[d] - lb[d]) / ((ub[d] - lb[d]) / n)).astype(int)) == list(range(n))
+    assert np.array_equal(orc.lhs_device(lb, ub, 100, 9, offset=40, n_local=20), orc.lhs_device(lb, ub, 100, 9)[:, 40:60])
+    assert not np.array_equal(orc.lhs_device(lb, ub, 100, 9), orc.lhs_device(lb, ub, 100, 10))
+
+
+def test_ascent_restatement_improves():
+    rng = np.random.default_rng(2)
+    X = rng.random((2, 30)); y = np.sin(4 * X[0]) + np.cos(3 * X[1])
+    gp = orc.GPOracle(2, "SEArd", "MeanZero", ll=[-1.0, -1.0], lsigma=0.0).fit(X, y)
+    X0 = rng.random((2, 20))
+    Xb, Fb = orc.ascent(gp, "MaxMean", (), X0, np.zeros(2), np.ones(2), steps=25)
+    f0 = orc.acq_value("MaxMean", (), *gp.predict(X0))
+    assert np.all(Fb >= f0) and Fb.mean() > f0.mean() + 0.05 and np.all((Xb >= 0) & (Xb <= 1))
