@@ -11,8 +11,9 @@
 //     K4 syrk_trailing: A_ij <- A_ij - L_ik L_jk^T  for i >= j > k              (TMA + DMMA tile GEMM: the dense contraction)
 //   The upper triangle of h->dL receives L^T ("mirrored factor") so the backward solve L^T w = v reads the same
 //   k-major rows as the forward one.
-//   Look-ahead: panel k+1 (its column of the trailing update, potrf, trsm) runs on the handle's stream while the
-//   rest of trailing update k runs on a second stream.
+//   Two-level blocking: inner panels of 128 inside outer panels of 512; the update right of an outer panel is one K = 512
+//   launch.  Look-ahead: the next outer panel is factorised on the handle's stream while the far part of the previous
+//   K = 512 update runs on a second stream.
 #include "tma.cuh"
 #include "handle.h"
 
@@ -171,8 +172,8 @@ constexpr int TG_STAGE_DBL = (TG_BM + TG_BN) * KC;
 constexpr uint32_t TG_A_BYTES = TG_BM * KC * 8, TG_B_BYTES = TG_BN * KC * 8;
 constexpr size_t TG_SMEM = (size_t)TG_STAGES * TG_STAGE_DBL * 8 + 64;
 
-__device__ __forceinline__ void tile_gemm_k128(double (&acc)[4][4][2], const CUtensorMap* mapA, int ak0, int arow, const CUtensorMap* mapB,
-                                               int bk0, int brow, uint8_t* smem_raw) {
+__device__ __forceinline__ void tile_gemm(double (&acc)[4][4][2], const CUtensorMap* mapA, int ak0, int arow, const CUtensorMap* mapB,
+                                          int bk0, int brow, int nch, uint8_t* smem_raw) {
   double* stages = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(stages + TG_STAGES * TG_STAGE_DBL);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -183,31 +184,30 @@ __device__ __forceinline__ void tile_gemm_k128(double (&acc)[4][4][2], const CUt
     fence_barrier_init();
   }
   __syncthreads();
-  constexpr int NCH = NB / KC;
-  if (tid == 0) {
-    for (int c = 0; c < TG_STAGES; ++c) {
-      mbar_arrive_expect_tx(&full[c], TG_A_BYTES + TG_B_BYTES);
-      tma_load_2d(stages + c * TG_STAGE_DBL, mapA, &full[c], ak0 + c * KC, arow);
-      tma_load_2d(stages + c * TG_STAGE_DBL + TG_BM * KC, mapB, &full[c], bk0 + c * KC, brow);
-    }
-  }
+  auto issue = [&](int c) {      // chunk c -> stage c % 4
+    const int s = c & (TG_STAGES - 1);
+    mbar_arrive_expect_tx(&full[s], TG_A_BYTES + TG_B_BYTES);
+    tma_load_2d(stages + s * TG_STAGE_DBL, mapA, &full[s], ak0 + c * KC, arow);
+    tma_load_2d(stages + s * TG_STAGE_DBL + TG_BM * KC, mapB, &full[s], bk0 + c * KC, brow);
+  };
+  if (tid == 0)
+    for (int c = 0; c < TG_STAGES && c < nch; ++c) issue(c);
   const FragAddr fa(rg, q);
   const uint32_t stage0 = smem_u32(stages);
   const uint32_t a_row = (uint32_t)(wm * 32 + rg) * 128u, b_row = (uint32_t)(wn * 32 + rg) * 128u;
+  // chunks are consumed in pairs; after a pair every warp meets once and thread 0 refills both stages (nch is even)
 #pragma unroll 1
-  for (int c = 0; c < NCH; ++c) {
-    const int s = c & (TG_STAGES - 1);
-    mbar_wait(&full[s], (uint32_t)(c / TG_STAGES) & 1u);
-    const uint32_t st = stage0 + (uint32_t)s * (TG_STAGE_DBL * 8);
-    warp_mma_chunk_t<4, 4, 128, 128>(acc, st + a_row, st + TG_BM * KC * 8 + b_row, fa);
-    if (c + TG_STAGES < NCH) {
-      __syncthreads();                               // every warp is done with stage s before it is refilled
-      if (tid == 0) {
-        const int cn = c + TG_STAGES;
-        mbar_arrive_expect_tx(&full[s], TG_A_BYTES + TG_B_BYTES);
-        tma_load_2d(stages + s * TG_STAGE_DBL, mapA, &full[s], ak0 + cn * KC, arow);
-        tma_load_2d(stages + s * TG_STAGE_DBL + TG_BM * KC, mapB, &full[s], bk0 + cn * KC, brow);
-      }
+  for (int c = 0; c < nch; c += 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int s = (c + h) & (TG_STAGES - 1);
+      mbar_wait(&full[s], (uint32_t)((c + h) / TG_STAGES) & 1u);
+      const uint32_t st = stage0 + (uint32_t)s * (TG_STAGE_DBL * 8);
+      warp_mma_chunk_t<4, 4, 128, 128>(acc, st + a_row, st + TG_BM * KC * 8 + b_row, fa);
+    }
+    if (c + TG_STAGES < nch) {
+      __syncthreads();                               // every warp is done with this pair of stages before the refill
+      if (tid == 0) { issue(c + TG_STAGES); issue(c + TG_STAGES + 1); }
     }
   }
 }
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(TG_THREADS, 2) trsm_panel_kernel(double* __res
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  tile_gemm_k128(acc, &maps.Linv, 0, kb * NB, &maps.L64, kb * NB, row0, smem_raw);
+  tile_gemm(acc, &maps.Linv, 0, kb * NB, &maps.L64, kb * NB, row0, NB / KC, smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3, rg = rho(g);
   double* Alo = A + (int64_t)row0 * ld + (int64_t)kb * NB;          // [row][panel col]
@@ -241,18 +241,19 @@ __global__ void __launch_bounds__(TG_THREADS, 2) trsm_panel_kernel(double* __res
       }
 }
 
-// K4: one CTA per 128 x 64 tile (row block bi, 64-wide column block bj2) of the trailing lower triangle:
-//     A_ij -= L_ik L_jk^T.  jlo/jhi select the 64-wide column blocks handled by this launch (look-ahead split).
-__global__ void __launch_bounds__(TG_THREADS, 2) syrk_trailing_kernel(double* __restrict__ A, int64_t ld, int kb, int col2_lo, int col2_hi,
-                                                                      int nblk, const __grid_constant__ CholMaps maps) {
+// K4: one CTA per 128 x 64 tile (row block bi >= bi_lo, 64-wide column block c2 in [col2_lo, min(col2_hi, 2 bi + 2)))
+// of the trailing lower triangle:   A_ij -= L_i,[kb0, kb0+nkb) L_j,[kb0, kb0+nkb)^T   (K = 128 nkb).
+// Two-level blocking: inside a 512-wide outer panel the update uses nkb = 1 and stops at the panel's last column; the update
+// of everything to the right of the panel is ONE launch with nkb = 4, where per-tile overheads are amortised over K = 512.
+__global__ void __launch_bounds__(TG_THREADS, 2) syrk_trailing_kernel(double* __restrict__ A, int64_t ld, int kb0, int nkb, int bi_lo,
+                                                                      int col2_lo, int col2_hi, int nblk,
+                                                                      const __grid_constant__ CholMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // tiles: for row block bi in (kb, nblk): column blocks c2 in [max(col2_lo, 2(kb+1)), min(col2_hi, 2 bi + 2))
-  int t = blockIdx.x, bi = kb + 1, c2 = 0;
-  const int base = 2 * (kb + 1) > col2_lo ? 2 * (kb + 1) : col2_lo;
+  int t = blockIdx.x, bi = bi_lo, c2 = 0;
   for (; bi < nblk; ++bi) {
     const int hi = (2 * bi + 2 < col2_hi) ? 2 * bi + 2 : col2_hi;
-    const int cnt = hi - base;
-    if (cnt > 0) { if (t < cnt) { c2 = base + t; break; } t -= cnt; }
+    const int cnt = hi - col2_lo;
+    if (cnt > 0) { if (t < cnt) { c2 = col2_lo + t; break; } t -= cnt; }
   }
   if (bi >= nblk) return;
   double acc[4][4][2];
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(TG_THREADS, 2) syrk_trailing_kernel(double* __
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  tile_gemm_k128(acc, &maps.L128, kb * NB, bi * NB, &maps.L64, kb * NB, c2 * TG_BN, smem_raw);
+  tile_gemm(acc, &maps.L128, kb0 * NB, bi * NB, &maps.L64, kb0 * NB, c2 * TG_BN, nkb * (NB / KC), smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3, rg = rho(g);
   double* C = A + ((int64_t)bi * NB) * ld + (int64_t)c2 * TG_BN;
@@ -276,19 +277,20 @@ __global__ void __launch_bounds__(TG_THREADS, 2) syrk_trailing_kernel(double* __
       }
 }
 
-static int syrk_tiles(int kb, int nblk, int col2_lo, int col2_hi) {
+static int syrk_tiles(int bi_lo, int nblk, int col2_lo, int col2_hi) {
   int n = 0;
-  const int base = 2 * (kb + 1) > col2_lo ? 2 * (kb + 1) : col2_lo;
-  for (int bi = kb + 1; bi < nblk; ++bi) {
+  for (int bi = bi_lo; bi < nblk; ++bi) {
     const int hi = (2 * bi + 2 < col2_hi) ? 2 * bi + 2 : col2_hi;
-    if (hi > base) n += hi - base;
+    if (hi > col2_lo) n += hi - col2_lo;
   }
   return n;
 }
 
+constexpr int OB = 4;   // outer panel = 4 inner panels = 512 columns
+
 cudaError_t launch_cholesky(b200bo_handle_s* h) {
   const int nblk = (int)(h->Np / NB);
-  const size_t sm_potrf = (size_t)(NB * PS + 1 + 2 * NB + 2 * NB + 4 + NB) * sizeof(double);
+  const size_t sm_potrf = (size_t)(NB * PS + 2 * NB + 2 * NB + 4 + NB) * sizeof(double);
   cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf);
   cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
   cudaFuncSetAttribute(syrk_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
@@ -296,38 +298,46 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
   maps.L128 = h->tmL; maps.L64 = h->tmL64; maps.Linv = h->tmLinv;
   cudaStream_t sa = h->stream, sb = h->stream2;
   cudaMemsetAsync(h->dinfo, 0, sizeof(int), sa);
-  while ((int)h->syrk_ev.size() < 2 * nblk) { cudaEvent_t e; cudaEventCreate(&e); h->syrk_ev.push_back(e); }
-  while ((int)h->la_ev.size() < 2 * nblk + 2) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->la_ev.push_back(e); }
+  const int npan = (nblk + OB - 1) / OB;
+  while ((int)h->syrk_ev.size() < 2 * npan + 2) { cudaEvent_t e; cudaEventCreate(&e); h->syrk_ev.push_back(e); }
+  while ((int)h->la_ev.size() < 2 * npan + 2) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->la_ev.push_back(e); }
   h->syrk_ev_used = 0;
   const int big = 1 << 30;
-  // stream A (handle stream): potrf(k), trsm(k), [wait rest(k-1)], syrk column k+1 of step k, potrf(k+1), ...
-  // stream B: [wait trsm(k)], rest of syrk step k (columns >= k+2)
-  for (int k = 0; k < nblk; ++k) {
-    potrf_diag_kernel<<<1, PD_THREADS, sm_potrf, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
-    h->launches++;
-    const int rem = nblk - k - 1;
-    if (rem <= 0) break;
-    trsm_panel_kernel<<<rem * (NB / TG_BN), TG_THREADS, TG_SMEM, sa>>>(h->dL, h->ld, k, maps);
-    h->launches++;
-    cudaEvent_t Pk = h->la_ev[2 * k], Rk = h->la_ev[2 * k + 1];
-    const int rest = syrk_tiles(k, nblk, 2 * (k + 2), big);
-    if (rest > 0) {
+  auto syrk = [&](cudaStream_t st, int kb0, int nkb, int bi_lo, int lo, int hi) {
+    const int n = syrk_tiles(bi_lo, nblk, lo, hi);
+    if (n > 0) {
+      syrk_trailing_kernel<<<n, TG_THREADS, TG_SMEM, st>>>(h->dL, h->ld, kb0, nkb, bi_lo, lo, hi, nblk, maps);
+      h->launches++;
+    }
+    return n;
+  };
+  // Outer panel P = inner panels [p0, p1).  Handle stream (A): the inner factorisation of P, then the K = 512 update of the
+  // NEXT outer panel's columns; second stream (B): the K = 512 update of everything further right, overlapping panel P+1.
+  for (int P = 0; P < npan; ++P) {
+    const int p0 = P * OB, p1 = (p0 + OB < nblk) ? p0 + OB : nblk, p2 = (p1 + OB < nblk) ? p1 + OB : nblk;
+    for (int k = p0; k < p1; ++k) {
+      potrf_diag_kernel<<<1, PD_THREADS, sm_potrf, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
+      h->launches++;
+      const int rem = nblk - k - 1;
+      if (rem <= 0) break;
+      trsm_panel_kernel<<<rem * (NB / TG_BN), TG_THREADS, TG_SMEM, sa>>>(h->dL, h->ld, k, maps);
+      h->launches++;
+      syrk(sa, k, 1, k + 1, 2 * (k + 1), 2 * p1);            // inner update: only the columns still inside the outer panel
+    }
+    if (p1 >= nblk) break;
+    cudaEvent_t Pk = h->la_ev[2 * P], Rk = h->la_ev[2 * P + 1];
+    if (syrk_tiles(p1, nblk, 2 * p2, big) > 0) {              // far part on stream B (after panel P is complete on A)
       cudaEventRecord(Pk, sa);
       cudaStreamWaitEvent(sb, Pk, 0);
       cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
-      syrk_trailing_kernel<<<rest, TG_THREADS, TG_SMEM, sb>>>(h->dL, h->ld, k, 2 * (k + 2), big, nblk, maps);
+      syrk(sb, p0, p1 - p0, p1, 2 * p2, big);
       cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
       cudaEventRecord(Rk, sb);
-      h->launches++;
     }
-    if (k > 0 && syrk_tiles(k - 1, nblk, 2 * (k + 1), big) > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (k - 1) + 1], 0);   // rest(k-1) touched column k+1
-    const int col = syrk_tiles(k, nblk, 0, 2 * (k + 2));
-    syrk_trailing_kernel<<<col, TG_THREADS, TG_SMEM, sa>>>(h->dL, h->ld, k, 0, 2 * (k + 2), nblk, maps);
-    h->launches++;
-    if (rest > 0 && k == nblk - 2) cudaStreamWaitEvent(sa, Rk, 0);
+    if (P > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (P - 1) + 1], 0);   // far part of panel P-1 also wrote the next panel's columns
+    syrk(sa, p0, p1 - p0, p1, 2 * p1, 2 * p2);                // near part: the next outer panel's columns
   }
-  // join: everything of stream B must be visible on the handle stream
-  if (nblk >= 3) cudaStreamWaitEvent(sa, h->la_ev[2 * (nblk - 3) + 1], 0);
+  if (npan >= 2) cudaStreamWaitEvent(sa, h->la_ev[2 * (npan - 2) + 1], 0);   // join stream B
   return cudaGetLastError();
 }
 
