@@ -35,9 +35,10 @@ int num_params(const b200bo_handle_s* h) {
 }
 
 void free_device(b200bo_handle_s* h) {
-  cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dinv_ell);
+  cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dz); cudaFree(h->dinv_ell);
   cudaFree(h->dL); cudaFree(h->dLinv); cudaFree(h->dLinvT); cudaFree(h->dV); cudaFree(h->dscal); cudaFree(h->dinfo);
   cudaFree(h->dcta_best); cudaFree(h->dbest); cudaFree(h->dpart);
+  h->dz = nullptr;
   h->dX = h->dZ = h->dy = h->dw = h->dalpha = h->dinv_ell = h->dL = h->dLinv = h->dLinvT = h->dV = h->dscal = h->dpart = nullptr;
   h->dinfo = nullptr; h->dcta_best = nullptr; h->dbest = nullptr;
 }
@@ -54,6 +55,7 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   CU(cudaMalloc(&h->dy, sizeof(double) * cap));
   CU(cudaMalloc(&h->dw, sizeof(double) * cap));
   CU(cudaMalloc(&h->dalpha, sizeof(double) * cap));
+  CU(cudaMalloc(&h->dz, sizeof(double) * cap));
   CU(cudaMalloc(&h->dinv_ell, sizeof(double) * h->D));
   CU(cudaMalloc(&h->dL, sizeof(double) * cap * cap));
   CU(cudaMalloc(&h->dLinv, sizeof(double) * nb * NB * NB));
@@ -111,6 +113,7 @@ int32_t refit(b200bo_handle_s* h) {
     noise += 1e-6 * (sf2 + noise);      // 1e-6 * tr(Sigma)/n with diag(Sigma) = sf2 + noise (EXT make_posdef!)
     h->jitter++;
   }
+  h->noise_total = noise;
   CU(launch_alpha_mll(h));
   CU(cudaEventRecord(h->ev[3], h->stream));
   double sc[2];
@@ -277,9 +280,31 @@ B200BO_API int32_t b200bo_fit(b200bo_handle_t h, const double* X, const double* 
 B200BO_API int32_t b200bo_append(b200bo_handle_t h, const double* Xn, const double* yn, int64_t m) {
   if (!h || m < 0 || (m > 0 && (!Xn || !yn))) return fail(h, B200BO_ERR_ARG, "bad arguments to append");
   cudaSetDevice(h->device);
-  h->hX.insert(h->hX.end(), Xn, Xn + m * h->D);
+  const int64_t D = h->D;
+  // Elastic path (EXT ElasticPDMats append!): a valid factor, room in the buffers, a handful of new points.
+  const bool elastic = h->fitted && h->N > 0 && m > 0 && m <= 16 && h->N + m <= h->cap;
+  h->hX.insert(h->hX.end(), Xn, Xn + m * D);
   h->hy.insert(h->hy.end(), yn, yn + m);
-  h->N += m;
+  if (elastic) {
+    bool ok = true;
+    for (int64_t j = 0; j < m && ok; ++j) {
+      const int64_t N = h->N;
+      CU(cudaMemcpyAsync(h->dX + N * D, Xn + j * D, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->dy + N, yn + j, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CU(launch_scale_inputs(h, N, N + 1));
+      CU(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+      CU(launch_append_one(h, h->noise_total));          // advances h->N / h->Np
+      int info = 0;
+      double sc[2];
+      CU(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(sc, h->dscal, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      if (info != 0) ok = false;                          // lost positive definiteness: refactor with the jitter rule
+      else h->mll = -0.5 * (sc[1] + sc[0] + (double)h->N * 1.8378770664093453);
+    }
+    if (ok) return B200BO_OK;
+  }
+  h->N = (int64_t)h->hy.size();
   int32_t rc = upload_data(h);
   if (rc) return rc;
   return refit(h);

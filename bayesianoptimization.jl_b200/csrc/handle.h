@@ -33,6 +33,8 @@ struct b200bo_handle_s {
   double* dy = nullptr;      // [cap]
   double* dw = nullptr;      // [cap] work vector for the single-RHS solves
   double* dalpha = nullptr;  // [cap] (zero in the padding)
+  double* dz = nullptr;      // [cap] z = L^-1 (y - m), kept for elastic appends
+  double noise_total = 0.0;  // diagonal noise of the current factor (incl. make_posdef! jitter)
   double* dinv_ell = nullptr;  // [D]
   double* dL = nullptr;      // [ld][ld] mirrored factor: lower = L (row-major) == U column-major, upper = L^T
   double* dLinv = nullptr;   // [cap/NB][NB][NB] inverses of the diagonal blocks
@@ -74,7 +76,12 @@ cudaError_t launch_kmat(b200bo_handle_s* h, double* dK, int64_t ld, int64_t N, i
 // chol.cu
 cudaError_t launch_cholesky(b200bo_handle_s* h);   // in place on h->dL (lower triangle), fills dLinv/dLinvT, upper mirror
 // solve.cu
-cudaError_t launch_alpha_mll(b200bo_handle_s* h);  // dw = y - m -> dalpha, dscal[0] = logdet, dscal[1] = r'alpha
+cudaError_t launch_alpha_mll(b200bo_handle_s* h);  // dw = y - m -> dz, dalpha, dscal[0] = logdet, dscal[1] = r'alpha
+cudaError_t launch_forward_solve(b200bo_handle_s* h, double* w, double* z, int nblk);
+cudaError_t launch_backward_solve(b200bo_handle_s* h, const double* z, double* w, double* alpha, int nblk);
+cudaError_t launch_logdet_dot(b200bo_handle_s* h);
+// append.cu
+cudaError_t launch_append_one(b200bo_handle_s* h, double noise);
 // acq.cu
 struct AcqLaunch {
   int acq_kind = -1;         // -1: predict only

@@ -106,27 +106,44 @@ __global__ void __launch_bounds__(256) logdet_dot_kernel(const double* __restric
   if (threadIdx.x == 0) { scal[0] = 2.0 * s0[0]; scal[1] = s1[0]; }
 }
 
+// z = L^-1 w  (w is overwritten), nblk blocks of the current factor
+cudaError_t launch_forward_solve(b200bo_handle_s* h, double* w, double* z, int nblk) {
+  for (int i = -1; i < nblk - 1; ++i) {
+    const int grid = i < 0 ? 1 : nblk - i - 1;
+    fwd_step_kernel<<<grid, 256, 0, h->stream>>>(h->dL, h->ld, h->dLinvT, w, z, i);
+    h->launches++;
+  }
+  return cudaGetLastError();
+}
+
+// alpha = L^-T z  (w is scratch)
+cudaError_t launch_backward_solve(b200bo_handle_s* h, const double* z, double* w, double* alpha, int nblk) {
+  cudaMemcpyAsync(w, z, sizeof(double) * nblk * NB, cudaMemcpyDeviceToDevice, h->stream);
+  for (int i = nblk; i >= 1; --i) {
+    const int grid = (i < nblk) ? i : 1;
+    bwd_step_kernel<<<grid, 256, 0, h->stream>>>(h->dL, h->ld, h->dLinv, w, alpha, i, nblk);
+    h->launches++;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_logdet_dot(b200bo_handle_s* h) {
+  const double beta = h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0;
+  logdet_dot_kernel<<<1, 256, 0, h->stream>>>(h->dL, h->ld, h->dy, beta, h->dalpha, (int)h->N, h->dscal);
+  h->launches++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_alpha_mll(b200bo_handle_s* h) {
   const int nblk = (int)(h->Np / NB);
   const double beta = h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0;
   residual_kernel<<<(int)((h->Np + 255) / 256), 256, 0, h->stream>>>(h->dy, beta, h->dw, (int)h->N, (int)h->Np);
   h->launches++;
-  double* z = h->dalpha;   // forward result lives in dalpha, then becomes w of the backward pass
-  for (int i = -1; i < nblk - 1; ++i) {
-    const int grid = i < 0 ? 1 : nblk - i - 1;
-    fwd_step_kernel<<<grid, 256, 0, h->stream>>>(h->dL, h->ld, h->dLinvT, h->dw, z, i);
-    h->launches++;
-  }
-  // backward: w := z, alpha overwrites block by block (block i of w is final before alpha_i is written)
-  cudaMemcpyAsync(h->dw, z, sizeof(double) * h->Np, cudaMemcpyDeviceToDevice, h->stream);
-  for (int i = nblk; i >= 1; --i) {
-    const int grid = (i < nblk) ? i : 1;
-    bwd_step_kernel<<<grid, 256, 0, h->stream>>>(h->dL, h->ld, h->dLinv, h->dw, h->dalpha, i, nblk);
-    h->launches++;
-  }
-  logdet_dot_kernel<<<1, 256, 0, h->stream>>>(h->dL, h->ld, h->dy, beta, h->dalpha, (int)h->N, h->dscal);
-  h->launches++;
-  return cudaGetLastError();
+  cudaError_t e = launch_forward_solve(h, h->dw, h->dz, nblk);          // z = L^-1 (y - m) is kept for elastic appends
+  if (e != cudaSuccess) return e;
+  e = launch_backward_solve(h, h->dz, h->dw, h->dalpha, nblk);
+  if (e != cudaSuccess) return e;
+  return launch_logdet_dot(h);
 }
 
 }  // namespace b200bo

@@ -316,3 +316,32 @@ def test_batched_ascent_against_restatement(bo):
         assert r["best_index"] == orc.first_strict_argmax_np(r["values"]) and r["best_value"] == r["values"][r["best_index"]]
     with pytest.raises(bo._lib.B200BOError):
         g.acquire_ascent("TS", (), X0, lb, ub)
+
+
+@pytest.mark.parametrize("kern,N0", [("SEArd", 126), ("Mat52Ard", 250), ("Mat32Iso", 128), ("SEArd", 1000)])
+def test_elastic_append_matches_refit(bo, kern, N0):
+    """update!(model::ElasticGPE, x, y) = append! (gp.jl:11): rank-1 factor extension on the device, across a 128-block
+    boundary, against a full refactor and the oracle."""
+    D = 4
+    rng = np.random.default_rng(N0)
+    X = rng.random((D, N0 + 9)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N0 + 9)
+    ll = np.full(1 if kern.endswith("Iso") else D, np.log(0.5))
+    mk = lambda: bo.B200GPE(D, mean=bo.MeanConst(0.2), kernel=bo.gp._Kernel(kern, ll, 0.1), logNoise=-2.0, capacity=N0 + 200)
+    g = mk(); g.fit(X[:, :N0], y[:N0])
+    l0 = g.launch_count
+    for j in range(N0, N0 + 5):
+        bo.update(g, X[:, j], y[j:j + 1])                     # one point per BO iteration
+    bo.update(g, X[:, N0 + 5:], y[N0 + 5:])                    # a small batch
+    assert bo.dims(g) == (D, N0 + 9) and np.array_equal(g.y, y)
+    ref = mk(); ref.fit(X, y)
+    o = orc.GPOracle(D, kern, "MeanConst", ll=ll, lsigma=0.1, lognoise=-2.0, beta=0.2).fit(X, y)
+    assert relmax(g.factor, o.U) < 1e-11 and relmax(g.alpha, o.alpha) < 1e-9 and abs(g.mll - o.mll) < 1e-10 * abs(o.mll)
+    assert relmax(g.factor, ref.factor) < 1e-12
+    Xs = rng.random((D, 300))
+    r, r0 = g.acquire("EI", (0.3,), Xs, want_grad=True, want_mu_var=True), ref.acquire("EI", (0.3,), Xs, want_grad=True, want_mu_var=True)
+    assert close(r["mu"], r0["mu"], 1e-9) and close(r["var"], r0["var"], 1e-8) and r["best_index"] == r0["best_index"]
+    assert relmax(r["grad"], r0["grad"]) < 1e-8
+    g.set_params(g.get_params() + 0.1)                         # hyper-parameters change: the next update refactors
+    bo.update(g, X[:, :1], y[:1])
+    ref.set_params(ref.get_params() + 0.1); ref.fit(np.hstack([X, X[:, :1]]), np.concatenate([y, y[:1]]))
+    assert relmax(g.alpha, ref.alpha) < 1e-10
