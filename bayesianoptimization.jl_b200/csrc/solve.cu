@@ -10,27 +10,40 @@
 
 namespace b200bo {
 
+// asm volatile loads keep their program order, so a batch really is in flight before its first use (the scheduler otherwise
+// re-serialises load/use pairs to save registers, turning one memory latency into sixteen)
+__device__ __forceinline__ double2 ldcg2_issue(const double* p) {
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldcg1_issue(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
+  return v;
+}
+
 __global__ void residual_kernel(const double* __restrict__ y, double beta, double* __restrict__ w, int N, int Np) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Np) w[i] = i < N ? y[i] - beta : 0.0;
 }
 
-// z_blk = M * w_blk with M given TRANSPOSED (MT[c][m]) so that threads m read coalesced.  256 threads: two halves of the
-// c range, 16 independent loads in flight per thread, fixed combine order (deterministic).
-__device__ __forceinline__ void diag_apply(const double* __restrict__ MT, const double* wblk, double* out, double* sh, int tid) {
+// z_blk = M * w_blk with M given TRANSPOSED (MT[c][m]) so that threads m read coalesced.  256 threads: two halves of the c
+// range, fixed combine order (deterministic).  The operand block is PREFETCHED into registers (diag_prefetch) before the
+// caller's update phase, so the solve itself touches no global memory except w.
+__device__ __forceinline__ void diag_prefetch(const double* __restrict__ MT, double (&v)[64], int tid) {
+  const int m = tid & (NB - 1), half = tid >> 7;
+#pragma unroll
+  for (int u = 0; u < 64; ++u) v[u] = ldcg1_issue(MT + (half * 64 + u) * NB + m);
+}
+__device__ __forceinline__ void diag_apply(const double (&v)[64], const double* wblk, double* out, double* sh, int tid) {
   __shared__ double dpart[2][NB];
   if (tid < NB) sh[tid] = wblk[tid];
   __syncthreads();
   const int m = tid & (NB - 1), half = tid >> 7;
   double s = 0.0;
-#pragma unroll 1
-  for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
-    double v[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldg(MT + (c0 + u) * NB + m);
-#pragma unroll
-    for (int u = 0; u < 16; ++u) s = fma(v[u], sh[c0 + u], s);
-  }
+  for (int u = 0; u < 64; ++u) s = fma(v[u], sh[half * 64 + u], s);
   dpart[half][m] = s;
   __syncthreads();
   if (tid < NB) out[tid] = dpart[0][tid] + dpart[1][tid];
@@ -42,26 +55,33 @@ __global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict_
   __shared__ double sh[NB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = i + 1 + blockIdx.x;     // row block handled by this CTA
+  double dv[64];
+  if (blockIdx.x == 0) diag_prefetch(LinvT + (int64_t)rb * NB * NB, dv, tid);
   if (i >= 0) {
+    // w[r] -= L[r][i*NB .. +127] . z_i ; one warp per row, 16 rows per warp, all 32 loads of a lane in flight at once
+    double2 a[16], b[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const double* Lr = L + ((int64_t)rb * NB + warp + 8 * u) * ld + (int64_t)i * NB;
+      a[u] = ldcg2_issue(Lr + 4 * lane);
+      b[u] = ldcg2_issue(Lr + 4 * lane + 2);
+    }
     if (tid < NB) sh[tid] = z[i * NB + tid];
     __syncthreads();
-    // w[r] -= L[r][i*NB .. +127] . z_i ; one warp per row, 16 rows per warp
-    for (int rr = warp; rr < NB; rr += 8) {
-      const int64_t r = (int64_t)rb * NB + rr;
-      const double* Lr = L + r * ld + (int64_t)i * NB;
-      const double2 a = *reinterpret_cast<const double2*>(Lr + 4 * lane);
-      const double2 b = *reinterpret_cast<const double2*>(Lr + 4 * lane + 2);
-      double s = a.x * sh[4 * lane];
-      s = fma(a.y, sh[4 * lane + 1], s);
-      s = fma(b.x, sh[4 * lane + 2], s);
-      s = fma(b.y, sh[4 * lane + 3], s);
+    const double z0 = sh[4 * lane], z1 = sh[4 * lane + 1], z2 = sh[4 * lane + 2], z3 = sh[4 * lane + 3];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      double s = a[u].x * z0;
+      s = fma(a[u].y, z1, s);
+      s = fma(b[u].x, z2, s);
+      s = fma(b[u].y, z3, s);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) w[r] -= s;
+      if (lane == 0) w[(int64_t)rb * NB + warp + 8 * u] -= s;
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0) diag_apply(LinvT + (int64_t)rb * NB * NB, w + (int64_t)rb * NB, z + (int64_t)rb * NB, sh, tid);
+  if (blockIdx.x == 0) diag_apply(dv, w + (int64_t)rb * NB, z + (int64_t)rb * NB, sh, tid);
 }
 
 // backward step i (descending; i = nblk: only the last diagonal solve).  grid = max(i,1) CTAs.
@@ -72,20 +92,26 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict_
   __shared__ double part[2][NB];
   const int tid = threadIdx.x;
   const int cb = (i < nblk) ? (int)blockIdx.x : nblk - 1;
+  const bool solver = (i == nblk || cb == i - 1);      // alpha_cb = L_cb^-T w_cb : (Linv^T) given transposed == Linv
+  double dv[64];
+  if (solver) diag_prefetch(Linv + (int64_t)cb * NB * NB, dv, tid);
   if (i < nblk) {
-    if (tid < NB) sh[tid] = alpha[i * NB + tid];
-    __syncthreads();
     const int c = tid & 127, half = tid >> 7;   // two halves of the 128 rows, fixed combine order
     const double* Lc = L + ((int64_t)i * NB + half * 64) * ld + (int64_t)cb * NB + c;
+    double v[64];
+#pragma unroll
+    for (int u = 0; u < 64; ++u) v[u] = ldcg1_issue(Lc + (int64_t)u * ld);       // 64 independent loads in flight
+    if (tid < NB) sh[tid] = alpha[i * NB + tid];
+    __syncthreads();
     double s = 0.0;
-    for (int m = 0; m < 64; ++m) s = fma(Lc[(int64_t)m * ld], sh[half * 64 + m], s);
+#pragma unroll
+    for (int u = 0; u < 64; ++u) s = fma(v[u], sh[half * 64 + u], s);
     part[half][c] = s;
     __syncthreads();
     if (tid < NB) w[(int64_t)cb * NB + tid] -= part[0][tid] + part[1][tid];
     __syncthreads();
   }
-  if (i == nblk || cb == i - 1)   // alpha_cb = L_cb^-T w_cb : (Linv^T) given transposed == Linv
-    diag_apply(Linv + (int64_t)cb * NB * NB, w + (int64_t)cb * NB, alpha + (int64_t)cb * NB, sh, tid);
+  if (solver) diag_apply(dv, w + (int64_t)cb * NB, alpha + (int64_t)cb * NB, sh, tid);
 }
 
 // scal[0] = logdet = 2 sum log L_ii (i < N), scal[1] = r'alpha.  Single CTA, fixed order.

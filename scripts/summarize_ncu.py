@@ -9,7 +9,7 @@ import sys
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed_pipe_tensor", "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor", "sm__pipe_tensor_cycles_active.avg.pct", "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct", "sm__pipe_fp64_cycles_active.avg.pct", "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg", "dram__cycles_active",
