@@ -20,7 +20,7 @@ __global__ void scale_inputs_kernel(const double* __restrict__ X, const double* 
 }
 
 template <int FAM>
-__global__ void __launch_bounds__(256, 4) kmat_kernel(const double* __restrict__ Z, int N, int Np, int D, double sf2, double noise,
+__global__ void __launch_bounds__(256, 3) kmat_kernel(const double* __restrict__ Z, int N, int Np, int D, double sf2, double noise,
                                                       int pad_identity, double* __restrict__ K, int64_t ld) {
   extern __shared__ double sm[];
   double* za = sm;                 // [D][KT]  rows of the tile (points bi*KT..)
