@@ -169,6 +169,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # the version banner goes to stdout and would precede the JSON line
         dist.init_process_group("nccl", device_id=dev)
     import b200bo
     from b200bo import _lib
