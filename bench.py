@@ -217,6 +217,8 @@ def main():
         else:
             gathered.copy_(dbest.view(1, 2))
 
+    clk = ClockSampler(local_rank)
+    clk.__enter__()                                  # sampled from the warm-up to the end of the e2e arm (all under load)
     for _ in range(args.warmup):
         step_dev(); flush.zero_()
     torch.cuda.synchronize(dev)
@@ -226,12 +228,11 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    with ClockSampler(local_rank) as clk:
-        for e0, e1 in evs:
-            e0.record(stream); step_dev(); e1.record(stream)
-            flush.zero_()                                                          # L2 flush between timed steps
-            torch.cuda.synchronize(dev)
-            kern_ms.append(model.timing_ms(_lib.T_ACQ))
+    for e0, e1 in evs:
+        e0.record(stream); step_dev(); e1.record(stream)
+        flush.zero_()                                                              # L2 flush between timed steps
+        torch.cuda.synchronize(dev)
+        kern_ms.append(model.timing_ms(_lib.T_ACQ))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -259,6 +260,7 @@ def main():
     if world > 1:
         dist.barrier()
     t_e2e = e0.elapsed_time(e1) * 1e-3
+    clk.__exit__(None, None, None)
 
     # ---- max over ranks ------------------------------------------------------------------------------------------
     tt = torch.tensor([t_dev, t_e2e, float(np.mean(kern_ms)) * 1e-3], dtype=torch.float64, device=dev)
