@@ -66,9 +66,8 @@ def _polish(opt: AcquisitionSearch, x0: np.ndarray, f0: float):
         r = model.acquire(a.kind, a.params(), x, want_grad=True)
         return -float(r["values"][0]), -r["grad"][:, 0]
 
-    kw = dict(maxfun=int(opt.maxeval) if opt.maxeval else 15000)
-    if opt.ftol_rel:
-        kw["ftol"] = float(opt.ftol_rel)
+    # stopping rules in the spirit of the NLopt options the reference forwards (acquisition.jl:24-27): maxeval, ftol_rel
+    kw = dict(maxfun=int(opt.maxeval) if opt.maxeval else 15000, gtol=1e-11, ftol=float(opt.ftol_rel) if opt.ftol_rel else 1e-15)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         res = minimize(negf, np.clip(x0, lb, ub), jac=True, method="L-BFGS-B", bounds=list(zip(lb, ub)), options=kw)

@@ -20,32 +20,35 @@
 namespace b200bo {
 
 // ------------------------------------------------------------------------------------------------------------
-// K2: diagonal block, register resident.  One thread per 4 x 4 tile of the lower triangle (528 of 544 threads); thread (ti, tk) keeps the 4 x 4 tile rows 4 ti + b, cols 4 tk + a in
-// registers: on and below the diagonal it starts as A and, column by column, turns into B = the forward substitution
-// applied to I (L^-1 with unscaled rows).  Per column j only the pivot column (unscaled a_ij) and row j-1 of B travel
-// through shared memory (double buffered), so there is ONE barrier per column and no shared-memory read-modify-write:
-//   phase 1 (cols k > j, rows i >= k):  r -= a_ij a_kj / a_jj
-//   phase 2 (cols k < j, rows i > j-1): r  = r - (l_{i,j-1}/l_{j-1,j-1}) B[j-1][k]     (B[j-1][j-1] = 1)
-// Consecutive threads walk along a tile row, so the row vector is a broadcast and the column vector is contiguous.
+// K2: diagonal block, register resident, blocked by 4 columns.  One thread per 4 x 4 tile of the lower triangle (528 of 544
+// threads); thread (ti, tk) keeps rows 4 ti + b, cols 4 tk + a in registers: on and below the diagonal it starts as A and, panel
+// by panel, turns into B = the forward substitution applied to I (L^-1 with unscaled rows).  Per 4-column panel j4:
+//   (a) the diagonal tile's thread factors its 4 x 4 block locally and publishes L44 and the reciprocal pivots;   -- barrier
+//   (b) the tile-column owners (ti > j4, tk = j4) solve X L44^T = A for their 4 x 4 blocks and publish the 4 finished columns
+//       of L; the tile-row owners (ti = j4) finish their 4 rows of B locally and publish them;                      -- barrier
+//   (c) every tile below the panel applies a rank-4 update: A -= Lcol Lcol^T (tk > j4) or B -= (Lcol / piv) Brow (tk <= j4).
+// Two barriers and ~110 instructions per thread per FOUR columns; no shared-memory read-modify-write.  Positions above the
+// diagonal collect garbage and are never read.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PS = NB + 1;
 constexpr int PD_THREADS = 544;   // 17 warps >= 32*33/2 = 528 lower-triangle tiles
 
 __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, int kb, double* __restrict__ Linv,
-                                                             double* __restrict__ LinvT, int* __restrict__ info) {
+                                                                   double* __restrict__ LinvT, int* __restrict__ info) {
   extern __shared__ __align__(16) double sm[];
   double* Lf = sm;                       // [NB][PS] finished columns of L (for the coalesced write-back)
-  double* colbuf = Lf + NB * PS;         // [2][NB] pivot column, unscaled (NB*PS is even: 16-byte aligned)
-  double* rowbuf = colbuf + 2 * NB;      // [2][NB] row j-1 of B
-  double* scal = rowbuf + 2 * NB;        // [2][2]  {1/a_jj, 1/sqrt(a_jj)}
-  double* dg = scal + 4;                 // [NB] diag(L)
+  double* colbuf = Lf + NB * PS;         // [4][NB] the panel's finished columns of L        (NB*PS is even: 16-byte aligned)
+  double* rowbuf = colbuf + 4 * NB;      // [4][NB] the panel's finished rows of B
+  double* l44 = rowbuf + 4 * NB;         // [2][16] the panel's diagonal block of L (row-major, strictly lower used)
+  double* rinv4 = l44 + 32;              // [2][4]  reciprocal pivots
+  double* dg = rinv4 + 8;                // [NB] pivots (raw until the end, then sqrt)
   const int tid = threadIdx.x;
   int ti = (int)((sqrt(8.0 * (double)tid + 1.0) - 1.0) * 0.5);
   while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
   while (ti * (ti + 1) / 2 > tid) --ti;
   int tk = tid - ti * (ti + 1) / 2;
   const bool active = tid < 528;                     // tile (ti, tk), tk <= ti, of the lower triangle
-  if (!active) { ti = 64; tk = 64; }                 // matches no column / row: idle threads only join the barriers
+  if (!active) { ti = 64; tk = 64; }                 // matches no panel: idle threads only join the barriers
   double* Ab = A + ((int64_t)kb * NB) * ld + (int64_t)kb * NB;
   double r[4][4];
 #pragma unroll
@@ -55,80 +58,132 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
       const int i = 4 * ti + b, k = 4 * tk + a;
       r[b][a] = (active && k <= i) ? Ab[(int64_t)i * ld + k] : 0.0;
     }
-  double lprev[4] = {0.0, 0.0, 0.0, 0.0};
-  double rinv2_prev = 0.0;
-  // Branch-free inner step: both updates are plain FMAs over the whole tile.  Masks live in the broadcast vectors
-  // (lk = 0 for k <= j, lf = 0 for i <= jj, rowbuf = 0 for k > jj); the pivot column is zeroed by its owners after it
-  // is broadcast, so "B[i][jj] = -lf_i" is the same accumulate as every other column.  Positions above the diagonal
-  // collect garbage and are never read.  The column loop is unrolled by 4 so that every register index is static.
 #pragma unroll 1
   for (int j4 = 0; j4 < NB / 4; ++j4) {
+    const int par = j4 & 1;
+    double* L4 = l44 + par * 16;
+    double* R4 = rinv4 + par * 4;
+    // ---------------- (a) diagonal tile: local 4 x 4 Cholesky, its block of B, its rows of rowbuf ----------------
+    if (ti == j4 && tk == j4) {
+      double rs[4];
 #pragma unroll
-    for (int a0 = 0; a0 < 4; ++a0) {
-      const int j = 4 * j4 + a0, cur = a0 & 1, jj = j - 1;
-      const int bb = (a0 + 3) & 3, jj4 = a0 > 0 ? j4 : j4 - 1;       // row jj = 4 jj4 + bb
-      // ---- writers: pivot column j (unscaled), 1/a_jj, and row jj of B ----
-      if (tk == j4) {
+      for (int c = 0; c < 4; ++c) {
+        double d = r[c][c];
+        if (!(d > 0.0)) { atomicCAS(info, 0, kb * NB + 4 * j4 + c + 1); d = 1.0; }
+        dg[4 * j4 + c] = d;
+        rs[c] = rsqrt(d);
+        R4[c] = rs[c];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) colbuf[cur * NB + 4 * ti + b] = r[b][a0];
-        if (ti == j4) {
-          double d = r[a0][a0];
-          if (!(d > 0.0)) { atomicCAS(info, 0, kb * NB + j + 1); d = 1.0; }
-          const double rs = rsqrt(d);
-          *reinterpret_cast<double2*>(scal + cur * 2) = make_double2(rs * rs, rs);
-          dg[j] = d;                                            // sqrt is taken after the sweep, off the critical path
-        }
+        for (int b = 0; b < 4; ++b)
+          if (b > c) r[b][c] *= rs[c];                         // l_{b,c}
 #pragma unroll
-        for (int b = 0; b < 4; ++b) r[b][a0] = 0.0;
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            if (b > c && a > c && a <= b) r[b][a] = fma(-r[b][c], r[a][c], r[b][a]);
       }
-      if (ti == jj4) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (b > c) { L4[b * 4 + c] = r[b][c]; Lf[(4 * j4 + b) * PS + 4 * j4 + c] = r[b][c]; }
+      // unit-lower block of B:  B[b][a] = -( f(b,a) + sum_{l=a+1}^{b-1} f(b,l) B[l][a] ),  f(b,l) = l_{b,l} / l_{l,l}
+      double bt[4][4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bt[b][a] = 0.0;
+#pragma unroll
+      for (int b = 1; b < 4; ++b)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (a < b) {
+            double sacc = r[b][a] * rs[a];
+#pragma unroll
+            for (int l = 1; l < 4; ++l)
+              if (l > a && l < b) sacc = fma(r[b][l] * rs[l], bt[l][a], sacc);
+            bt[b][a] = -sacc;
+          }
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          const int k = 4 * tk + a;
-          rowbuf[cur * NB + k] = (k < jj) ? r[bb][a] : (k == jj ? 1.0 : 0.0);
+          r[b][a] = (a < b) ? bt[b][a] : 0.0;
+          rowbuf[b * NB + 4 * j4 + a] = (a < b) ? bt[b][a] : (a == b ? 1.0 : 0.0);
         }
+    }
+    __syncthreads();
+    // ---------------- (b) tile-column owners solve, tile-row owners finish their rows of B ----------------
+    if (tk == j4 && ti > j4) {
+      double x[4][4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double v = r[b][c];
+#pragma unroll
+          for (int c2 = 0; c2 < 4; ++c2)
+            if (c2 < c) v = fma(-x[b][c2], L4[c * 4 + c2], v);
+          x[b][c] = v * R4[c];
+        }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<double2*>(colbuf + c * NB + 4 * ti) = make_double2(x[0][c], x[1][c]);
+        *reinterpret_cast<double2*>(colbuf + c * NB + 4 * ti + 2) = make_double2(x[2][c], x[3][c]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { Lf[(4 * ti + b) * PS + 4 * j4 + c] = x[b][c]; r[b][c] = 0.0; }
       }
-      __syncthreads();
-      if (active) {
-        const double2 sc = *reinterpret_cast<const double2*>(scal + cur * 2);
-        const double rinv2 = sc.x, rinv = sc.y;
-        double li[4];
-        {
-          const double2 u = *reinterpret_cast<const double2*>(colbuf + cur * NB + 4 * ti);
-          const double2 v = *reinterpret_cast<const double2*>(colbuf + cur * NB + 4 * ti + 2);
-          li[0] = u.x; li[1] = u.y; li[2] = v.x; li[3] = v.y;
-        }
-        if (tk == j4) {                                         // finished column j of L
+    } else if (ti == j4 && tk < j4) {
+#pragma unroll
+      for (int b = 1; b < 4; ++b)
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if (l < b) {
+            const double f = L4[b * 4 + l] * R4[l];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) r[b][a] = fma(-f, r[l][a], r[b][a]);
+          }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        *reinterpret_cast<double2*>(rowbuf + b * NB + 4 * tk) = make_double2(r[b][0], r[b][1]);
+        *reinterpret_cast<double2*>(rowbuf + b * NB + 4 * tk + 2) = make_double2(r[b][2], r[b][3]);
+      }
+    }
+    __syncthreads();
+    // ---------------- (c) rank-4 update of every tile below the panel ----------------
+    if (active && ti > j4) {
+      double li[4][4];                                       // li[c][b] = L[4 ti + b][4 j4 + c]
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double2 u = *reinterpret_cast<const double2*>(colbuf + c * NB + 4 * ti);
+        const double2 v = *reinterpret_cast<const double2*>(colbuf + c * NB + 4 * ti + 2);
+        li[c][0] = u.x; li[c][1] = u.y; li[c][2] = v.x; li[c][3] = v.y;
+      }
+      if (tk > j4) {                                         // Cholesky: A -= Lcol Lcol^T
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double2 u = *reinterpret_cast<const double2*>(colbuf + c * NB + 4 * tk);
+          const double2 v = *reinterpret_cast<const double2*>(colbuf + c * NB + 4 * tk + 2);
+          const double lk[4] = {u.x, u.y, v.x, v.y};
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            if (4 * ti + b > j) Lf[(4 * ti + b) * PS + j] = li[b] * rinv;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) r[b][a] = fma(-li[c][b], lk[a], r[b][a]);
         }
-        if (tk > j4 || (tk == j4 && a0 < 3)) {                  // Cholesky rank-1 update of the columns k > j
-          const double2 u = *reinterpret_cast<const double2*>(colbuf + cur * NB + 4 * tk);
-          const double2 v = *reinterpret_cast<const double2*>(colbuf + cur * NB + 4 * tk + 2);
-          double lk[4] = {u.x * rinv2, u.y * rinv2, v.x * rinv2, v.y * rinv2};
+      } else {                                               // forward substitution on I: B -= (Lcol / piv) Brow
 #pragma unroll
-          for (int a = 0; a < 4; ++a) lk[a] = (tk > j4 || a > a0) ? lk[a] : 0.0;
+        for (int c = 0; c < 4; ++c) {
+          const double rc = R4[c];
+          const double2 u = *reinterpret_cast<const double2*>(rowbuf + c * NB + 4 * tk);
+          const double2 v = *reinterpret_cast<const double2*>(rowbuf + c * NB + 4 * tk + 2);
+          const double bj[4] = {u.x, u.y, v.x, v.y};
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) {
+            const double f = li[c][b] * rc;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) r[b][a] = fma(-li[b], lk[a], r[b][a]);
+            for (int a = 0; a < 4; ++a) r[b][a] = fma(-f, bj[a], r[b][a]);
+          }
         }
-        if (tk <= jj4 && (ti > jj4 || (ti == jj4 && bb < 3))) { // forward substitution on I with column jj
-          const double2 w = *reinterpret_cast<const double2*>(rowbuf + cur * NB + 4 * tk);
-          const double2 x = *reinterpret_cast<const double2*>(rowbuf + cur * NB + 4 * tk + 2);
-          const double bj[4] = {w.x, w.y, x.x, x.y};
-          double lf[4];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) lf[b] = (ti > jj4 || b > bb) ? lprev[b] * rinv2_prev : 0.0;   // l_{i,jj} / l_{jj,jj}
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) r[b][a] = fma(-lf[b], bj[a], r[b][a]);
-        }
-#pragma unroll
-        for (int b = 0; b < 4; ++b) lprev[b] = li[b];
-        rinv2_prev = rinv2;
       }
     }
   }
@@ -290,7 +345,7 @@ constexpr int OB = 4;   // outer panel = 4 inner panels = 512 columns
 
 cudaError_t launch_cholesky(b200bo_handle_s* h) {
   const int nblk = (int)(h->Np / NB);
-  const size_t sm_potrf = (size_t)(NB * PS + 2 * NB + 2 * NB + 4 + NB) * sizeof(double);
+  const size_t sm_potrf = (size_t)(NB * PS + 4 * NB + 4 * NB + 32 + 8 + NB) * sizeof(double);
   cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf);
   cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
   cudaFuncSetAttribute(syrk_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);

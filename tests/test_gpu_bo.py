@@ -18,10 +18,10 @@ def test_acquire_max_known_answer():
     model = bo.B200GPE.from_data([1.0], [2.0], bo.MeanZero(), bo.SEIso(1.0, 0.0))
     ac = bo.MaxMean()
     opt = bo.nlopt_setup(ac, model, [-5.0], [5.0], {**bo.defaultoptions(type(model), type(ac)), "maxtime": 3.0,
-                                                    "ftol_abs": np.finfo(float).eps})
+                                                    "ftol_abs": np.finfo(float).eps, "rng": np.random.default_rng(7)})
     assert opt.maxeval == 2000 and opt.maxtime == 3.0 and opt.ftol_abs == np.finfo(float).eps
     maxf, maxx = bo.acquire_max(opt, [-5.0], [5.0], 10)
-    assert maxx == pytest.approx([1.0], abs=1e-5)
+    assert maxx == pytest.approx([1.0], abs=1e-6)
     assert maxf == pytest.approx(2.0 / (1.0 + np.exp(-4.0) + orc.EPS), rel=1e-9)
 
 
