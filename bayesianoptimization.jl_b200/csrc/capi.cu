@@ -35,11 +35,11 @@ int num_params(const b200bo_handle_s* h) {
 }
 
 void free_device(b200bo_handle_s* h) {
-  cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dz); cudaFree(h->dinv_ell);
+  cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dZk); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dz); cudaFree(h->dinv_ell);
   cudaFree(h->dL); cudaFree(h->dLinv); cudaFree(h->dLinvT); cudaFree(h->dV); cudaFree(h->dscal); cudaFree(h->dinfo);
   cudaFree(h->dcta_best); cudaFree(h->dbest); cudaFree(h->dpart);
   h->dz = nullptr;
-  h->dX = h->dZ = h->dy = h->dw = h->dalpha = h->dinv_ell = h->dL = h->dLinv = h->dLinvT = h->dV = h->dscal = h->dpart = nullptr;
+  h->dX = h->dZ = h->dZk = h->dy = h->dw = h->dalpha = h->dinv_ell = h->dL = h->dLinv = h->dLinvT = h->dV = h->dscal = h->dpart = nullptr;
   h->dinfo = nullptr; h->dcta_best = nullptr; h->dbest = nullptr;
 }
 
@@ -52,6 +52,7 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   const int64_t T = cap / 64;
   CU(cudaMalloc(&h->dX, sizeof(double) * cap * h->D));
   CU(cudaMalloc(&h->dZ, sizeof(double) * cap * h->D));
+  CU(cudaMalloc(&h->dZk, sizeof(double) * (cap / 64) * (8 * ((h->D + 3) / 4) + 2) * 64));
   CU(cudaMalloc(&h->dy, sizeof(double) * cap));
   CU(cudaMalloc(&h->dw, sizeof(double) * cap));
   CU(cudaMalloc(&h->dalpha, sizeof(double) * cap));
@@ -69,6 +70,7 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   CU(cudaMalloc(&h->dpart, sizeof(double) * T * T * 35));
   CU(cudaMemsetAsync(h->dX, 0, sizeof(double) * cap * h->D, h->stream));
   CU(cudaMemsetAsync(h->dZ, 0, sizeof(double) * cap * h->D, h->stream));
+  CU(cudaMemsetAsync(h->dZk, 0, sizeof(double) * (cap / 64) * (8 * ((h->D + 3) / 4) + 2) * 64, h->stream));
   CU(cudaMemsetAsync(h->dalpha, 0, sizeof(double) * cap, h->stream));
   CU(cudaMemsetAsync(h->dy, 0, sizeof(double) * cap, h->stream));
   CU(make_tensor_maps(h));

@@ -42,6 +42,30 @@ __device__ __forceinline__ double exp_neg(double x) {
   return x != x ? x : res;
 }
 
+// exp(x) * T[0] for x <= 0 with a 16-entry table T[j] = c * 2^(j/16) (shared memory; c folds a constant factor in):
+// n = rint(16 x log2 e), x = n ln2/16 + r, |r| <= ln2/32, degree-7 Taylor polynomial (truncation 1.2e-18), 2^(n>>4) added into
+// the exponent field.  12 FP64 instructions (exp_neg: 17).  x < -670 -> 0 (keeps c in [2^-40, 2^40] clear of denormals).
+__device__ __forceinline__ double exp_neg16(double x, const double* __restrict__ T) {
+  const double MAGIC = 6755399441055744.0;
+  const double t = fma(x, 23.083120654223414, MAGIC);           // 16 / ln 2
+  const int n = __double2loint(t);
+  const double fn = t - MAGIC;
+  double r = fma(fn, -4.33216987730702385306e-02, x);            // ln2_hi / 16
+  r = fma(fn, -1.19263433079411731251e-11, r);                   // ln2_lo / 16
+  double p = 1.984126984126984e-04;             // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  p *= T[n & 15];
+  double res = __hiloint2double(__double2hiint(p) + ((n >> 4) << 20), __double2loint(p));
+  res = x < -670.0 ? 0.0 : res;
+  return x != x ? x : res;
+}
+
 template <int FAM>
 __device__ __forceinline__ double kern_phi(double r2) {
   if (FAM == FAM_SE) return exp_neg(-0.5 * r2);

@@ -30,6 +30,7 @@ struct b200bo_handle_s {
   // device buffers
   double* dX = nullptr;      // [cap][D] raw inputs (point-major == D x N column-major)
   double* dZ = nullptr;      // [cap][D] inputs scaled by 1/l_d
+  double* dZk = nullptr;     // [cap/64] K1 staging blocks (kmat.cu): DMMA fragment order of z for 64 points as tile rows / cols + |z|^2/2
   double* dy = nullptr;      // [cap]
   double* dw = nullptr;      // [cap] work vector for the single-RHS solves
   double* dalpha = nullptr;  // [cap] (zero in the padding)
