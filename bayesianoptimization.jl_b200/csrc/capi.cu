@@ -71,6 +71,8 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   CU(cudaMemsetAsync(h->dX, 0, sizeof(double) * cap * h->D, h->stream));
   CU(cudaMemsetAsync(h->dZ, 0, sizeof(double) * cap * h->D, h->stream));
   CU(cudaMemsetAsync(h->dZk, 0, sizeof(double) * (cap / 64) * (8 * ((h->D + 3) / 4) + 2) * 64, h->stream));
+  CU(cudaMemsetAsync(h->dLinv, 0, sizeof(double) * nb * NB * NB, h->stream));     // K2 writes one triangle of each block only
+  CU(cudaMemsetAsync(h->dLinvT, 0, sizeof(double) * nb * NB * NB, h->stream));
   CU(cudaMemsetAsync(h->dalpha, 0, sizeof(double) * cap, h->stream));
   CU(cudaMemsetAsync(h->dy, 0, sizeof(double) * cap, h->stream));
   CU(make_tensor_maps(h));

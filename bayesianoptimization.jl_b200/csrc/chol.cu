@@ -14,207 +14,283 @@
 //   Two-level blocking: inner panels of 128 inside outer panels of 512; the update right of an outer panel is one K = 512
 //   launch.  Look-ahead: the next outer panel is factorised on the handle's stream while the far part of the previous
 //   K = 512 update runs on a second stream.
+#include <cstdio>
+#include <cstring>
 #include "tma.cuh"
 #include "handle.h"
 
 namespace b200bo {
 
 // ------------------------------------------------------------------------------------------------------------
-// K2: diagonal block, register resident, blocked by 4 columns.  One thread per 4 x 4 tile of the lower triangle (528 of 544
-// threads); thread (ti, tk) keeps rows 4 ti + b, cols 4 tk + a in registers: on and below the diagonal it starts as A and, panel
-// by panel, turns into B = the forward substitution applied to I (L^-1 with unscaled rows).  Per 4-column panel j4:
-//   (a) the diagonal tile's thread factors its 4 x 4 block locally and publishes L44 and the reciprocal pivots;   -- barrier
-//   (b) the tile-column owners (ti > j4, tk = j4) solve X L44^T = A for their 4 x 4 blocks and publish the 4 finished columns
-//       of L; the tile-row owners (ti = j4) finish their 4 rows of B locally and publish them;                      -- barrier
-//   (c) every tile below the panel applies a rank-4 update: A -= Lcol Lcol^T (tk > j4) or B -= (Lcol / piv) Brow (tk <= j4).
-// Two barriers and ~110 instructions per thread per FOUR columns; no shared-memory read-modify-write.  Positions above the
-// diagonal collect garbage and are never read.
+// K2: diagonal block (128 x 128) by ONE 256-thread CTA, latency-first.  The block lives in shared memory (row stride 132 doubles:
+// DMMA fragment loads are conflict-free); it is factored in four 32-column sub-panels:
+//   F(s)   warp 0 factors the 32 x 32 diagonal sub-block in REGISTERS (lane = row, columns exchanged by shuffles: no barrier, no
+//          shared-memory round trip on the 128-column dependency chain), while warps 1-7 finish the far part U2(s-1) of the
+//          previous rank-32 update (look-ahead);
+//   T(s)   warps 1-3: one thread per row below solves X L11^T = A21 by substitution; warp 4 inverts L11 (lane = column);
+//   U1(s)  all warps: rank-32 update of the NEXT sub-panel's 32 columns on the FP64 tensor pipe (DMMA.8x8x4, K = 32).
+// Then the off-diagonal blocks of L^-1 (W_ij = -W_ii sum_k L_ik W_kj) as 32^3 DMMA products, and a coalesced write-back of the
+// mirrored factor block, L^-1 and L^-T.  Shared-memory image: lower triangle = L, strictly upper triangle = (L^-1)^T, rinv = 1/l_ii.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int PS = NB + 1;
-constexpr int PD_THREADS = 544;   // 17 warps >= 32*33/2 = 528 lower-triangle tiles
+constexpr int PLD = 132;                 // shared-memory row stride of the block (doubles)
+constexpr int PD_THREADS = 256;
+constexpr int PSUB = 32;                 // sub-panel width
+constexpr size_t PD_SMEM = (size_t)(NB * PLD + PSUB * PSUB + 3 * PSUB * PSUB + 2 * NB + 2 * PSUB + 2) * sizeof(double);
+
+#ifdef POTRF_PROF
+__device__ unsigned long long g_potrf_prof[16];
+#define PROF_T(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); g_potrf_prof[i] += (unsigned long long)(_t - t_prev); t_prev = _t; } } while (0)
+#else
+#define PROF_T(i) do {} while (0)
+#endif
+
+// C(8x8 at rows r0, cols q0 of S) -= sum_{k < 32} S[r0 + .][k0 + k] * S[q0 + .][k0 + k]   (one warp; the k-steps are split into
+// two independent accumulator chains: the DMMA dependent-issue latency, not its throughput, bounds a single tile)
+__device__ __forceinline__ void rank32_tile(double* __restrict__ S, int r0, int q0, int k0, int g, int q) {
+  double2* cp = reinterpret_cast<double2*>(S + (r0 + g) * PLD + q0 + 2 * q);
+  double2 c = *cp;
+  double e0 = 0.0, e1 = 0.0;
+  const double* ap = S + (r0 + g) * PLD + k0 + q;
+  const double* bp = S + (q0 + g) * PLD + k0 + q;
+#pragma unroll
+  for (int ks = 0; ks < PSUB / 4; ks += 2) {
+    dmma884(c.x, c.y, -ap[4 * ks], bp[4 * ks]);
+    dmma884(e0, e1, -ap[4 * ks + 4], bp[4 * ks + 4]);
+  }
+  c.x += e0; c.y += e1;
+  *cp = c;
+}
+
+// 1/d and 1/sqrt(d) for d > 0 (normal range): MUFU seed + ONE cubically convergent step (3 dependent FP64 operations instead of
+// the 8 of the library routines -- these sit on the 128-column dependency chain of the diagonal block)
+__device__ __forceinline__ double fast_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-d, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = d * y;
+  const double e = fma(-h, y, 1.0);                  // 1 - d y^2
+  const double t = fma(e, 0.375, 0.5) * e;           // e/2 + 3 e^2 / 8
+  return fma(y, t, y);
+}
+
+// Block row i (1..3) of W = L^-1:  W_ij = -W_ii sum_{k=j}^{i-1} L_ik W_kj for j < i, as 32^3 DMMA products by `nw` warps (this warp
+// is worker `wid`); `named` selects the barrier between the two product phases (warps 1-7 only, or the whole CTA).
+// W[r][c] (r >= c) is kept at S[c][r] (the diagonal of S holds w_rr = 1/l_rr); L[r][c] (r > c) at S[r][c].
+__device__ __forceinline__ void winv_block_row(double* __restrict__ S, double* __restrict__ Pb, int i, int wid, int nw, bool named, int g,
+                                               int q) {
+  // P_j = sum_k L_ik W_kj  (32 x 32, K = 32 (i - j)); two accumulator chains per 8 x 8 tile
+  for (int t = wid; t < i * 16; t += nw) {
+    const int j = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
+    double c0a = 0.0, c1a = 0.0, e0a = 0.0, e1a = 0.0;
+    const double* lrow = S + (PSUB * i + 8 * tr + g) * PLD + q;     // L[r][kk + q]
+    const int cw = PSUB * j + 8 * tc + g;                            // column of W_kj read by this lane as B[k = q][n = g]
+    const double* wcol = S + cw * PLD + q;                           // W[kk + q][cw]
+#pragma unroll
+    for (int kk = PSUB * j; kk < PSUB * j + PSUB; kk += 8) {         // k = j: W_jj is lower triangular
+      const double w0 = wcol[kk], w1 = wcol[kk + 4];
+      dmma884(c0a, c1a, lrow[kk], (kk + q >= cw) ? w0 : 0.0);
+      dmma884(e0a, e1a, lrow[kk + 4], (kk + 4 + q >= cw) ? w1 : 0.0);
+    }
+#pragma unroll 2
+    for (int kk = PSUB * (j + 1); kk < PSUB * i; kk += 8) {          // k > j: full blocks
+      dmma884(c0a, c1a, lrow[kk], wcol[kk]);
+      dmma884(e0a, e1a, lrow[kk + 4], wcol[kk + 4]);
+    }
+    double* pp = Pb + (j * PSUB + 8 * tr + g) * PSUB + 8 * tc + 2 * q;
+    *reinterpret_cast<double2*>(pp) = make_double2(c0a + e0a, c1a + e1a);
+  }
+  if (named) asm volatile("bar.sync 1, 224;\n" ::: "memory"); else __syncthreads();
+  // W_ij = -W_ii P_j, stored transposed into the upper triangle
+  for (int t = wid; t < i * 16; t += nw) {
+    const int j = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
+    double c0a = 0.0, c1a = 0.0, e0a = 0.0, e1a = 0.0;
+    const int r = PSUB * i + 8 * tr + g;
+    const double* pcol = Pb + (j * PSUB + q) * PSUB + 8 * tc + g;    // P_j[kk + q][8 tc + g]
+#pragma unroll
+    for (int kk = 0; kk < PSUB; kk += 8) {
+      const int k0 = PSUB * i + kk + q;
+      const double w0 = S[k0 * PLD + r], w1 = S[(k0 + 4) * PLD + r]; // W_ii[r][k] at S[k][r], lower triangular
+      dmma884(c0a, c1a, (r >= k0) ? -w0 : 0.0, pcol[kk * PSUB]);
+      dmma884(e0a, e1a, (r >= k0 + 4) ? -w1 : 0.0, pcol[(kk + 4) * PSUB]);
+    }
+    const int cc = PSUB * j + 8 * tc + 2 * q;
+    S[cc * PLD + r] = c0a + e0a;
+    S[(cc + 1) * PLD + r] = c1a + e1a;
+  }
+}
 
 __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __restrict__ A, int64_t ld, int kb, double* __restrict__ Linv,
                                                                    double* __restrict__ LinvT, int* __restrict__ info) {
   extern __shared__ __align__(16) double sm[];
-  double* Lf = sm;                       // [NB][PS] finished columns of L (for the coalesced write-back)
-  double* colbuf = Lf + NB * PS;         // [4][NB] the panel's finished columns of L        (NB*PS is even: 16-byte aligned)
-  double* rowbuf = colbuf + 4 * NB;      // [4][NB] the panel's finished rows of B
-  double* l44 = rowbuf + 4 * NB;         // [2][16] the panel's diagonal block of L (row-major, strictly lower used)
-  double* rinv4 = l44 + 32;              // [2][4]  reciprocal pivots
-  double* dg = rinv4 + 8;                // [NB] pivots (raw until the end, then sqrt)
-  const int tid = threadIdx.x;
-  int ti = (int)((sqrt(8.0 * (double)tid + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
-  while (ti * (ti + 1) / 2 > tid) --ti;
-  int tk = tid - ti * (ti + 1) / 2;
-  const bool active = tid < 528;                     // tile (ti, tk), tk <= ti, of the lower triangle
-  if (!active) { ti = 64; tk = 64; }                 // matches no panel: idle threads only join the barriers
+  double* S = sm;                          // [NB][PLD]
+  double* Mt = S + NB * PLD;               // [32][32] current diagonal sub-block, scaled and transposed: Mt[c*32 + r] = l_rc / l_cc
+  double* Pb = Mt + PSUB * PSUB;           // [3][32][32] products of the block inverse
+  double* rinv = Pb + 3 * PSUB * PSUB;     // [NB] 1 / l_ii
+  double* ldiag = rinv + NB;               // [NB] l_ii
+  double* cb = ldiag + NB;                 // [2][32] column exchange buffer of F(s)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(cb + 2 * PSUB);
+  const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler
   double* Ab = A + ((int64_t)kb * NB) * ld + (int64_t)kb * NB;
-  double r[4][4];
-#pragma unroll
-  for (int b = 0; b < 4; ++b)
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int i = 4 * ti + b, k = 4 * tk + a;
-      r[b][a] = (active && k <= i) ? Ab[(int64_t)i * ld + k] : 0.0;
-    }
+#ifdef POTRF_PROF
+  long long t_prev = clock64();
+#endif
+  // ---- load the lower triangle: one 1-D TMA bulk copy per row (the strictly upper part is never read before it is written) ----
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(8 * (NB / 2) * (NB / 2 + 1) * 2));   // sum_i 8 * ((i + 2) & ~1)
+  __syncthreads();
+  if (tid < NB) {
+    const uint32_t bytes = (uint32_t)(((tid + 2) & ~1) * 8);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(S + tid * PLD)),
+                 "l"(Ab + (int64_t)tid * ld), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
+  mbar_wait(bar, 0);
+  PROF_T(0);
 #pragma unroll 1
-  for (int j4 = 0; j4 < NB / 4; ++j4) {
-    const int par = j4 & 1;
-    double* L4 = l44 + par * 16;
-    double* R4 = rinv4 + par * 4;
-    // ---------------- (a) diagonal tile: local 4 x 4 Cholesky, its block of B, its rows of rowbuf ----------------
-    if (ti == j4 && tk == j4) {
-      double rs[4];
+  for (int s = 0; s < NB / PSUB; ++s) {
+    const int c0 = s * PSUB;
+    if (warp == 0) {
+      // ---------------- F(s): 32 x 32 factorisation in registers, lane = row, square-root free on the chain ----------------
+      // a[j] holds the UNSCALED column c_ij = l_ij sqrt(d_j); the update is a_ik -= c_ij (c_kj / d_j).  The only serial chain is
+      // d_j -> 1/d_j -> d_{j+1} (the diagonal stays in the owning lane); the scaled column c_kj / d_j reaches the other lanes
+      // through a 2 x 32 shared-memory buffer (one STS + broadcast LDS.128 instead of 31 shuffle pairs per column).
+      double a[PSUB];
+      const double* row = S + (c0 + lane) * PLD + c0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        double d = r[c][c];
-        if (!(d > 0.0)) { atomicCAS(info, 0, kb * NB + 4 * j4 + c + 1); d = 1.0; }
-        dg[4 * j4 + c] = d;
-        rs[c] = rsqrt(d);
-        R4[c] = rs[c];
+      for (int j = 0; j < PSUB; j += 2) { const double2 v = *reinterpret_cast<const double2*>(row + j); a[j] = v.x; a[j + 1] = v.y; }
+      double dg = 0.0;                                 // this lane's diagonal element, fully updated once column lane-1 is done
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (b > c) r[b][c] *= rs[c];                         // l_{b,c}
+      for (int j = 0; j < PSUB; ++j) if (j == lane) dg = a[j];
+      double my_rs = 1.0, my_d = 1.0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+      for (int j = 0; j < PSUB; ++j) {
+        double d = __shfl_sync(0xffffffffu, dg, j);
+        if (!(d > 0.0)) { if (lane == 0) atomicCAS(info, 0, kb * NB + c0 + j + 1); d = 1.0; }
+        const double rc = fast_rcp(d);
+        double* cbj = cb + (j & 1) * PSUB;
+        cbj[lane] = a[j] * rc;                        // c_ij / d_j
+        if (lane == j) { my_d = d; my_rs = fast_rsqrt(d); }
+        dg = fma(-(a[j] * a[j]), rc, dg);             // lanes i > j (a[j]^2 is ready before rc is)
+        __syncwarp();
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
-            if (b > c && a > c && a <= b) r[b][a] = fma(-r[b][c], r[a][c], r[b][a]);
-      }
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (b > c) { L4[b * 4 + c] = r[b][c]; Lf[(4 * j4 + b) * PS + 4 * j4 + c] = r[b][c]; }
-      // unit-lower block of B:  B[b][a] = -( f(b,a) + sum_{l=a+1}^{b-1} f(b,l) B[l][a] ),  f(b,l) = l_{b,l} / l_{l,l}
-      double bt[4][4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) bt[b][a] = 0.0;
-#pragma unroll
-      for (int b = 1; b < 4; ++b)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (a < b) {
-            double sacc = r[b][a] * rs[a];
-#pragma unroll
-            for (int l = 1; l < 4; ++l)
-              if (l > a && l < b) sacc = fma(r[b][l] * rs[l], bt[l][a], sacc);
-            bt[b][a] = -sacc;
-          }
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          r[b][a] = (a < b) ? bt[b][a] : 0.0;
-          rowbuf[b * NB + 4 * j4 + a] = (a < b) ? bt[b][a] : (a == b ? 1.0 : 0.0);
+        for (int k = (j + 1) & ~1; k < PSUB; k += 2) {
+          const double2 m = *reinterpret_cast<const double2*>(cbj + k);
+          if (k > j) a[k] = fma(-a[j], m.x, a[k]);    // meaningful for lanes i > k
+          a[k + 1] = fma(-a[j], m.y, a[k + 1]);
         }
+      }
+      rinv[c0 + lane] = my_rs;
+      ldiag[c0 + lane] = my_d * my_rs;                // l_ii = sqrt(d_i)
+      __syncwarp();
+      double* wrow = S + (c0 + lane) * PLD + c0;
+#pragma unroll
+      for (int j = 0; j < PSUB; ++j) {
+        const double rj = rinv[c0 + j];
+        const double l = a[j] * rj;                   // l_ij
+        if (j < lane) wrow[j] = l;
+        Mt[j * PSUB + lane] = (j < lane) ? l * rj : 0.0;
+      }
+      wrow[lane] = my_rs;                             // the diagonal of S carries w_ii = 1 / l_ii
+    } else {
+      if (s > 0) {
+        // ---------------- U2(s-1): far part of the previous rank-32 update (columns >= c0 + 32) ----------------
+        const int k0 = c0 - PSUB, t0 = (c0 + PSUB) / 8, n = NB / 8 - t0;     // tile rows/cols t0 .. 15
+        for (int t = warp - 1; t < n * (n + 1) / 2; t += PD_THREADS / 32 - 1) {
+          int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+          while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+          while (ti * (ti + 1) / 2 > t) --ti;
+          const int tj = t - ti * (ti + 1) / 2;
+          rank32_tile(S, 8 * (t0 + ti), 8 * (t0 + tj), k0, g, q);
+        }
+      }
+      // block row s-1 of L^-1 (needs the inverses of diagonal sub-blocks 0 .. s-1): hidden behind F(s)
+      if (s >= 2) winv_block_row(S, Pb, s - 1, warp - 1, PD_THREADS / 32 - 1, true, g, q);
+    }
+#ifdef POTRF_PROF
+    if (threadIdx.x == 0) g_potrf_prof[8 + s] += (unsigned long long)(clock64() - t_prev);      // warp 0's own F(s) time
+#endif
+    __syncthreads();
+    PROF_T(1);
+    // ---------------- T(s): rows below (warps 1-3) and the inverse of L11 (warp 4); one FMA per column on either chain --------
+    if (warp >= 1 && warp <= 3) {
+      const int r = c0 + PSUB + (tid - 32);
+      if (r < NB) {
+        double y[PSUB];                               // y_c = x_c l_cc:  y_c2 -= y_c (l_c2,c / l_cc)
+        double* row = S + r * PLD + c0;
+#pragma unroll
+        for (int j = 0; j < PSUB; j += 2) { const double2 v = *reinterpret_cast<const double2*>(row + j); y[j] = v.x; y[j + 1] = v.y; }
+#pragma unroll
+        for (int c = 0; c < PSUB; ++c) {
+#pragma unroll
+          for (int c2 = c + 1; c2 < PSUB; ++c2) y[c2] = fma(-y[c], Mt[c * PSUB + c2], y[c2]);
+        }
+#pragma unroll
+        for (int j = 0; j < PSUB; j += 2)
+          *reinterpret_cast<double2*>(row + j) = make_double2(y[j] * rinv[c0 + j], y[j + 1] * rinv[c0 + j + 1]);
+      }
+    } else if (warp == 4) {
+      // W = L11^-1, lane = column c:  v_k = w_k l_kk = (k == c) ? 1 : nacc_k,   nacc_i -= (l_ik / l_kk) v_k   (v_k = 0 for k < c)
+      double nacc[PSUB];
+#pragma unroll
+      for (int i = 0; i < PSUB; ++i) nacc[i] = 0.0;
+      double* wrow = S + (c0 + lane) * PLD + c0;      // (W^T)[c][i] = W[i][c] -> strictly upper part of row c
+#pragma unroll
+      for (int k = 0; k < PSUB; ++k) {
+        const double vk = (k == lane) ? 1.0 : nacc[k];
+        if (k > lane) wrow[k] = vk * rinv[c0 + k];
+#pragma unroll
+        for (int i = k + 1; i < PSUB; ++i) nacc[i] = fma(-Mt[k * PSUB + i], vk, nacc[i]);
+      }
     }
     __syncthreads();
-    // ---------------- (b) tile-column owners solve, tile-row owners finish their rows of B ----------------
-    if (tk == j4 && ti > j4) {
-      double x[4][4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          double v = r[b][c];
-#pragma unroll
-          for (int c2 = 0; c2 < 4; ++c2)
-            if (c2 < c) v = fma(-x[b][c2], L4[c * 4 + c2], v);
-          x[b][c] = v * R4[c];
-        }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        *reinterpret_cast<double2*>(colbuf + c * NB + 4 * ti) = make_double2(x[0][c], x[1][c]);
-        *reinterpret_cast<double2*>(colbuf + c * NB + 4 * ti + 2) = make_double2(x[2][c], x[3][c]);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) { Lf[(4 * ti + b) * PS + 4 * j4 + c] = x[b][c]; r[b][c] = 0.0; }
+    PROF_T(2);
+    // ---------------- U1(s): rank-32 update of the next sub-panel's columns ----------------
+    if (s + 1 < NB / PSUB) {
+      const int t0 = (c0 + PSUB) / 8, nr = NB / 8 - t0;                    // tile rows t0 .. 15, tile cols t0 .. t0 + 3
+      const int ntile = 10 + 4 * (nr - 4);
+      for (int t = warp; t < ntile; t += PD_THREADS / 32) {
+        int ti, tj;
+        if (t < 10) { ti = (t >= 6) ? 3 : (t >= 3) ? 2 : (t >= 1) ? 1 : 0; tj = t - ti * (ti + 1) / 2; }
+        else { ti = 4 + ((t - 10) >> 2); tj = (t - 10) & 3; }
+        rank32_tile(S, 8 * (t0 + ti), 8 * (t0 + tj), c0, g, q);
       }
-    } else if (ti == j4 && tk < j4) {
-#pragma unroll
-      for (int b = 1; b < 4; ++b)
-#pragma unroll
-        for (int l = 0; l < 4; ++l)
-          if (l < b) {
-            const double f = L4[b * 4 + l] * R4[l];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) r[b][a] = fma(-f, r[l][a], r[b][a]);
-          }
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        *reinterpret_cast<double2*>(rowbuf + b * NB + 4 * tk) = make_double2(r[b][0], r[b][1]);
-        *reinterpret_cast<double2*>(rowbuf + b * NB + 4 * tk + 2) = make_double2(r[b][2], r[b][3]);
-      }
+      __syncthreads();
     }
-    __syncthreads();
-    // ---------------- (c) rank-4 update of every tile below the panel ----------------
-    if (active && ti > j4) {
-      double li[4][4];                                       // li[c][b] = L[4 ti + b][4 j4 + c]
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double2 u = *reinterpret_cast<const double2*>(colbuf + c * NB + 4 * ti);
-        const double2 v = *reinterpret_cast<const double2*>(colbuf + c * NB + 4 * ti + 2);
-        li[c][0] = u.x; li[c][1] = u.y; li[c][2] = v.x; li[c][3] = v.y;
-      }
-      if (tk > j4) {                                         // Cholesky: A -= Lcol Lcol^T
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double2 u = *reinterpret_cast<const double2*>(colbuf + c * NB + 4 * tk);
-          const double2 v = *reinterpret_cast<const double2*>(colbuf + c * NB + 4 * tk + 2);
-          const double lk[4] = {u.x, u.y, v.x, v.y};
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int a = 0; a < 4; ++a) r[b][a] = fma(-li[c][b], lk[a], r[b][a]);
-        }
-      } else {                                               // forward substitution on I: B -= (Lcol / piv) Brow
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double rc = R4[c];
-          const double2 u = *reinterpret_cast<const double2*>(rowbuf + c * NB + 4 * tk);
-          const double2 v = *reinterpret_cast<const double2*>(rowbuf + c * NB + 4 * tk + 2);
-          const double bj[4] = {u.x, u.y, v.x, v.y};
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const double f = li[c][b] * rc;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) r[b][a] = fma(-f, bj[a], r[b][a]);
-          }
-        }
-      }
-    }
+    PROF_T(3);
   }
+  // ---------------- the last block row of L^-1 ----------------
+  winv_block_row(S, Pb, NB / PSUB - 1, warp, PD_THREADS / 32, false, g, q);
   __syncthreads();
-  if (tid < NB) dg[tid] = sqrt(dg[tid]);
-  // the last column (jj = NB - 1) has no rows below it: nothing left for phase 2
-  __syncthreads();
-  // ---- L^-1 and its transpose straight from the registers: Linv[i][k] = B[i][k] / l_ii ----
-  double* Li = Linv + (int64_t)kb * NB * NB;
-  double* LiT = LinvT + (int64_t)kb * NB * NB;
-  if (active) {
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = 4 * ti + b;
-      const double inv_i = 1.0 / dg[i];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int k = 4 * tk + a;
-        const double y = (k < i) ? r[b][a] * inv_i : (k == i ? inv_i : 0.0);
-        Li[i * NB + k] = y;
-        LiT[k * NB + i] = y;
-        if (ti != tk) { Li[k * NB + i] = 0.0; LiT[i * NB + k] = 0.0; }     // the strictly upper tile of L^-1 is zero
-      }
+  PROF_T(4);
+  // ---------------- write-back: mirrored factor block (full), L^-1 (lower) and L^-T (upper); the other triangles of the inverse
+  // buffers are zero from allocation and never written.  Every warp store = 4 rows x 64 bytes. ----------------
+  {
+    double* Li = Linv + (int64_t)kb * NB * NB;
+    double* LiT = LinvT + (int64_t)kb * NB * NB;
+    const int il = lane >> 3, cl = lane & 7;
+#pragma unroll 4
+    for (int pt = warp; pt < (NB / 4) * (NB / 8); pt += PD_THREADS / 32) {
+      const int i = 4 * (pt >> 4) + il, c = 8 * (pt & 15) + cl;
+      const int hi = i >= c ? i : c, lo = i >= c ? c : i;
+      const double lv = (i == c) ? ldiag[i] : S[hi * PLD + lo];   // L[max][min]
+      const double wv = S[lo * PLD + hi];                          // W[max][min]
+      Ab[(int64_t)i * ld + c] = lv;
+      if (i >= c) Li[i * NB + c] = wv;                // W[i][c]
+      if (i <= c) LiT[i * NB + c] = wv;               // (W^T)[i][c] = W[c][i]
     }
   }
-  // ---- mirrored factor block ----
-  for (int e = tid; e < NB * NB; e += PD_THREADS) {
-    const int i = e >> 7, c = e & 127;
-    const int lo = i < c ? i : c, hi = i < c ? c : i;
-    Ab[(int64_t)i * ld + c] = (i == c) ? dg[i] : Lf[hi * PS + lo];
-  }
+#ifdef POTRF_PROF
+  __syncthreads();
+  PROF_T(5);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -345,7 +421,7 @@ constexpr int OB = 4;   // outer panel = 4 inner panels = 512 columns
 
 cudaError_t launch_cholesky(b200bo_handle_s* h) {
   const int nblk = (int)(h->Np / NB);
-  const size_t sm_potrf = (size_t)(NB * PS + 4 * NB + 4 * NB + 32 + 8 + NB) * sizeof(double);
+  const size_t sm_potrf = PD_SMEM;
   cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf);
   cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
   cudaFuncSetAttribute(syrk_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
@@ -393,6 +469,18 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
     syrk(sa, p0, p1 - p0, p1, 2 * p1, 2 * p2);                // near part: the next outer panel's columns
   }
   if (npan >= 2) cudaStreamWaitEvent(sa, h->la_ev[2 * (npan - 2) + 1], 0);   // join stream B
+#ifdef POTRF_PROF
+  {
+    cudaDeviceSynchronize();
+    unsigned long long pr[16];
+    cudaMemcpyFromSymbol(pr, g_potrf_prof, sizeof(pr));
+    fprintf(stderr, "potrf phases (cycles per kernel, %d kernels): load %llu | F+U2 %llu | T+inv %llu | U1 %llu | offdiag inverse %llu | write-back %llu\n", nblk,
+            pr[0] / nblk, pr[1] / nblk, pr[2] / nblk, pr[3] / nblk, pr[4] / nblk, pr[5] / nblk);
+    fprintf(stderr, "  F(s) alone on warp 0: %llu %llu %llu %llu\n", pr[8] / nblk, pr[9] / nblk, pr[10] / nblk, pr[11] / nblk);
+    memset(pr, 0, sizeof(pr));
+    cudaMemcpyToSymbol(g_potrf_prof, pr, sizeof(pr));
+  }
+#endif
   return cudaGetLastError();
 }
 
