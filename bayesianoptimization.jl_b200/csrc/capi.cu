@@ -118,7 +118,7 @@ int32_t refit(b200bo_handle_s* h) {
     h->jitter++;
   }
   h->noise_total = noise;
-  CU(launch_alpha_mll(h));
+  CU(launch_alpha_mll(h, true));      // z = L^-1 (y - m) came out of the factorisation
   CU(cudaEventRecord(h->ev[3], h->stream));
   double sc[2];
   CU(cudaMemcpyAsync(sc, h->dscal, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
@@ -219,6 +219,7 @@ B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->syrk_ev) cudaEventDestroy(e);
   for (auto& e : h->la_ev) cudaEventDestroy(e);
+  for (auto& e : h->fw_ev) cudaEventDestroy(e);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -169,16 +169,27 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
       double dg = 0.0;                                 // this lane's diagonal element, fully updated once column lane-1 is done
 #pragma unroll
       for (int j = 0; j < PSUB; ++j) if (j == lane) dg = a[j];
-      double my_rs = 1.0, my_d = 1.0;
+      // Branch-free straight-line code: the next pivot's broadcast and reciprocal are issued BEFORE the bulk of the current
+      // column's update, so the in-order warp overlaps the d -> 1/d chain with the independent FMAs.
+      double my_d = 1.0;
+      int bad = 64;
+      double d = __shfl_sync(0xffffffffu, dg, 0);
+      bad = (d > 0.0) ? bad : 0;
+      d = (d > 0.0) ? d : 1.0;
+      double rc = fast_rcp(d);
 #pragma unroll
       for (int j = 0; j < PSUB; ++j) {
-        double d = __shfl_sync(0xffffffffu, dg, j);
-        if (!(d > 0.0)) { if (lane == 0) atomicCAS(info, 0, kb * NB + c0 + j + 1); d = 1.0; }
-        const double rc = fast_rcp(d);
         double* cbj = cb + (j & 1) * PSUB;
         cbj[lane] = a[j] * rc;                        // c_ij / d_j
-        if (lane == j) { my_d = d; my_rs = fast_rsqrt(d); }
+        my_d = (lane == j) ? d : my_d;
         dg = fma(-(a[j] * a[j]), rc, dg);             // lanes i > j (a[j]^2 is ready before rc is)
+        double dn = 1.0, rcn = 1.0;
+        if (j + 1 < PSUB) {
+          dn = __shfl_sync(0xffffffffu, dg, j + 1);   // lane j+1's diagonal is final now
+          bad = (dn > 0.0) ? bad : min(bad, j + 1);
+          dn = (dn > 0.0) ? dn : 1.0;
+          rcn = fast_rcp(dn);
+        }
         __syncwarp();
 #pragma unroll
         for (int k = (j + 1) & ~1; k < PSUB; k += 2) {
@@ -186,7 +197,10 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
           if (k > j) a[k] = fma(-a[j], m.x, a[k]);    // meaningful for lanes i > k
           a[k + 1] = fma(-a[j], m.y, a[k + 1]);
         }
+        d = dn; rc = rcn;
       }
+      if (bad < 64 && lane == 0) atomicCAS(info, 0, kb * NB + c0 + bad + 1);
+      const double my_rs = fast_rsqrt(my_d);
       rinv[c0 + lane] = my_rs;
       ldiag[c0 + lane] = my_d * my_rs;                // l_ii = sqrt(d_i)
       __syncwarp();
@@ -432,8 +446,13 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
   const int npan = (nblk + OB - 1) / OB;
   while ((int)h->syrk_ev.size() < 2 * npan + 2) { cudaEvent_t e; cudaEventCreate(&e); h->syrk_ev.push_back(e); }
   while ((int)h->la_ev.size() < 2 * npan + 2) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->la_ev.push_back(e); }
+  while ((int)h->fw_ev.size() < nblk + 2) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->fw_ev.push_back(e); }
   h->syrk_ev_used = 0;
   const int big = 1 << 30;
+  // the forward solve z = L^-1 (y - m) rides along on stream B (solve.cu: launch_fwd_step)
+  cudaEventRecord(h->fw_ev[nblk], sa);
+  cudaStreamWaitEvent(sb, h->fw_ev[nblk], 0);
+  launch_residual(h, sb);
   auto syrk = [&](cudaStream_t st, int kb0, int nkb, int bi_lo, int lo, int hi) {
     const int n = syrk_tiles(bi_lo, nblk, lo, hi);
     if (n > 0) {
@@ -449,6 +468,9 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
     for (int k = p0; k < p1; ++k) {
       potrf_diag_kernel<<<1, PD_THREADS, sm_potrf, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
       h->launches++;
+      cudaEventRecord(h->fw_ev[k], sa);
+      cudaStreamWaitEvent(sb, h->fw_ev[k], 0);
+      launch_fwd_step(h, sb, k - 1, nblk);
       const int rem = nblk - k - 1;
       if (rem <= 0) break;
       trsm_panel_kernel<<<rem * (NB / TG_BN), TG_THREADS, TG_SMEM, sa>>>(h->dL, h->ld, k, maps);
@@ -468,7 +490,8 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
     if (P > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (P - 1) + 1], 0);   // far part of panel P-1 also wrote the next panel's columns
     syrk(sa, p0, p1 - p0, p1, 2 * p1, 2 * p2);                // near part: the next outer panel's columns
   }
-  if (npan >= 2) cudaStreamWaitEvent(sa, h->la_ev[2 * (npan - 2) + 1], 0);   // join stream B
+  cudaEventRecord(h->fw_ev[nblk + 1], sb);
+  cudaStreamWaitEvent(sa, h->fw_ev[nblk + 1], 0);                             // join stream B (forward solve and far updates)
 #ifdef POTRF_PROF
   {
     cudaDeviceSynchronize();

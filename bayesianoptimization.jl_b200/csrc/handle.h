@@ -56,6 +56,7 @@ struct b200bo_handle_s {
   bool own_stream = true;
   cudaStream_t stream2 = nullptr;     // look-ahead stream of the factorisation (trailing update k overlaps panel k+1)
   std::vector<cudaEvent_t> la_ev;     // look-ahead dependencies
+  std::vector<cudaEvent_t> fw_ev;     // per panel: the forward solve of y - m rides along the factorisation on stream2
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> syrk_ev;   // start/stop pairs around every trailing-update launch of the last factorisation
   int syrk_ev_used = 0;
@@ -77,7 +78,9 @@ cudaError_t launch_kmat(b200bo_handle_s* h, double* dK, int64_t ld, int64_t N, i
 // chol.cu
 cudaError_t launch_cholesky(b200bo_handle_s* h);   // in place on h->dL (lower triangle), fills dLinv/dLinvT, upper mirror
 // solve.cu
-cudaError_t launch_alpha_mll(b200bo_handle_s* h);  // dw = y - m -> dz, dalpha, dscal[0] = logdet, dscal[1] = r'alpha
+cudaError_t launch_alpha_mll(b200bo_handle_s* h, bool have_z);  // dw = y - m -> dz (unless have_z), dalpha, dscal[0] = logdet, dscal[1] = r'alpha
+cudaError_t launch_residual(b200bo_handle_s* h, cudaStream_t st);            // dw = y - m (zero in the padding)
+cudaError_t launch_fwd_step(b200bo_handle_s* h, cudaStream_t st, int i, int nblk);   // step i of z = L^-1 dw (i = -1 .. nblk-2)
 cudaError_t launch_forward_solve(b200bo_handle_s* h, double* w, double* z, int nblk);
 cudaError_t launch_backward_solve(b200bo_handle_s* h, const double* z, double* w, double* alpha, int nblk);
 cudaError_t launch_logdet_dot(b200bo_handle_s* h);

@@ -132,6 +132,22 @@ __global__ void __launch_bounds__(256) logdet_dot_kernel(const double* __restric
   if (threadIdx.x == 0) { scal[0] = 2.0 * s0[0]; scal[1] = s1[0]; }
 }
 
+cudaError_t launch_residual(b200bo_handle_s* h, cudaStream_t st) {
+  const double beta = h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0;
+  residual_kernel<<<(int)((h->Np + 255) / 256), 256, 0, st>>>(h->dy, beta, h->dw, (int)h->N, (int)h->Np);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+// Step i of z = L^-1 dw.  It needs column block i of L (K3 of panel i) and the inverse of diagonal block i+1 (K2 of panel i+1),
+// so the factorisation launches it on its second stream right after K2 of panel i+1: the forward solve costs no time of its own.
+cudaError_t launch_fwd_step(b200bo_handle_s* h, cudaStream_t st, int i, int nblk) {
+  const int grid = i < 0 ? 1 : nblk - i - 1;
+  fwd_step_kernel<<<grid, 256, 0, st>>>(h->dL, h->ld, h->dLinvT, h->dw, h->dz, i);
+  h->launches++;
+  return cudaGetLastError();
+}
+
 // z = L^-1 w  (w is overwritten), nblk blocks of the current factor
 cudaError_t launch_forward_solve(b200bo_handle_s* h, double* w, double* z, int nblk) {
   for (int i = -1; i < nblk - 1; ++i) {
@@ -160,13 +176,15 @@ cudaError_t launch_logdet_dot(b200bo_handle_s* h) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_alpha_mll(b200bo_handle_s* h) {
+cudaError_t launch_alpha_mll(b200bo_handle_s* h, bool have_z) {
   const int nblk = (int)(h->Np / NB);
-  const double beta = h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0;
-  residual_kernel<<<(int)((h->Np + 255) / 256), 256, 0, h->stream>>>(h->dy, beta, h->dw, (int)h->N, (int)h->Np);
-  h->launches++;
-  cudaError_t e = launch_forward_solve(h, h->dw, h->dz, nblk);          // z = L^-1 (y - m) is kept for elastic appends
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  if (!have_z) {
+    e = launch_residual(h, h->stream);
+    if (e != cudaSuccess) return e;
+    e = launch_forward_solve(h, h->dw, h->dz, nblk);                    // z = L^-1 (y - m) is kept for elastic appends
+    if (e != cudaSuccess) return e;
+  }
   e = launch_backward_solve(h, h->dz, h->dw, h->dalpha, nblk);
   if (e != cudaSuccess) return e;
   return launch_logdet_dot(h);
