@@ -560,7 +560,7 @@ cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& l) {
 
 // Sigma^-1 = L^-T L^-1 by the same fused forward/backward sweep applied to the columns of I.  Result: h->dV viewed
 // as [Np][ld] (row j = column j of the symmetric inverse).
-cudaError_t launch_kinv(b200bo_handle_s* h) {
+cudaError_t launch_kinv_solve(b200bo_handle_s* h) {
   AcqArgs a = {};
   a.L = h->dL; a.ld = h->ld; a.Linv = h->dLinv; a.LinvT = h->dLinvT;
   a.V = h->dV; a.M = h->Np; a.N = (int)h->N; a.nblk = (int)(h->Np / NB); a.D = 0;

@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libb200bo.so (include/b200bo.h).  Host orchestration only; all arithmetic is in the
 // CUDA kernels (kmat.cu, chol.cu, solve.cu, acq.cu, mll.cu).  No CPU fallback: without a device every compute
 // entry fails with B200BO_ERR_CUDA.
+#include <cstdlib>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -36,9 +37,9 @@ int num_params(const b200bo_handle_s* h) {
 
 void free_device(b200bo_handle_s* h) {
   cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dZk); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dz); cudaFree(h->dinv_ell);
-  cudaFree(h->dL); cudaFree(h->dLinv); cudaFree(h->dLinvT); cudaFree(h->dV); cudaFree(h->dscal); cudaFree(h->dinfo);
+  cudaFree(h->dL); cudaFree(h->dLinv); cudaFree(h->dLinvT); cudaFree(h->dV); cudaFree(h->dKi); cudaFree(h->dWT); cudaFree(h->dTT); cudaFree(h->dscal); cudaFree(h->dinfo);
   cudaFree(h->dcta_best); cudaFree(h->dbest); cudaFree(h->dpart);
-  h->dz = nullptr;
+  h->dz = nullptr; h->dKi = h->dWT = h->dTT = nullptr;
   h->dX = h->dZ = h->dZk = h->dy = h->dw = h->dalpha = h->dinv_ell = h->dL = h->dLinv = h->dLinvT = h->dV = h->dscal = h->dpart = nullptr;
   h->dinfo = nullptr; h->dcta_best = nullptr; h->dbest = nullptr;
 }
@@ -628,8 +629,9 @@ B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int3
     mll[s] = h->mll;
     if (dmll) {
       double raw[35];
-      cudaError_t e = launch_kinv(h);
-      if (e == cudaSuccess) e = launch_dmll(h, mask, h->dscal + 8);
+      static const bool by_solves = getenv("B200BO_KINV_SOLVE") != nullptr;   // developer cross-check of the two Sigma^-1 paths
+      cudaError_t e = by_solves ? launch_kinv_solve(h) : launch_kinv(h);
+      if (e == cudaSuccess) e = launch_dmll(h, mask, h->dscal + 8, by_solves ? h->dV : h->dKi);
       if (e == cudaSuccess) e = cudaMemcpyAsync(raw, h->dscal + 8, sizeof(raw), cudaMemcpyDeviceToHost, h->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
       if (e != cudaSuccess) { rc = fail(h, B200BO_ERR_CUDA, std::string("mll gradient: ") + cudaGetErrorString(e)); break; }

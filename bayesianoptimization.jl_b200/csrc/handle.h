@@ -41,6 +41,8 @@ struct b200bo_handle_s {
   double* dLinv = nullptr;   // [cap/NB][NB][NB] inverses of the diagonal blocks
   double* dLinvT = nullptr;  //   and their transposes
   double* dV = nullptr;      // per-CTA solve panels [nslots][TILE_N][ld]
+  double *dKi = nullptr, *dWT = nullptr, *dTT = nullptr;   // [cap][cap] each, allocated by the first MAP gradient (kinv.cu)
+  CUtensorMap tmKi64, tmWT128, tmWT64, tmTT128;
   int64_t nslots = 0;
   double* dscal = nullptr;   // small scalar outputs (logdet, r'alpha, ...)
   int* dinfo = nullptr;      // non-PD flag
@@ -106,7 +108,8 @@ cudaError_t launch_ascent(b200bo_handle_s* h, const AcqLaunch& base, double* dX,
 // peak.cu
 cudaError_t launch_dmma_peak(b200bo_handle_s* h, double* tflops);
 // mll.cu
-cudaError_t launch_kinv(b200bo_handle_s* h);       // K^-1 into h->dV (panel layout [n][ld])
-cudaError_t launch_dmll(b200bo_handle_s* h, int mask, double* dout /*P*/);
+cudaError_t launch_kinv(b200bo_handle_s* h);       // kinv.cu: Sigma^-1 into h->dKi by recursive block inversion + W^T W
+cudaError_t launch_kinv_solve(b200bo_handle_s* h); // acq.cu (MODE 1): the same by column solves against I, into h->dV; cross-check only
+cudaError_t launch_dmll(b200bo_handle_s* h, int mask, double* dout /*P*/, const double* Kinv);
 
 }  // namespace b200bo

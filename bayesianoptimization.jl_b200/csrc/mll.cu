@@ -4,7 +4,7 @@
 // (reference src/models/gp.jl:59-64).  With A = alpha alpha' - Sigma^-1 (SURVEY App. A "dmll"):
 //   d/dlogNoise = e^{2 logNoise} tr(A);  d/dbeta = sum(alpha);  d/dll_d = 1/2 sum_ij A_ij sf2 psi(r2_ij) z_dij^2;
 //   d/dlsigma = sum_ij A_ij K_ij.
-// Sigma^-1 comes from launch_kinv (acq.cu, MODE 1) on the same factor; this pass is one HBM-bound sweep over it
+// Sigma^-1 comes from launch_kinv (kinv.cu) on the same factor; this pass is one HBM-bound sweep over it
 // (8 N^2 bytes read) that regenerates K_ij and its derivatives on the fly.  Two-stage fixed-order reduction.
 #include "common.cuh"
 #include "handle.h"
@@ -91,14 +91,14 @@ __global__ void dmll_final_kernel(const double* __restrict__ part, int nblocks, 
 }
 
 // raw sums into h->dscal[8 .. 8 + DM_NACC): [0..32) per-dim, [32] sum A.K, [33] tr(A), [34] sum(alpha)
-cudaError_t launch_dmll(b200bo_handle_s* h, int /*mask*/, double* dout) {
+cudaError_t launch_dmll(b200bo_handle_s* h, int /*mask*/, double* dout, const double* Kinv) {
   const int N = (int)h->N;
   const int T = (N + DM_T - 1) / DM_T;
   const int nblocks = T * T;
   if (nblocks == 0) return cudaSuccess;
   const size_t smem = (size_t)(2 * h->D * DM_T + 2 * DM_T + 8 * DM_NACC) * sizeof(double);
   const double sf2 = exp(2.0 * h->hp.lsigma);
-#define B200BO_DMLL(F) dmll_partial_kernel<F><<<nblocks, 256, smem, h->stream>>>(h->dV, h->ld, h->dZ, h->dalpha, N, h->D, sf2, h->dpart)
+#define B200BO_DMLL(F) dmll_partial_kernel<F><<<nblocks, 256, smem, h->stream>>>(Kinv, h->ld, h->dZ, h->dalpha, N, h->D, sf2, h->dpart)
   switch (h->fam) {
     case FAM_SE: B200BO_DMLL(FAM_SE); break;
     case FAM_MAT12: B200BO_DMLL(FAM_MAT12); break;

@@ -32,6 +32,10 @@ static bool make2d(CUtensorMap* m, double* base, uint64_t rows, uint64_t cols, u
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+cudaError_t make_map2d(CUtensorMap* m, double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make2d(m, base, rows, cols, ld, box_rows) ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 cudaError_t make_tensor_maps(b200bo_handle_s* h) {
   const uint64_t cap = (uint64_t)h->cap, nb = cap / NB;
   bool ok = make2d(&h->tmL, h->dL, cap, cap, cap, NB);
