@@ -105,6 +105,36 @@ def test_against_oracle(bo, kern, mean, D, N, M):
     assert close(r["values"], ts, RTOL_ACQ) and r["best_index"] - 1000 == orc.first_strict_argmax_np(ts)
 
 
+@pytest.mark.parametrize("kern,D,N", [("SEArd", 5, 300), ("Mat52Ard", 3, 700), ("SEIso", 4, 1300), ("Mat32Ard", 6, 2048)])
+def test_mll_gradient_block_inversion(bo, kern, D, N):
+    """Sigma^-1 by recursive block inversion (3, 6, 11 and 16 panels: uneven merges) against the oracle's mll gradient."""
+    rng, o, g, X, y = make_pair(bo, kern, "MeanConst", D, N, seed=7 * N + D)
+    th = g.get_params()
+    th2 = th.copy(); th2[0] -= 0.4; th2[2:] += 0.15
+    mll, dmll = g.mll_sweep(np.stack([th, th2], axis=1))
+    for k, t in enumerate((th, th2)):
+        mo, go = o.mll_dmll(t)
+        assert abs(mll[k] - mo) <= 1e-10 * abs(mo)
+        assert relmax(dmll[:, k], go) < 1e-8
+    assert np.array_equal(g.get_params(), th)
+
+
+def test_kmat_extreme_signal_variance(bo):
+    """sf2 outside [1e-12, 1e12] is applied after the table-based exponential (K1's `post` path); identical structure otherwise."""
+    rng = np.random.default_rng(11)
+    D, N = 5, 200
+    X = rng.random((D, N)); y = rng.standard_normal(N)
+    for ls in (15.0, -15.0):
+        ll = np.full(D, -0.5)
+        o = orc.GPOracle(D, "SEArd", "MeanZero", ll=ll, lsigma=ls, lognoise=ls - 2.0, beta=0.0).fit(X, y)
+        g = bo.B200GPE(D, mean=bo.MeanZero(), kernel=bo.SEArd(ll, ls), logNoise=ls - 2.0, capacity=N)
+        g.fit(X, y)
+        S = o.cov(o.X, o.X); S[np.diag_indices(N)] += np.exp(2 * o.lognoise) + orc.EPS
+        K = g.kmat()
+        assert relmax(K, S) < 1e-13 and np.array_equal(K, K.T)
+        assert relmax(g.alpha, o.alpha) < 1e-8
+
+
 @pytest.mark.parametrize("N", [1920, 2560, 4096])
 def test_factor_many_panels(bo, N):
     """blocked Cholesky with many 128-panels (persistent trailing update walks several tiles per CTA, look-ahead streams)."""
