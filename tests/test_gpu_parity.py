@@ -281,6 +281,68 @@ def test_full_size_properties_config2(bo):
     assert g.launch_count > 0
 
 
+def _bumps(X, rng):
+    c = rng.random((X.shape[0], 8))
+    return sum(np.exp(-0.5 * np.sum((X - c[:, k:k + 1]) ** 2, axis=0) / 0.15) for k in range(8)) + np.exp(-2.0) * rng.standard_normal(X.shape[1])
+
+
+def test_full_size_properties_config3(bo):
+    """BASELINE configs[2] at its full model size (D=32, N=4096, EI + gradient) on a slice of the candidate sweep:
+    size-independent properties + an oracle subsample + a finite-difference check of the fused gradient."""
+    rng = np.random.default_rng(3)
+    D, N, M = 32, 4096, 8192
+    X = rng.random((D, N)); y = _bumps(X, rng)
+    ll = np.full(D, np.log(np.sqrt(D) * 0.25))
+    g = bo.B200GPE(D, mean=bo.MeanConst(0.0), kernel=bo.SEArd(ll, 0.0), logNoise=-2.0, capacity=N)
+    g.fit(X, y)
+    assert g.jitter_tries == 0
+    o = orc.GPOracle(D, "SEArd", "MeanConst", ll=ll, lsigma=0.0, lognoise=-2.0, beta=0.0).fit(X, y)
+    assert relmax(g.alpha, o.alpha) < 1e-8 and abs(g.mll - o.mll) < 1e-10 * abs(o.mll)
+    noise = np.exp(-4.0) + orc.EPS
+    mu_tr, var_tr = g.predict(X[:, :1024])
+    assert np.allclose(mu_tr, y[:1024] - noise * g.alpha[:1024], rtol=0, atol=1e-9) and np.all(var_tr >= 0)
+    Xs = orc.latin_hypercube_sampling(np.zeros(D), np.ones(D), M, np.random.default_rng(30))
+    tau = float(y.max())
+    r = g.acquire("EI", (tau,), Xs, want_grad=True, want_mu_var=True)
+    assert r["best_index"] == orc.first_strict_argmax_np(r["values"])
+    sub = np.sort(np.random.default_rng(31).choice(M, 96, replace=False)); sub[0] = r["best_index"]
+    a, gr = orc.acq_grad(o, "EI", (tau,), Xs[:, sub])
+    mo, vo = o.predict(Xs[:, sub])
+    assert close(r["mu"][sub], mo, RTOL_POST) and close(r["var"][sub], vo, RTOL_POST) and close(r["values"][sub], a, RTOL_ACQ)
+    assert relmax(r["grad"][:, sub], gr) < 1e-7
+    # central finite differences of the device value along random directions agree with the device gradient
+    k = int(sub[1]); u = np.random.default_rng(32).standard_normal(D); u /= np.linalg.norm(u); h = 1e-5
+    pm = g.acquire("EI", (tau,), np.stack([Xs[:, k] + h * u, Xs[:, k] - h * u], axis=1))["values"]
+    fd = (pm[0] - pm[1]) / (2 * h)
+    assert abs(fd - r["grad"][:, k] @ u) <= 1e-5 * max(abs(fd), np.abs(r["grad"][:, k]).max())
+    # the gradient launch and the value-only launch give the same values and the same selection
+    r0 = g.acquire("EI", (tau,), Xs)
+    assert np.array_equal(r0["values"], r["values"]) and r0["best_index"] == r["best_index"]
+
+
+def test_full_size_properties_config5_shard(bo):
+    """BASELINE configs[4] at its full model size (D=16, N=8192, ThompsonSamplingSimple) on a slice of one rank's shard: the
+    Philox stream is keyed by the GLOBAL candidate index, so shards of different shapes agree bit for bit."""
+    rng = np.random.default_rng(5)
+    D, N, M = 16, 8192, 4096
+    X = rng.random((D, N)); y = _bumps(X, rng)
+    ll = np.full(D, np.log(np.sqrt(D) * 0.25))
+    g = bo.B200GPE(D, mean=bo.MeanConst(0.0), kernel=bo.SEArd(ll, 0.0), logNoise=-2.0, capacity=N)
+    g.fit(X, y)
+    assert g.jitter_tries == 0
+    noise = np.exp(-4.0) + orc.EPS
+    mu_tr, var_tr = g.predict(X[:, -512:])
+    assert np.allclose(mu_tr, y[-512:] - noise * g.alpha[-512:], rtol=0, atol=1e-9) and np.all(var_tr >= 0) and np.all(var_tr <= 1.0)
+    Xs = orc.latin_hypercube_sampling(np.zeros(D), np.ones(D), M, np.random.default_rng(51))
+    off = 3 * 131072                                            # rank 3 of 8
+    r = g.acquire("TS", (), Xs, seed=50, idx_offset=off, want_mu_var=True)
+    eps = orc.philox_normal(50, off + np.arange(M))
+    assert close(r["values"], orc.acq_value("TS", (), r["mu"], r["var"], eps=eps), RTOL_ACQ)
+    assert r["best_index"] - off == orc.first_strict_argmax_np(r["values"])
+    halves = [g.acquire("TS", (), Xs[:, lo:hi], seed=50, idx_offset=off + lo) for lo, hi in ((0, 1000), (1000, M))]
+    assert np.array_equal(np.concatenate([h_["values"] for h_ in halves]), r["values"])
+
+
 def test_linearity_in_y_large(bo):
     """posterior mean is linear in y (MeanZero): mu[y1 + y2] = mu[y1] + mu[y2]; variance does not depend on y."""
     rng = np.random.default_rng(8)
