@@ -430,16 +430,22 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
     }
     if (p1 >= nblk) break;
     cudaEvent_t Pk = h->la_ev[2 * P], Rk = h->la_ev[2 * P + 1];
+    // K = 512 updates on tcgen05 (int8 slices, syrk_i8.cu) when enabled and the outer panel is full; else the DMMA tile GEMM
+    const bool i8 = syrk_i8_enabled() && (p1 - p0) == OB;
+    if (i8) {
+      if (P > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (P - 1) + 1], 0);   // the far part of panel P-1 still reads the previous slices
+      launch_slice_panel(h, sa, p1 * NB, p0 * NB);
+    }
     if (syrk_tiles(p1, nblk, 2 * p2, big) > 0) {              // far part on stream B (after panel P is complete on A)
       cudaEventRecord(Pk, sa);
       cudaStreamWaitEvent(sb, Pk, 0);
       cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
-      syrk(sb, p0, p1 - p0, p1, 2 * p2, big);
+      if (i8) launch_syrk_i8(h, sb, p1, 2 * p2, big, nullptr); else syrk(sb, p0, p1 - p0, p1, 2 * p2, big);
       cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
       cudaEventRecord(Rk, sb);
     }
     if (P > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (P - 1) + 1], 0);   // far part of panel P-1 also wrote the next panel's columns
-    syrk(sa, p0, p1 - p0, p1, 2 * p1, 2 * p2);                // near part: the next outer panel's columns
+    if (i8) launch_syrk_i8(h, sa, p1, 2 * p1, 2 * p2, nullptr); else syrk(sa, p0, p1 - p0, p1, 2 * p1, 2 * p2);   // near part: the next outer panel's columns
   }
   cudaEventRecord(h->fw_ev[nblk + 1], sb);
   cudaStreamWaitEvent(sa, h->fw_ev[nblk + 1], 0);                             // join stream B (forward solve and far updates)

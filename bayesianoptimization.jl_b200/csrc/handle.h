@@ -43,6 +43,9 @@ struct b200bo_handle_s {
   double* dV = nullptr;      // per-CTA solve panels [nslots][TILE_N][ld]
   double *dKi = nullptr, *dWT = nullptr, *dTT = nullptr;   // [cap][cap] each, allocated by the first MAP gradient (kinv.cu)
   CUtensorMap tmKi64, tmWT128, tmWT64, tmTT128;
+  void* dSl = nullptr;       // [8 slices][cap][512] int8 slices of the current outer panel (syrk_i8.cu), allocated on first use
+  double* dSe = nullptr;     // [cap] per-row scale 2^(e-6) of the slices
+  CUtensorMap tmSlA, tmSlB;
   int64_t nslots = 0;
   double* dscal = nullptr;   // small scalar outputs (logdet, r'alpha, ...)
   int* dinfo = nullptr;      // non-PD flag
@@ -79,6 +82,10 @@ cudaError_t launch_scale_inputs(b200bo_handle_s* h, int64_t n0, int64_t n1);
 cudaError_t launch_kmat(b200bo_handle_s* h, double* dK, int64_t ld, int64_t N, int64_t Np, double noise, bool pad_identity);
 // chol.cu
 cudaError_t launch_cholesky(b200bo_handle_s* h);   // in place on h->dL (lower triangle), fills dLinv/dLinvT, upper mirror
+// syrk_i8.cu
+bool syrk_i8_enabled();
+cudaError_t launch_slice_panel(b200bo_handle_s* h, cudaStream_t st, int row0, int col0);
+cudaError_t launch_syrk_i8(b200bo_handle_s* h, cudaStream_t st, int bi_lo, int col2_lo, int col2_hi, int* ntiles);
 // solve.cu
 cudaError_t launch_alpha_mll(b200bo_handle_s* h, bool have_z);  // dw = y - m -> dz (unless have_z), dalpha, dscal[0] = logdet, dscal[1] = r'alpha
 cudaError_t launch_residual(b200bo_handle_s* h, cudaStream_t st);            // dw = y - m (zero in the padding)

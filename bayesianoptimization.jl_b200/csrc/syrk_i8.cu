@@ -1,0 +1,304 @@
+// syrk_i8.cu -- K4 on the 5th-generation tensor cores: the K = 512 trailing update  A_ij -= L_i,P L_j,P^T  of the blocked Cholesky
+// (chol.cu) as an error-free int8-slice product (Ozaki scheme) on tcgen05.mma kind::i8 with TMEM accumulators.
+//
+// tcgen05 has no FP64 kind, so each FP64 operand row is split ONCE per outer panel into 8 signed 7-bit slices with a per-row
+// power-of-two scale:   x_k = 2^(e-6) sum_p d_p[k] 2^(-7p),  |d_p| <= 64   (slice_panel_kernel; the splitting is exact).
+// Then  x.y = 2^(ex+ey-12) sum_{p+q<=7} 2^(-7(p+q)) <d_p, d'_q>  + O(2^-53 max|x| max|y|) per term: 36 exact int8 dot products,
+// accumulated in int32 by anti-diagonal d = p + q (|sum| <= 8 * 512 * 64^2 < 2^24) in 8 TMEM accumulators of 64 columns.
+// Persistent CTAs (one per SM) over the 128 x 64 tiles of the trailing matrix (the same tile set as the DMMA kernel), 320 threads:
+//   warp 0   TMA producer: per 128-byte k-block the 8 slices of the 64 B-rows (64 KB, double buffered) and, through a 4-deep
+//            ring, the 8 slices of the 128 A-rows one at a time (16 KB each), all SWIZZLE_128B tiles by cp.async.bulk.tensor.3d;
+//   warp 1   allocates the 512 TMEM columns and issues the 36 x 4 x 4 = 576 MMAs (128 x 64 x 32) of the tile; tcgen05.commit
+//            releases the shared-memory stages and finally publishes the accumulators;
+//   warps 2-9 read the accumulators back (tcgen05.ld 32x32b), recombine the anti-diagonals exactly in two 64-bit integer groups, convert
+//            once per group, apply the row scales and subtract from A (only the lower triangle of diagonal tiles is touched).
+// Every mbarrier wait is bounded (trap instead of hanging the GPU).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "tma.cuh"
+#include "handle.h"
+
+namespace b200bo {
+
+constexpr int I8_S = 8;                 // slices per FP64 value
+constexpr int I8_K = 512;               // bytes of K per slice row = columns of one outer panel
+constexpr int I8_BM = 128, I8_BN = 64;
+constexpr int I8_ASTAGES = 4;
+constexpr uint32_t I8_A_BYTES = I8_BM * 128, I8_B_BYTES = I8_BN * 128;
+constexpr size_t I8_SMEM = 2 * I8_S * I8_B_BYTES + I8_ASTAGES * I8_A_BYTES + 1024;
+constexpr int I8_THREADS = 320;          // producer warp, MMA warp, 8 epilogue warps
+
+// ---- FP64 panel rows -> 8 int8 slices + scale.  One warp per row, 16 consecutive columns per lane. ----
+__global__ void __launch_bounds__(256) slice_panel_kernel(const double* __restrict__ L, int64_t ld, int row0, int nrows, int col0,
+                                                          int8_t* __restrict__ Sl, double* __restrict__ Se, int64_t cap) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nrows) return;
+  const int row = row0 + warp;
+  const double* src = L + (int64_t)row * ld + col0 + 16 * lane;
+  double x[16];
+#pragma unroll
+  for (int u = 0; u < 16; u += 2) { const double2 v = *reinterpret_cast<const double2*>(src + u); x[u] = v.x; x[u + 1] = v.y; }
+  double m = 0.0;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) m = fmax(m, fabs(x[u]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const int e = (m > 0.0) ? ilogb(m) + 1 : 0;                 // |x| < 2^e
+  const double sc = ldexp(1.0, 6 - e);                        // |x sc| < 64
+  double t[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) t[u] = x[u] * sc;
+#pragma unroll
+  for (int s = 0; s < I8_S; ++s) {
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const double d = rint(t[u]);                            // |d| <= 64, exact
+      t[u] = (t[u] - d) * 128.0;                              // remainder in [-64, 64], exact
+      w[u >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)d) << (8 * (u & 3));
+    }
+    *reinterpret_cast<uint4*>(Sl + ((int64_t)s * cap + row) * I8_K + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (lane == 0) Se[row] = ldexp(1.0, e - 6);
+}
+
+// ---- tcgen05 plumbing ----
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {   // K-major, SWIZZLE_128B, 8-row groups 1024 B apart (version 1)
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (int i = 0; i < (1 << 24) && !ok; ++i)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  if (!ok) __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+struct I8Maps { CUtensorMap A, B; };   // [slice][row][512 B] with 128-row and 64-row boxes
+
+// tile t of the update: row block bi >= bi_lo, 64-wide column block c2 in [col2_lo, min(col2_hi, 2 bi + 2))
+__device__ __forceinline__ void i8_tile(int t, int bi_lo, int col2_lo, int col2_hi, int nblk, int& bi, int& c2) {
+  bi = bi_lo; c2 = 0;
+  for (; bi < nblk; ++bi) {
+    const int hi = (2 * bi + 2 < col2_hi) ? 2 * bi + 2 : col2_hi;
+    const int cnt = hi - col2_lo;
+    if (cnt > 0) { if (t < cnt) { c2 = col2_lo + t; return; } t -= cnt; }
+  }
+}
+
+// Persistent: CTA b walks tiles b, b + grid, ...; the pipelines (A ring, B double buffer, TMEM full/empty) run across tiles, so the
+// producer prefetches the next tile's operands during the epilogue and the next tile's MMAs start as soon as TMEM has been read.
+__global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restrict__ C, int64_t ld, const double* __restrict__ Se, int bi_lo,
+                                                                int col2_lo, int col2_hi, int nblk, int ntiles,
+                                                                const __grid_constant__ I8Maps maps) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sB = smem_raw;                                     // [2][8 slices][64 rows x 128 B]
+  uint8_t* sA = smem_raw + 2 * I8_S * I8_B_BYTES;             // [4][128 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + I8_ASTAGES * I8_A_BYTES);
+  uint64_t *afull = bars, *aempty = bars + 4, *bfull = bars + 8, *bempty = bars + 10, *tfull = bars + 12, *tempty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 8);                                     // one arrival per epilogue warp
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                          // ===== TMA producer =====
+      tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B);
+      int as = 0; uint32_t aph = 0, bcnt = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int bi, c2; i8_tile(tile, bi_lo, col2_lo, col2_hi, nblk, bi, c2);
+        const int arow = bi * I8_BM, brow = c2 * I8_BN;
+        for (int kb = 0; kb < I8_K / 128; ++kb, ++bcnt) {
+          const int bs = bcnt & 1;
+          mbar_wait_or_trap(&bempty[bs], ((bcnt >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bfull[bs], I8_S * I8_B_BYTES);
+          for (int q = 0; q < I8_S; ++q) tma_load_3d(sB + (bs * I8_S + q) * I8_B_BYTES, &maps.B, &bfull[bs], kb * 128, brow, q);
+          for (int p = 0; p < I8_S; ++p) {
+            mbar_wait_or_trap(&aempty[as], aph ^ 1u);
+            mbar_arrive_expect_tx(&afull[as], I8_A_BYTES);
+            tma_load_3d(sA + as * I8_A_BYTES, &maps.A, &afull[as], kb * 128, arow, p);
+            if (++as == I8_ASTAGES) { as = 0; aph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                          // ===== MMA issuer =====
+      // D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
+      int as = 0; uint32_t aph = 0, bcnt = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        mbar_wait_or_trap(tempty, (it & 1u) ^ 1u);            // the epilogue has read the previous tile's accumulators
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        uint32_t started = 0;                                 // bit d: accumulator d already holds a product of this tile
+        for (int kb = 0; kb < I8_K / 128; ++kb, ++bcnt) {
+          const int bs = bcnt & 1;
+          mbar_wait_or_trap(&bfull[bs], (bcnt >> 1) & 1u);
+          for (int p = 0; p < I8_S; ++p) {
+            mbar_wait_or_trap(&afull[as], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint64_t da = umma_desc_sw128(smem_u32(sA + as * I8_A_BYTES));
+            for (int q = 0; q + p < I8_S; ++q) {
+              const int d = p + q;
+              const uint64_t db = umma_desc_sw128(smem_u32(sB + (bs * I8_S + q) * I8_B_BYTES));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)                  // 32 bytes of K per MMA: +2 in the 16-byte start-address field
+                umma_i8(tmem + (uint32_t)(d * I8_BN), da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, ((started >> d) & 1u) | (ks > 0));
+              started |= 1u << d;
+            }
+            umma_commit(&aempty[as]);                         // the A stage is free once these MMAs have read it
+            if (++as == I8_ASTAGES) { as = 0; aph ^= 1u; }
+          }
+          umma_commit(&bempty[bs]);
+        }
+        umma_commit(tfull);                                   // all 576 MMAs of the tile retired: accumulators complete
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps; warp w reads TMEM lanes 32 (w & 3) .. +31 (= rows of the tile), columns 32 half .. +31 =====
+    const int g4 = warp & 3, half = (warp - 2) >> 2;
+    const int m = 32 * g4 + lane;                             // row inside the tile
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      int bi, c2; i8_tile(tile, bi_lo, col2_lo, col2_hi, nblk, bi, c2);
+      const int arow = bi * I8_BM, brow = c2 * I8_BN;
+      const double srow = Se[arow + m];
+      const int diag_off = arow - brow;                       // element (m, n) is on/below the diagonal iff n <= m + diag_off
+      double* crow = C + (int64_t)(arow + m) * ld + brow;
+      mbar_wait_or_trap(tfull, it & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      // sum_d a_d 2^(-7d) in two exact 64-bit integer groups (|a_d| < 2^24):  (((a0 128 + a1) 128 + a2) 128 + a3) 2^-21 + (a4 ..) 2^-49
+      double acc[32];
+#pragma unroll 1
+      for (int grp = 1; grp >= 0; --grp) {                    // the small group first
+        long long H[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) H[c] = 0;
+#pragma unroll 1
+        for (int dd = 0; dd < 4; ++dd) {
+          uint32_t r[32];
+          tmem_ld32(tmem + ((uint32_t)(32 * g4) << 16) + (uint32_t)((4 * grp + dd) * I8_BN + 32 * half), r);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) H[c] = (H[c] << 7) + (long long)(int32_t)r[c];
+        }
+        if (grp == 0) {                                       // TMEM has been read: the next tile's MMAs may overwrite it
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+        }
+        const double w = grp ? 0x1p-49 : 0x1p-21;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = grp ? (double)H[c] * w : fma((double)H[c], w, acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const int n = 32 * half + c;
+        if (n + 1 <= m + diag_off) {
+          const double2 se = *reinterpret_cast<const double2*>(Se + brow + n);
+          double2 v = *reinterpret_cast<double2*>(crow + n);
+          v.x -= acc[c] * srow * se.x;
+          v.y -= acc[c + 1] * srow * se.y;
+          *reinterpret_cast<double2*>(crow + n) = v;
+        } else if (n <= m + diag_off) {
+          crow[n] -= acc[c] * srow * Se[brow + n];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+cudaError_t make_map3d_u8(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1);
+
+static int tiles_of(int bi_lo, int nblk, int col2_lo, int col2_hi) {
+  int n = 0;
+  for (int bi = bi_lo; bi < nblk; ++bi) {
+    const int hi = (2 * bi + 2 < col2_hi) ? 2 * bi + 2 : col2_hi;
+    if (hi > col2_lo) n += hi - col2_lo;
+  }
+  return n;
+}
+
+bool syrk_i8_enabled() {
+  static const bool on = !(getenv("B200BO_SYRK_I8") && atoi(getenv("B200BO_SYRK_I8")) == 0);   // B200BO_SYRK_I8=0 selects the DMMA kernel
+  return on;
+}
+
+// slices of the finished outer panel: rows [row0, Np) x columns [col0, col0 + 512) of the factor
+cudaError_t launch_slice_panel(b200bo_handle_s* h, cudaStream_t st, int row0, int col0) {
+  const int64_t cap = h->cap;
+  if (!h->dSl) {
+    cudaError_t e = cudaMalloc(&h->dSl, (size_t)I8_S * cap * I8_K);
+    if (e == cudaSuccess) e = cudaMalloc(&h->dSe, sizeof(double) * cap);
+    if (e == cudaSuccess) e = make_map3d_u8(&h->tmSlA, h->dSl, I8_K, (uint64_t)cap, I8_S, 128, I8_BM);
+    if (e == cudaSuccess) e = make_map3d_u8(&h->tmSlB, h->dSl, I8_K, (uint64_t)cap, I8_S, 128, I8_BN);
+    if (e != cudaSuccess) return e;
+  }
+  const int nrows = (int)h->Np - row0;
+  if (nrows <= 0) return cudaSuccess;
+  slice_panel_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(h->dL, h->ld, row0, nrows, col0, reinterpret_cast<int8_t*>(h->dSl), h->dSe, cap);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+// A_ij -= L_i,P L_j,P^T over the tiles (bi >= bi_lo, 64-wide column blocks [col2_lo, min(col2_hi, 2 bi + 2))) from the current slices
+cudaError_t launch_syrk_i8(b200bo_handle_s* h, cudaStream_t st, int bi_lo, int col2_lo, int col2_hi, int* ntiles) {
+  const int nblk = (int)(h->Np / NB);
+  const int n = tiles_of(bi_lo, nblk, col2_lo, col2_hi);
+  if (ntiles) *ntiles = n;
+  if (n == 0) return cudaSuccess;
+  cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM);
+  I8Maps maps;
+  maps.A = h->tmSlA; maps.B = h->tmSlB;
+  const int grid = n < h->num_sms ? n : h->num_sms;
+  syrk_i8_kernel<<<grid, I8_THREADS, I8_SMEM, st>>>(h->dL, h->ld, h->dSe, bi_lo, col2_lo, col2_hi, nblk, n, maps);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace b200bo
