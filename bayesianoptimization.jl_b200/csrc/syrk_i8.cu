@@ -1,14 +1,15 @@
 // syrk_i8.cu -- K4 on the 5th-generation tensor cores: the K = 512 trailing update  A_ij -= L_i,P L_j,P^T  of the blocked Cholesky
 // (chol.cu) as an error-free int8-slice product (Ozaki scheme) on tcgen05.mma kind::i8 with TMEM accumulators.
 //
-// tcgen05 has no FP64 kind, so each FP64 operand row is split ONCE per outer panel into 8 signed 7-bit slices with a per-row
-// power-of-two scale:   x_k = 2^(e-6) sum_p d_p[k] 2^(-7p),  |d_p| <= 64   (slice_panel_kernel; the splitting is exact).
-// Then  x.y = 2^(ex+ey-12) sum_{p+q<=7} 2^(-7(p+q)) <d_p, d'_q>  + O(2^-53 max|x| max|y|) per term: 36 exact int8 dot products,
-// accumulated in int32 by anti-diagonal d = p + q (|sum| <= 8 * 512 * 64^2 < 2^24) in 8 TMEM accumulators of 64 columns.
+// tcgen05 has no FP64 kind, so each FP64 operand row is split ONCE per outer panel into 7 int8 slices with a per-row power-of-two
+// scale:   x_k = 2^(e-6) sum_p d_p[k] 2^(-8p),  d_0 in [-64, 64], d_p in [-128, 127] (p >= 1, balanced signed digits): 6 + 6 x 8 = 54
+// bits, the splitting is exact (slice_panel_kernel).  Then  x.y = 2^(ex+ey-12) sum_{p+q<=6} 2^(-8(p+q)) <d_p, d'_q>  + O(2^-51 max|x| max|y|) per term:
+// 28 exact int8 dot products, accumulated in int32 by anti-diagonal d = p + q (|sum| <= 7 * 512 * 2^14 < 2^26) in 7 TMEM
+// accumulators of 64 columns.
 // Persistent CTAs (one per SM) over the 128 x 64 tiles of the trailing matrix (the same tile set as the DMMA kernel), 320 threads:
-//   warp 0   TMA producer: per 128-byte k-block the 8 slices of the 64 B-rows (64 KB, double buffered) and, through a 4-deep
-//            ring, the 8 slices of the 128 A-rows one at a time (16 KB each), all SWIZZLE_128B tiles by cp.async.bulk.tensor.3d;
-//   warp 1   allocates the 512 TMEM columns and issues the 36 x 4 x 4 = 576 MMAs (128 x 64 x 32) of the tile; tcgen05.commit
+//   warp 0   TMA producer: per 128-byte k-block the 7 slices of the 64 B-rows (56 KB, double buffered) and, through a 4-deep
+//            ring, the 7 slices of the 128 A-rows one at a time (16 KB each), all SWIZZLE_128B tiles by cp.async.bulk.tensor.3d;
+//   warp 1   allocates the 512 TMEM columns and issues the 28 x 4 x 4 = 448 MMAs (128 x 64 x 32) of the tile; tcgen05.commit
 //            releases the shared-memory stages and finally publishes the accumulators;
 //   warps 2-9 read the accumulators back (tcgen05.ld 32x32b), recombine the anti-diagonals exactly in two 64-bit integer groups, convert
 //            once per group, apply the row scales and subtract from A (only the lower triangle of diagonal tiles is touched).
@@ -21,7 +22,7 @@
 
 namespace b200bo {
 
-constexpr int I8_S = 8;                 // slices per FP64 value
+constexpr int I8_S = 7;                 // slices per FP64 value
 constexpr int I8_K = 512;               // bytes of K per slice row = columns of one outer panel
 constexpr int I8_BM = 128, I8_BN = 64;
 constexpr int I8_ASTAGES = 4;
@@ -54,8 +55,10 @@ __global__ void __launch_bounds__(256) slice_panel_kernel(const double* __restri
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      const double d = rint(t[u]);                            // |d| <= 64, exact
-      t[u] = (t[u] - d) * 128.0;                              // remainder in [-64, 64], exact
+      // digit rule d = floor(t + c), c = 128/255: the remainder stays in [-c, 1 - c], so 256 x remainder + c stays in [-128, 128]
+      // and every later digit fits [-128, 127] (the clamp only catches the closed end of that interval); t - d is exact
+      const double d = fmin(fmax(floor(t[u] + (128.0 / 255.0)), -128.0), 127.0);
+      t[u] = (t[u] - d) * 256.0;
       w[u >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)d) << (8 * (u & 3));
     }
     *reinterpret_cast<uint4*>(Sl + ((int64_t)s * cap + row) * I8_K + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
           }
           umma_commit(&bempty[bs]);
         }
-        umma_commit(tfull);                                   // all 576 MMAs of the tile retired: accumulators complete
+        umma_commit(tfull);                                   // all 448 MMAs of the tile retired: accumulators complete
       }
     }
   } else {
@@ -210,26 +213,27 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
       double* crow = C + (int64_t)(arow + m) * ld + brow;
       mbar_wait_or_trap(tfull, it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      // sum_d a_d 2^(-7d) in two exact 64-bit integer groups (|a_d| < 2^24):  (((a0 128 + a1) 128 + a2) 128 + a3) 2^-21 + (a4 ..) 2^-49
+      // sum_d a_d 2^(-8d) in two exact 64-bit integer groups (|a_d| < 2^26):  (((a0 256 + a1) 256 + a2) 256 + a3) 2^-24 + ((a4 256 + a5) 256 + a6) 2^-48
       double acc[32];
 #pragma unroll 1
       for (int grp = 1; grp >= 0; --grp) {                    // the small group first
         long long H[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) H[c] = 0;
+        const int nd = grp ? I8_S - 4 : 4;
 #pragma unroll 1
-        for (int dd = 0; dd < 4; ++dd) {
+        for (int dd = 0; dd < nd; ++dd) {
           uint32_t r[32];
           tmem_ld32(tmem + ((uint32_t)(32 * g4) << 16) + (uint32_t)((4 * grp + dd) * I8_BN + 32 * half), r);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) H[c] = (H[c] << 7) + (long long)(int32_t)r[c];
+          for (int c = 0; c < 32; ++c) H[c] = (H[c] << 8) + (long long)(int32_t)r[c];
         }
         if (grp == 0) {                                       // TMEM has been read: the next tile's MMAs may overwrite it
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty);
         }
-        const double w = grp ? 0x1p-49 : 0x1p-21;
+        const double w = grp ? 0x1p-48 : 0x1p-24;
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = grp ? (double)H[c] * w : fma((double)H[c], w, acc[c]);
       }
