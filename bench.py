@@ -304,7 +304,9 @@ def main():
                                   "frac": kbytes / (fit_ms["kmat"] * 1e-3) * 1e-9 / hbm_peak, "algorithmic_bytes": kbytes},
                 "cholesky": {"ms": fit_ms["chol"], "tflops_fp64": (N ** 3 / 3.0) / (fit_ms["chol"] * 1e-3) * 1e-12,
                              "syrk_k512_ms": fit_ms["syrk"], "syrk_k512_flops": far_flops,
-                             "syrk_k512_tflops_fp64": far_flops / max(fit_ms["syrk"], 1e-9) * 1e-9, "peak_tflops_fp64": peak_fp64},
+                             "syrk_k512_tflops_fp64": far_flops / max(fit_ms["syrk"], 1e-9) * 1e-9, "peak_tflops_fp64": peak_fp64,
+                             "syrk_k512_engine": "tcgen05.mma kind::i8, 7-slice error-free product, TMEM accumulators (csrc/syrk_i8.cu); "
+                                                 "timed on the second stream while the next outer panel runs"},
                 "alpha_ms": fit_ms["alpha"]}
         # the north_star's fit targets are quoted at N=4096, D=8 (SEArd): measure that fit beside the workload's own (outside every
         # timed region; best of three warm refits, library CUDA-event timers around K1 / the factorisation / the K=512 updates)
