@@ -671,6 +671,12 @@ B200BO_API int32_t b200bo_fp64_peak_tflops(b200bo_handle_t h, double* tflops) {
   return B200BO_OK;
 }
 
+B200BO_API int32_t b200bo_set_syrk_engine(b200bo_handle_t h, int32_t engine) {
+  if (!h || engine < 0 || engine > 1) return fail(h, B200BO_ERR_ARG, "engine must be 0 (DMMA) or 1 (tcgen05)");
+  h->syrk_engine = engine;
+  return B200BO_OK;
+}
+
 B200BO_API int32_t b200bo_launch_count(b200bo_handle_t h, int64_t* n) {
   if (!h || !n) return fail(h, B200BO_ERR_ARG, "null argument");
   *n = h->launches;

@@ -65,6 +65,7 @@ struct b200bo_handle_s {
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> syrk_ev;   // start/stop pairs around every trailing-update launch of the last factorisation
   int syrk_ev_used = 0;
+  int syrk_engine = -1;      // -1: default (tcgen05 unless B200BO_SYRK_I8=0), 0: DMMA, 1: tcgen05
   bool fitted = false;
   double mll = 0.0;
   int jitter = 0;

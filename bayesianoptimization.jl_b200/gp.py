@@ -170,6 +170,10 @@ class B200GPE:
         check(lib.b200bo_fp64_peak_tflops(self._h, C.byref(v)), self._h)
         return v.value
 
+    def set_syrk_engine(self, engine: int) -> None:
+        """1 = tcgen05 int8-slice trailing updates (default), 0 = DMMA tile GEMM; takes effect at the next fit."""
+        check(lib.b200bo_set_syrk_engine(self._h, int(engine)), self._h)
+
     @property
     def launch_count(self) -> int:
         n = C.c_int64()

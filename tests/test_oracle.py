@@ -253,3 +253,25 @@ def test_ascent_restatement_improves():
     Xb, Fb = orc.ascent(gp, "MaxMean", (), X0, np.zeros(2), np.ones(2), steps=25)
     f0 = orc.acq_value("MaxMean", (), *gp.predict(X0))
     assert np.all(Fb >= f0) and Fb.mean() > f0.mean() + 0.05 and np.all((Xb >= 0) & (Xb <= 1))
+
+
+def test_int8_slicing_is_exact_and_fp64_accurate():
+    """The digit rule of the tcgen05 trailing update (csrc/syrk_i8.cu, restated in oracle/ozaki.py): digits fit int8, the 7-slice
+    representation is exact to 54 bits, and the 28-product reconstruction matches a long-double product to FP64 round-off."""
+    from oracle import ozaki
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((96, 512)) * np.exp(rng.uniform(-12, 3, (96, 1)))       # rows of very different scale
+    A[:, :40] *= 1e-7                                                               # and wide dynamic range inside a row
+    A[5] = 0.0
+    A[6, 17] = 1.0; A[6, 18] = -0.49999999999999994                                 # half-way digits
+    D, sc = ozaki.slice_rows(A)
+    assert D[0].min() >= -64 and D[0].max() <= 64 and D[1:].min() >= -128 and D[1:].max() <= 127
+    rowmax = np.abs(A).max(axis=1, keepdims=True)
+    assert np.all(np.abs(ozaki.reconstruct(D, sc) - A) <= 2.0 ** -53 * rowmax)
+    B = rng.standard_normal((64, 512)) * np.exp(rng.uniform(-6, 6, (64, 1)))
+    ref = (A.astype(np.longdouble) @ B.astype(np.longdouble).T).astype(float)
+    got = ozaki.product(A, B)
+    bound = 2.0 ** -49 * np.sqrt(512) * rowmax * np.abs(B).max(axis=1)[None, :]
+    assert np.all(np.abs(got - ref) <= bound)
+    plain = A @ B.T                                                                  # ordinary FP64 product: same error class
+    assert np.abs(got - ref).max() <= 8 * max(np.abs(plain - ref).max(), 1e-300) + bound.min()
