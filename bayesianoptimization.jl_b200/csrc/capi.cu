@@ -672,7 +672,7 @@ B200BO_API int32_t b200bo_fp64_peak_tflops(b200bo_handle_t h, double* tflops) {
 }
 
 B200BO_API int32_t b200bo_set_syrk_engine(b200bo_handle_t h, int32_t engine) {
-  if (!h || engine < 0 || engine > 1) return fail(h, B200BO_ERR_ARG, "engine must be 0 (DMMA) or 1 (tcgen05)");
+  if (!h || engine < 0 || engine > 2) return fail(h, B200BO_ERR_ARG, "engine must be 0 (DMMA), 1 (tcgen05, 128 x 64 tiles) or 2 (tcgen05, 128 x 128 tiles, two passes)");
   h->syrk_engine = engine;
   return B200BO_OK;
 }

@@ -431,7 +431,7 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
     if (p1 >= nblk) break;
     cudaEvent_t Pk = h->la_ev[2 * P], Rk = h->la_ev[2 * P + 1];
     // K = 512 updates on tcgen05 (int8 slices, syrk_i8.cu) when enabled and the outer panel is full; else the DMMA tile GEMM
-    const bool i8 = (h->syrk_engine < 0 ? syrk_i8_enabled() : h->syrk_engine == 1) && (p1 - p0) == OB;
+    const bool i8 = (h->syrk_engine < 0 ? syrk_i8_enabled() : h->syrk_engine >= 1) && (p1 - p0) == OB;
     if (i8) {
       if (P > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (P - 1) + 1], 0);   // the far part of panel P-1 still reads the previous slices
       launch_slice_panel(h, sa, p1 * NB, p0 * NB);

@@ -153,7 +153,8 @@ B200BO_API int32_t b200bo_last_timing_ms(b200bo_handle_t h, int32_t which, float
 B200BO_API int32_t b200bo_launch_count(b200bo_handle_t h, int64_t* launches);   /* kernels launched since create */
 B200BO_API int32_t b200bo_fp64_peak_tflops(b200bo_handle_t h, double* tflops);   /* self-measured DMMA.8x8x4 rate: the
                                                                         FP64 tensor-pipe roofline denominator */
-/* engine of the K = 512 trailing updates of the factorisation: 1 = tcgen05 int8-slice product (default), 0 = DMMA tile GEMM.
+/* engine of the K = 512 trailing updates of the factorisation: 1 = tcgen05 int8-slice product on 128 x 64 tiles (default),
+   2 = the same on 128 x 128 tiles in two passes (experimental, no faster), 0 = DMMA tile GEMM.
    Both are FP64-accurate; the switch exists so that tests and benches can compare them in one process. */
 B200BO_API int32_t b200bo_set_syrk_engine(b200bo_handle_t h, int32_t engine);
 B200BO_API int32_t b200bo_version(void);

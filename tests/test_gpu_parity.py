@@ -137,14 +137,14 @@ def test_kmat_extreme_signal_variance(bo):
 
 @pytest.mark.parametrize("N,D", [(1100, 4), (2560, 8), (4096, 16)])
 def test_trailing_update_engines_agree(bo, N, D):
-    """K = 512 trailing updates on tcgen05 (int8 slices, default) and on DMMA give the same factor to FP64 round-off, and both
-    match LAPACK; the tcgen05 path is deterministic."""
+    """K = 512 trailing updates on tcgen05 (int8 slices; 64-wide tiles = default, 128-wide two-pass variant) and on DMMA give the
+    same factor to FP64 round-off, and all match LAPACK; the tcgen05 path is deterministic."""
     rng = np.random.default_rng(N)
     X = rng.random((D, N)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N)
     ll = np.full(D, np.log(np.sqrt(D) * 0.3))
     o = orc.GPOracle(D, "SEArd", "MeanConst", ll=ll, lsigma=0.1, lognoise=-2.0, beta=0.2).fit(X, y)
     res = {}
-    for eng in (1, 0, 1):
+    for eng in (1, 0, 2, 1):
         g = bo.B200GPE(D, mean=bo.MeanConst(0.2), kernel=bo.SEArd(ll, 0.1), logNoise=-2.0, capacity=N)
         g.set_syrk_engine(eng)
         g.fit(X, y)
@@ -154,7 +154,7 @@ def test_trailing_update_engines_agree(bo, N, D):
         if eng in res:
             assert np.array_equal(res[eng][0], U) and np.array_equal(res[eng][1], g.alpha)      # bitwise reproducible
         res[eng] = (U, g.alpha.copy())
-    assert relmax(res[1][0], res[0][0]) < 1e-12
+    assert relmax(res[1][0], res[0][0]) < 1e-12 and relmax(res[2][0], res[0][0]) < 1e-12
 
 
 @pytest.mark.parametrize("N", [1920, 2560, 4096])
