@@ -14,6 +14,7 @@
 //   Two-level blocking: inner panels of 128 inside outer panels of 512; the update right of an outer panel is one K = 512
 //   launch.  Look-ahead: the next outer panel is factorised on the handle's stream while the far part of the previous
 //   K = 512 update runs on a second stream.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include "tma.cuh"
@@ -382,7 +383,7 @@ static int syrk_tiles(int bi_lo, int nblk, int col2_lo, int col2_hi) {
   return n;
 }
 
-constexpr int OB = 4;   // outer panel = 4 inner panels = 512 columns
+static const int OB = (getenv("B200BO_OB") && atoi(getenv("B200BO_OB")) >= 1 && atoi(getenv("B200BO_OB")) <= 4) ? atoi(getenv("B200BO_OB")) : 4;   // inner panels per outer panel (developer knob; 4 = 512 columns)
 
 cudaError_t launch_cholesky(b200bo_handle_s* h) {
   const int nblk = (int)(h->Np / NB);
@@ -434,18 +435,22 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
     const bool i8 = (h->syrk_engine < 0 ? syrk_i8_enabled() : h->syrk_engine >= 1) && (p1 - p0) == OB;
     if (i8) {
       if (P > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (P - 1) + 1], 0);   // the far part of panel P-1 still reads the previous slices
-      launch_slice_panel(h, sa, p1 * NB, p0 * NB);
+      launch_slice_panel(h, sa, p1 * NB, p0 * NB, p1 - p0);
     }
-    if (syrk_tiles(p1, nblk, 2 * p2, big) > 0) {              // far part on stream B (after panel P is complete on A)
-      cudaEventRecord(Pk, sa);
-      cudaStreamWaitEvent(sb, Pk, 0);
+    // The tcgen05 kernels are persistent (one CTA per SM, 176 KB of shared memory): the far update would occupy every SM for its
+    // whole duration and starve the critical chain (K2 needs a free SM).  It therefore runs on num_sms - reserve CTAs, which
+    // leaves `reserve` SMs to the next outer panel's chain -- a static SM partition -- and the near part (on the chain) goes first.
+    static const int reserve = getenv("B200BO_I8_RESERVE") ? atoi(getenv("B200BO_I8_RESERVE")) : 40;   // measured at N=8192: 0 -> 8.43 ms, 24 -> 7.76, 40 -> 7.51, 64 -> 7.90
+    const bool have_far = syrk_tiles(p1, nblk, 2 * p2, big) > 0;
+    if (have_far) { cudaEventRecord(Pk, sa); cudaStreamWaitEvent(sb, Pk, 0); }
+    if (P > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (P - 1) + 1], 0);   // far part of panel P-1 also wrote the next panel's columns
+    if (i8) launch_syrk_i8(h, sa, p1, 2 * p1, 2 * p2, nullptr, h->num_sms); else syrk(sa, p0, p1 - p0, p1, 2 * p1, 2 * p2);   // near part: the next outer panel's columns
+    if (have_far) {                                           // far part on stream B (after panel P is complete on A)
       cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
-      if (i8) launch_syrk_i8(h, sb, p1, 2 * p2, big, nullptr); else syrk(sb, p0, p1 - p0, p1, 2 * p2, big);
+      if (i8) launch_syrk_i8(h, sb, p1, 2 * p2, big, nullptr, std::max(8, h->num_sms - reserve)); else syrk(sb, p0, p1 - p0, p1, 2 * p2, big);
       cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
       cudaEventRecord(Rk, sb);
     }
-    if (P > 0) cudaStreamWaitEvent(sa, h->la_ev[2 * (P - 1) + 1], 0);   // far part of panel P-1 also wrote the next panel's columns
-    if (i8) launch_syrk_i8(h, sa, p1, 2 * p1, 2 * p2, nullptr); else syrk(sa, p0, p1 - p0, p1, 2 * p1, 2 * p2);   // near part: the next outer panel's columns
   }
   cudaEventRecord(h->fw_ev[nblk + 1], sb);
   cudaStreamWaitEvent(sa, h->fw_ev[nblk + 1], 0);                             // join stream B (forward solve and far updates)

@@ -45,6 +45,7 @@ struct b200bo_handle_s {
   CUtensorMap tmKi64, tmWT128, tmWT64, tmTT128;
   void* dSl = nullptr;       // [8 slices][cap][512] int8 slices of the current outer panel (syrk_i8.cu), allocated on first use
   double* dSe = nullptr;     // [cap] per-row scale 2^(e-6) of the slices
+  int i8_nkb = 4;            // 128-column k-blocks in the current slices (= inner panels per outer panel)
   CUtensorMap tmSlA, tmSlB;
   int64_t nslots = 0;
   double* dscal = nullptr;   // small scalar outputs (logdet, r'alpha, ...)
@@ -85,8 +86,8 @@ cudaError_t launch_kmat(b200bo_handle_s* h, double* dK, int64_t ld, int64_t N, i
 cudaError_t launch_cholesky(b200bo_handle_s* h);   // in place on h->dL (lower triangle), fills dLinv/dLinvT, upper mirror
 // syrk_i8.cu
 bool syrk_i8_enabled();
-cudaError_t launch_slice_panel(b200bo_handle_s* h, cudaStream_t st, int row0, int col0);
-cudaError_t launch_syrk_i8(b200bo_handle_s* h, cudaStream_t st, int bi_lo, int col2_lo, int col2_hi, int* ntiles);
+cudaError_t launch_slice_panel(b200bo_handle_s* h, cudaStream_t st, int row0, int col0, int nkb);
+cudaError_t launch_syrk_i8(b200bo_handle_s* h, cudaStream_t st, int bi_lo, int col2_lo, int col2_hi, int* ntiles, int max_ctas);
 // solve.cu
 cudaError_t launch_alpha_mll(b200bo_handle_s* h, bool have_z);  // dw = y - m -> dz (unless have_z), dalpha, dscal[0] = logdet, dscal[1] = r'alpha
 cudaError_t launch_residual(b200bo_handle_s* h, cudaStream_t st);            // dw = y - m (zero in the padding)

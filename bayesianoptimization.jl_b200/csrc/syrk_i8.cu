@@ -31,15 +31,19 @@ constexpr size_t I8_SMEM = 2 * I8_S * I8_B_BYTES + I8_ASTAGES * I8_A_BYTES + 102
 constexpr int I8_THREADS = 320;          // producer warp, MMA warp, 8 epilogue warps
 
 // ---- FP64 panel rows -> 8 int8 slices + scale.  One warp per row, 16 consecutive columns per lane. ----
-__global__ void __launch_bounds__(256) slice_panel_kernel(const double* __restrict__ L, int64_t ld, int row0, int nrows, int col0,
+__global__ void __launch_bounds__(256) slice_panel_kernel(const double* __restrict__ L, int64_t ld, int row0, int nrows, int col0, int ncols,
                                                           int8_t* __restrict__ Sl, double* __restrict__ Se, int64_t cap) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= nrows) return;
   const int row = row0 + warp;
+  const bool live = 16 * lane < ncols;                        // the panel is 128 * nkb <= 512 columns wide
   const double* src = L + (int64_t)row * ld + col0 + 16 * lane;
   double x[16];
 #pragma unroll
-  for (int u = 0; u < 16; u += 2) { const double2 v = *reinterpret_cast<const double2*>(src + u); x[u] = v.x; x[u + 1] = v.y; }
+  for (int u = 0; u < 16; u += 2) {
+    const double2 v = live ? *reinterpret_cast<const double2*>(src + u) : make_double2(0.0, 0.0);
+    x[u] = v.x; x[u + 1] = v.y;
+  }
   double m = 0.0;
 #pragma unroll
   for (int u = 0; u < 16; ++u) m = fmax(m, fabs(x[u]));
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(256) slice_panel_kernel(const double* __restri
       t[u] = (t[u] - d) * 256.0;
       w[u >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)d) << (8 * (u & 3));
     }
-    *reinterpret_cast<uint4*>(Sl + ((int64_t)s * cap + row) * I8_K + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (live) *reinterpret_cast<uint4*>(Sl + ((int64_t)s * cap + row) * I8_K + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   if (lane == 0) Se[row] = ldexp(1.0, e - 6);
 }
@@ -120,7 +124,7 @@ __device__ __forceinline__ void i8_tile(int t, int bi_lo, int col2_lo, int col2_
 // Persistent: CTA b walks tiles b, b + grid, ...; the pipelines (A ring, B double buffer, TMEM full/empty) run across tiles, so the
 // producer prefetches the next tile's operands during the epilogue and the next tile's MMAs start as soon as TMEM has been read.
 __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restrict__ C, int64_t ld, const double* __restrict__ Se, int bi_lo,
-                                                                int col2_lo, int col2_hi, int nblk, int ntiles,
+                                                                int col2_lo, int col2_hi, int nblk, int ntiles, int nkb,
                                                                 const __grid_constant__ I8Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sB = smem_raw;                                     // [2][8 slices][64 rows x 128 B]
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int bi, c2; i8_tile(tile, bi_lo, col2_lo, col2_hi, nblk, bi, c2);
         const int arow = bi * I8_BM, brow = c2 * I8_BN;
-        for (int kb = 0; kb < I8_K / 128; ++kb, ++bcnt) {
+        for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
           const int bs = bcnt & 1;
           mbar_wait_or_trap(&bempty[bs], ((bcnt >> 1) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&bfull[bs], I8_S * I8_B_BYTES);
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
         mbar_wait_or_trap(tempty, (it & 1u) ^ 1u);            // the epilogue has read the previous tile's accumulators
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         uint32_t started = 0;                                 // bit d: accumulator d already holds a product of this tile
-        for (int kb = 0; kb < I8_K / 128; ++kb, ++bcnt) {
+        for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
           const int bs = bcnt & 1;
           mbar_wait_or_trap(&bfull[bs], (bcnt >> 1) & 1u);
           for (int p = 0; p < I8_S; ++p) {
@@ -291,7 +295,7 @@ __device__ __forceinline__ int i8w_qhi(int pass, int p) { return pass ? 6 - p : 
 __device__ __forceinline__ int i8w_last_p(int pass, int q) { return pass ? (4 - q > 0 ? 4 - q : 0) : 3 - q; }   // last p that uses B slice q
 
 __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8w_kernel(double* __restrict__ C, int64_t ld, const double* __restrict__ Se, int bi_lo,
-                                                                 int cj_lo, int cj_hi, int nblk, int ntiles,
+                                                                 int cj_lo, int cj_hi, int nblk, int ntiles, int nkb,
                                                                  const __grid_constant__ CUtensorMap map) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sB = smem_raw;                                     // [7 slots][128 rows x 128 B], slot q = slice q of the current k-block
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8w_kernel(double* __restr
         int bi, cj; i8w_tile(tile, bi_lo, cj_lo, cj_hi, nblk, bi, cj);
         const int arow = bi * I8_BM, brow = cj * I8W_BN;
         for (int pass = 0; pass < 2; ++pass)
-          for (int kb = 0; kb < I8_K / 128; ++kb) {
+          for (int kb = 0; kb < nkb; ++kb) {
             uint32_t have = 0;                                // B slices already requested for this (pass, k-block)
             for (int i = 0; i < i8w_np(pass); ++i) {
               const int p = i8w_p(pass, i);
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8w_kernel(double* __restr
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           uint32_t started = 0;                               // bit a: accumulator a already holds a product of this pass
           const int dmin = pass ? 4 : 0;
-          for (int kb = 0; kb < I8_K / 128; ++kb) {
+          for (int kb = 0; kb < nkb; ++kb) {
             uint32_t have = 0;
             for (int i = 0; i < i8w_np(pass); ++i) {
               const int p = i8w_p(pass, i);
@@ -473,7 +477,7 @@ bool syrk_i8_enabled() {
 }
 
 // slices of the finished outer panel: rows [row0, Np) x columns [col0, col0 + 512) of the factor
-cudaError_t launch_slice_panel(b200bo_handle_s* h, cudaStream_t st, int row0, int col0) {
+cudaError_t launch_slice_panel(b200bo_handle_s* h, cudaStream_t st, int row0, int col0, int nkb) {
   const int64_t cap = h->cap;
   if (!h->dSl) {
     cudaError_t e = cudaMalloc(&h->dSl, (size_t)I8_S * cap * I8_K);
@@ -484,13 +488,14 @@ cudaError_t launch_slice_panel(b200bo_handle_s* h, cudaStream_t st, int row0, in
   }
   const int nrows = (int)h->Np - row0;
   if (nrows <= 0) return cudaSuccess;
-  slice_panel_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(h->dL, h->ld, row0, nrows, col0, reinterpret_cast<int8_t*>(h->dSl), h->dSe, cap);
+  slice_panel_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(h->dL, h->ld, row0, nrows, col0, 128 * nkb, reinterpret_cast<int8_t*>(h->dSl), h->dSe, cap);
+  h->i8_nkb = nkb;
   h->launches++;
   return cudaGetLastError();
 }
 
 // A_ij -= L_i,P L_j,P^T over the tiles (bi >= bi_lo, 64-wide column blocks [col2_lo, min(col2_hi, 2 bi + 2))) from the current slices
-cudaError_t launch_syrk_i8(b200bo_handle_s* h, cudaStream_t st, int bi_lo, int col2_lo, int col2_hi, int* ntiles) {
+cudaError_t launch_syrk_i8(b200bo_handle_s* h, cudaStream_t st, int bi_lo, int col2_lo, int col2_hi, int* ntiles, int max_ctas) {
   const int nblk = (int)(h->Np / NB);
   static const bool wide_env = getenv("B200BO_SYRK_I8") && atoi(getenv("B200BO_SYRK_I8")) == 2;
   if (h->syrk_engine == 2 || (h->syrk_engine < 0 && wide_env)) {   // 128 x 128 tiles, two passes (measured: no faster, see the header)
@@ -500,8 +505,8 @@ cudaError_t launch_syrk_i8(b200bo_handle_s* h, cudaStream_t st, int bi_lo, int c
     if (ntiles) *ntiles = n;
     if (n == 0) return cudaSuccess;
     cudaFuncSetAttribute(syrk_i8w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8W_SMEM);
-    const int grid = n < h->num_sms ? n : h->num_sms;
-    syrk_i8w_kernel<<<grid, I8_THREADS, I8W_SMEM, st>>>(h->dL, h->ld, h->dSe, bi_lo, cj_lo, cj_hi, nblk, n, h->tmSlA);
+    const int grid = n < max_ctas ? n : max_ctas;
+    syrk_i8w_kernel<<<grid, I8_THREADS, I8W_SMEM, st>>>(h->dL, h->ld, h->dSe, bi_lo, cj_lo, cj_hi, nblk, n, h->i8_nkb, h->tmSlA);
     h->launches++;
     return cudaGetLastError();
   }
@@ -511,8 +516,8 @@ cudaError_t launch_syrk_i8(b200bo_handle_s* h, cudaStream_t st, int bi_lo, int c
   cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM);
   I8Maps maps;
   maps.A = h->tmSlA; maps.B = h->tmSlB;
-  const int grid = n < h->num_sms ? n : h->num_sms;
-  syrk_i8_kernel<<<grid, I8_THREADS, I8_SMEM, st>>>(h->dL, h->ld, h->dSe, bi_lo, col2_lo, col2_hi, nblk, n, maps);
+  const int grid = n < max_ctas ? n : max_ctas;
+  syrk_i8_kernel<<<grid, I8_THREADS, I8_SMEM, st>>>(h->dL, h->ld, h->dSe, bi_lo, col2_lo, col2_hi, nblk, n, h->i8_nkb, maps);
   h->launches++;
   return cudaGetLastError();
 }
