@@ -5,15 +5,16 @@
 // Sigma = U'U in column-major storage; that is byte-identical to the row-major lower L = U' kept here.
 //
 //   for each 128-wide panel k:
-//     K2 potrf_diag   : L_kk = chol(A_kk) by ONE 1024-thread CTA, one barrier per column; the same sweep carries the
-//                       forward substitution on I, so L_kk^-1 (needed by every GEMM-shaped solve) costs no extra pass.
+//     K2 potrf_diag   : L_kk = chol(A_kk) and L_kk^-1 by ONE 256-thread CTA (latency-first; see the kernel's header).
 //     K3 trsm_panel   : A_ik <- A_ik L_kk^-T = (L_kk^-1 A_ik^T)^T                (TMA + DMMA tile GEMM, K = 128)
-//     K4 syrk_trailing: A_ij <- A_ij - L_ik L_jk^T  for i >= j > k              (TMA + DMMA tile GEMM: the dense contraction)
+//     K4 syrk_trailing: A_ij <- A_ij - L_ik L_jk^T  for i >= j > k              (inner updates: TMA + DMMA tile GEMM, K = 128)
 //   The upper triangle of h->dL receives L^T ("mirrored factor") so the backward solve L^T w = v reads the same
 //   k-major rows as the forward one.
-//   Two-level blocking: inner panels of 128 inside outer panels of 512; the update right of an outer panel is one K = 512
-//   launch.  Look-ahead: the next outer panel is factorised on the handle's stream while the far part of the previous
-//   K = 512 update runs on a second stream.
+//   Two-level blocking: inner panels of 128 inside outer panels of 512; the update right of a full outer panel is a K = 512
+//   launch on the 5th-generation tensor cores (syrk_i8.cu: int8-slice product on tcgen05.mma, TMEM accumulators) -- the DMMA
+//   kernel serves ragged panels and `b200bo_set_syrk_engine(h, 0)`.  Look-ahead: the next outer panel is factorised on the
+//   handle's stream while the far part of the previous K = 512 update runs on a second stream, on num_sms - 40 persistent CTAs so
+//   that the critical chain always finds free SMs; the forward solve of y - m rides along on that stream too.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
