@@ -85,9 +85,11 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 // Block row i (1..3) of W = L^-1:  W_ij = -W_ii sum_{k=j}^{i-1} L_ik W_kj for j < i, as 32^3 DMMA products by `nw` warps (this warp
 // is worker `wid`); `named` selects the barrier between the two product phases (warps 1-7 only, or the whole CTA).
 // W[r][c] (r >= c) is kept at S[c][r] (the diagonal of S holds w_rr = 1/l_rr); L[r][c] (r > c) at S[r][c].
+// `phases`: 1 = the products P_j only (they need block rows < i of W, not W_ii), 2 = the final products only, 3 = both.
 __device__ __forceinline__ void winv_block_row(double* __restrict__ S, double* __restrict__ Pb, int i, int wid, int nw, bool named, int g,
-                                               int q) {
+                                               int q, int phases = 3) {
   // P_j = sum_k L_ik W_kj  (32 x 32, K = 32 (i - j)); two accumulator chains per 8 x 8 tile
+  if (phases & 1)
   for (int t = wid; t < i * 16; t += nw) {
     const int j = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
     double c0a = 0.0, c1a = 0.0, e0a = 0.0, e1a = 0.0;
@@ -108,8 +110,9 @@ __device__ __forceinline__ void winv_block_row(double* __restrict__ S, double* _
     double* pp = Pb + (j * PSUB + 8 * tr + g) * PSUB + 8 * tc + 2 * q;
     *reinterpret_cast<double2*>(pp) = make_double2(c0a + e0a, c1a + e1a);
   }
-  if (named) asm volatile("bar.sync 1, 224;\n" ::: "memory"); else __syncthreads();
+  if (phases == 3) { if (named) asm volatile("bar.sync 1, 224;\n" ::: "memory"); else __syncthreads(); }
   // W_ij = -W_ii P_j, stored transposed into the upper triangle
+  if (phases & 2)
   for (int t = wid; t < i * 16; t += nw) {
     const int j = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
     double c0a = 0.0, c1a = 0.0, e0a = 0.0, e1a = 0.0;
@@ -230,6 +233,10 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
       }
       // block row s-1 of L^-1 (needs the inverses of diagonal sub-blocks 0 .. s-1): hidden behind F(s)
       if (s >= 2) winv_block_row(S, Pb, s - 1, warp - 1, PD_THREADS / 32 - 1, true, g, q);
+      if (s == NB / PSUB - 1) {   // the products of the LAST block row only need rows < 3 of W: also hidden behind F(3)
+        asm volatile("bar.sync 1, 224;\n" ::: "memory");       // row s-1 of W complete, Pb free again
+        winv_block_row(S, Pb, s, warp - 1, PD_THREADS / 32 - 1, true, g, q, 1);
+      }
     }
 #ifdef POTRF_PROF
     if (threadIdx.x == 0) g_potrf_prof[8 + s] += (unsigned long long)(clock64() - t_prev);      // warp 0's own F(s) time
@@ -283,8 +290,8 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
     }
     PROF_T(3);
   }
-  // ---------------- the last block row of L^-1 ----------------
-  winv_block_row(S, Pb, NB / PSUB - 1, warp, PD_THREADS / 32, false, g, q);
+  // ---------------- the last block row of L^-1: only its final products are left ----------------
+  winv_block_row(S, Pb, NB / PSUB - 1, warp, PD_THREADS / 32, false, g, q, 2);   // W_3j = -W_33 P_j (P_j computed during F(3))
   __syncthreads();
   PROF_T(4);
   // ---------------- write-back: mirrored factor block (full), L^-1 (lower) and L^-T (upper); the other triangles of the inverse
