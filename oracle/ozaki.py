@@ -12,11 +12,16 @@ S = 7
 C = 128.0 / 255.0
 
 
-def slice_rows(X):
-    """X [rows][K] float64 -> (digits int64 [S][rows][K], scale [rows] = 2^(e-6)) with the kernel's digit rule."""
+def slice_rows(X, e=None):
+    """X [rows][K] float64 -> (digits int64 [S][rows][K], scale [rows] = 2^(e-6)) with the kernel's digit rule.
+    `e` (scalar or per row) fixes the exponent instead of taking it from the row maximum (|x| <= 2^e must hold)."""
     X = np.asarray(X, float)
     m = np.max(np.abs(X), axis=1)
-    e = np.where(m > 0, np.frexp(m)[1], 0)                    # |x| < 2^e  (frexp: m = f 2^e, f in [0.5, 1))
+    if e is None:
+        e = np.where(m > 0, np.frexp(m)[1], 0)                # |x| < 2^e  (frexp: m = f 2^e, f in [0.5, 1))
+    else:
+        e = np.broadcast_to(np.asarray(e, int), m.shape)
+        assert np.all(m <= np.ldexp(1.0, e))
     t = X * np.ldexp(1.0, 6 - e)[:, None]
     D = np.empty((S,) + X.shape, np.int64)
     for s in range(S):
@@ -33,10 +38,10 @@ def reconstruct(D, scale):
     return acc * scale[:, None]
 
 
-def product(A, B):
+def product(A, B, ea=None, eb=None):
     """A [m][K], B [n][K] -> A B^T as the kernel computes it: anti-diagonal int accumulators, two 64-bit groups, row scales."""
-    Da, sa = slice_rows(A)
-    Db, sb = slice_rows(B)
+    Da, sa = slice_rows(A, ea)
+    Db, sb = slice_rows(B, eb)
     acc = [np.zeros((A.shape[0], B.shape[0]), np.int64) for _ in range(S)]
     for p in range(S):
         for q in range(S - p):

@@ -275,3 +275,34 @@ def test_int8_slicing_is_exact_and_fp64_accurate():
     assert np.all(np.abs(got - ref) <= bound)
     plain = A @ B.T                                                                  # ordinary FP64 product: same error class
     assert np.abs(got - ref).max() <= 8 * max(np.abs(plain - ref).max(), 1e-300) + bound.min()
+
+
+def test_sliced_forward_solve_keeps_posterior_accuracy():
+    """Design check for moving the acquisition kernel's off-diagonal products to int8 slices (tcgen05 findings):
+    L sliced once with one scale per ROW over the whole row, the solve panel V sliced with the FIXED scale sigma_f (|v| <= sigma_f
+    because ||v||^2 <= k**), diagonal-block solves in FP64.  The posterior variance -- the cancelling quantity -- must stay within
+    the north_star tolerance by orders of magnitude."""
+    from oracle import ozaki
+    from scipy.linalg import solve_triangular
+    rng = np.random.default_rng(5)
+    D, N, M, nb = 6, 512, 48, 128
+    X = rng.random((D, N)); y = -orc.hartmann6(X)
+    o = orc.GPOracle(D, "Mat52Ard", "MeanConst", ll=np.zeros(D), lsigma=0.3, lognoise=-2.0, beta=0.0).fit(X, y)
+    Xs = rng.random((D, M)); Xs[:, 0] = X[:, 7]; Xs[:, 1] = X[:, 300] + 1e-7           # on / next to training points: s2 cancels
+    L = o.U.T.copy()
+    ks = o.cov(o.X, Xs)                                                               # N x M
+    sf = np.exp(o.lsigma)
+    eV = int(np.frexp(sf * (1 + 1e-12))[1])                                           # |v| <= sigma_f < 2^eV
+    eL = np.frexp(np.abs(L).max(axis=1))[1]                                           # one exponent per row of L, whole row
+    V = np.zeros((N, M))
+    for i in range(0, N, nb):
+        R = ks[i:i + nb].copy()
+        if i > 0:
+            R -= ozaki.product(L[i:i + nb, :i], V[:i].T.copy(), ea=eL[i:i + nb], eb=eV)
+        V[i:i + nb] = solve_triangular(L[i:i + nb, i:i + nb], R, lower=True)
+    Vref = solve_triangular(L.astype(np.longdouble).astype(float), ks, lower=True)
+    var = np.maximum(sf ** 2 - np.sum(V * V, axis=0), 0.0)
+    mo, vo = o.predict(Xs)
+    vref = np.maximum(sf ** 2 - np.sum(Vref * Vref, axis=0), 0.0)
+    assert np.abs(V - Vref).max() <= 1e-13 * sf
+    assert np.all(np.abs(var - vo) <= 1e-9 * np.abs(vo) + 1e-13) and np.all(np.abs(vref - vo) <= 1e-9 * np.abs(vo) + 1e-13)
