@@ -459,3 +459,26 @@ def test_elastic_append_matches_refit(bo, kern, N0):
     bo.update(g, X[:, :1], y[:1])
     ref.set_params(ref.get_params() + 0.1); ref.fit(np.hstack([X, X[:, :1]]), np.concatenate([y, y[:1]]))
     assert relmax(g.alpha, ref.alpha) < 1e-10
+
+
+def test_kmat_dev_unaligned_target_uses_the_16_byte_store_path(bo):
+    """b200bo_kmat_dev into a caller buffer that is only 16-byte aligned with ld = 2 (mod 4): K1's 128-bit store instantiation
+    (the 32-byte STG.E.256 path needs 32-byte alignment and ld % 4 == 0) must give the same matrix, ragged N included."""
+    import ctypes as C
+    import torch
+    from b200bo import _lib
+    rng = np.random.default_rng(9)
+    D, N = 5, 333
+    X = rng.random((D, N)); y = rng.standard_normal(N)
+    g = bo.B200GPE(D, mean=bo.MeanZero(), kernel=bo.Mat32Ard(np.full(D, -0.3), 0.2), logNoise=-1.5, capacity=N)
+    g.fit(X, y)
+    K = g.kmat()
+    for ld, off in ((336, 0), (334, 2)):                                        # 32-byte aligned, ld % 4 == 0  /  16-byte aligned, ld % 4 == 2
+        buf = torch.zeros(ld * N + 8, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()                                                # the fill runs on torch's stream, K1 on the library's
+        ptr = buf.data_ptr() + 8 * off
+        assert ptr % 32 == (16 if off else 0)
+        _lib.check(_lib.lib.b200bo_kmat_dev(g._h, C.c_void_p(ptr), ld), g._h)
+        _lib.check(_lib.lib.b200bo_sync(g._h), g._h)
+        out = buf[off:off + ld * N].view(N, ld)[:, :N].cpu().numpy()
+        assert np.array_equal(out, K), (ld, off)
