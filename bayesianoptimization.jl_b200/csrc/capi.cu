@@ -36,10 +36,10 @@ int num_params(const b200bo_handle_s* h) {
 }
 
 void free_device(b200bo_handle_s* h) {
-  cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dZk); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dz); cudaFree(h->dinv_ell);
+  cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dZk); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dz); cudaFree(h->dflags); cudaFree(h->dinv_ell);
   cudaFree(h->dL); cudaFree(h->dLinv); cudaFree(h->dLinvT); cudaFree(h->dV); cudaFree(h->dKi); cudaFree(h->dWT); cudaFree(h->dTT); cudaFree(h->dSl); cudaFree(h->dSe); cudaFree(h->dscal); cudaFree(h->dinfo);
   cudaFree(h->dcta_best); cudaFree(h->dbest); cudaFree(h->dpart);
-  h->dz = nullptr; h->dKi = h->dWT = h->dTT = nullptr; h->dSl = nullptr; h->dSe = nullptr;
+  h->dz = nullptr; h->dflags = nullptr; h->dKi = h->dWT = h->dTT = nullptr; h->dSl = nullptr; h->dSe = nullptr;
   h->dX = h->dZ = h->dZk = h->dy = h->dw = h->dalpha = h->dinv_ell = h->dL = h->dLinv = h->dLinvT = h->dV = h->dscal = h->dpart = nullptr;
   h->dinfo = nullptr; h->dcta_best = nullptr; h->dbest = nullptr;
 }
@@ -58,6 +58,9 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   CU(cudaMalloc(&h->dw, sizeof(double) * cap));
   CU(cudaMalloc(&h->dalpha, sizeof(double) * cap));
   CU(cudaMalloc(&h->dz, sizeof(double) * cap));
+  CU(cudaMalloc(&h->dflags, sizeof(int) * (cap / NB)));
+  CU(cudaMemsetAsync(h->dflags, 0, sizeof(int) * (cap / NB), h->stream));
+  h->solve_epoch = 0;
   CU(cudaMalloc(&h->dinv_ell, sizeof(double) * h->D));
   CU(cudaMalloc(&h->dL, sizeof(double) * cap * cap));
   CU(cudaMalloc(&h->dLinv, sizeof(double) * nb * NB * NB));

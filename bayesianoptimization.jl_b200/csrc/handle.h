@@ -35,6 +35,8 @@ struct b200bo_handle_s {
   double* dw = nullptr;      // [cap] work vector for the single-RHS solves
   double* dalpha = nullptr;  // [cap] (zero in the padding)
   double* dz = nullptr;      // [cap] z = L^-1 (y - m), kept for elastic appends
+  int* dflags = nullptr;     // [cap/128] "alpha block ready" epochs of the one-launch backward solve (solve.cu)
+  int solve_epoch = 0;
   double noise_total = 0.0;  // diagonal noise of the current factor (incl. make_posdef! jitter)
   double* dinv_ell = nullptr;  // [D]
   double* dL = nullptr;      // [ld][ld] mirrored factor: lower = L (row-major) == U column-major, upper = L^T

@@ -5,6 +5,7 @@
 // HBM-bound: each solve reads the triangle once (4 N^2 bytes).  Right-looking over 128-wide blocks, one launch
 // per block: CTA b applies the just-solved block to its 128 rows; the CTA that owns the next diagonal block
 // then solves it with the pre-inverted block (fixed summation order => deterministic).
+#include <cstdlib>
 #include "common.cuh"
 #include "handle.h"
 
@@ -114,6 +115,62 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict_
   if (solver) diag_apply(dv, w + (int64_t)cb * NB, alpha + (int64_t)cb * NB, sh, tid);
 }
 
+// The whole backward solve alpha = L^-T z in ONE launch: CTA b owns column block cb = nblk - 1 - b and stays resident; it streams
+// the blocks L[i][cb] (i = nblk-1 .. cb+1) into registers one block ahead, waits for alpha_i through a release/acquire flag in
+// global memory, accumulates, and finally applies the pre-inverted diagonal block and publishes alpha_cb.  The dependency chain
+// costs one flag hop + a 128 x 128 product per block instead of one kernel launch (bwd_step_kernel: 32 dependent launches at
+// N = 4096).  Deadlock-free: a CTA only waits on CTAs with a SMALLER blockIdx (dispatched no later than itself), nblk <= 148 CTAs
+// of 512 threads are co-resident, and the spin is bounded (trap).  512 threads: thread (c, qd) covers rows 32 qd .. +31 of every
+// block for column c; fixed summation order => deterministic.
+__global__ void __launch_bounds__(512, 1) bwd_persistent_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ Linv,
+                                                                const double* __restrict__ z, double* __restrict__ alpha, int nblk,
+                                                                int* __restrict__ flags, int epoch) {
+  __shared__ double sh[NB];
+  __shared__ double part[4][NB];
+  const int tid = threadIdx.x, c = tid & 127, qd = tid >> 7;
+  const int cb = nblk - 1 - (int)blockIdx.x;
+  double dv[32], v[32];
+  {
+    const double* MT = Linv + (int64_t)cb * NB * NB;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) dv[u] = ldcg1_issue(MT + (qd * 32 + u) * NB + c);
+  }
+  double acc = 0.0;
+  for (int i = nblk - 1; i > cb; --i) {
+    const double* Lc = L + ((int64_t)i * NB + qd * 32) * ld + (int64_t)cb * NB + c;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) v[u] = ldcg1_issue(Lc + (int64_t)u * ld);       // in flight while the flag is awaited
+    if (tid == 0) {
+      int f = 0, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(f) : "l"(flags + i) : "memory");
+      } while (f != epoch && ++spins < (1 << 26));
+      if (f != epoch) __trap();
+    }
+    __syncthreads();
+    if (tid < NB) sh[tid] = __ldcg(alpha + (int64_t)i * NB + tid);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 32; ++u) acc = fma(v[u], sh[qd * 32 + u], acc);
+    __syncthreads();                                           // sh is rewritten in the next round
+  }
+  part[qd][c] = acc;
+  __syncthreads();
+  if (tid < NB) sh[tid] = z[(int64_t)cb * NB + tid] - (((part[0][tid] + part[1][tid]) + part[2][tid]) + part[3][tid]);
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) s = fma(dv[u], sh[qd * 32 + u], s);
+  part[qd][c] = s;
+  __syncthreads();
+  if (tid < NB) alpha[(int64_t)cb * NB + tid] = ((part[0][tid] + part[1][tid]) + part[2][tid]) + part[3][tid];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(flags + cb), "r"(epoch) : "memory");
+  }
+}
+
 // scal[0] = logdet = 2 sum log L_ii (i < N), scal[1] = r'alpha.  Single CTA, fixed order.
 __global__ void __launch_bounds__(256) logdet_dot_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ y,
                                                          double beta, const double* __restrict__ alpha, int N, double* __restrict__ scal) {
@@ -160,6 +217,12 @@ cudaError_t launch_forward_solve(b200bo_handle_s* h, double* w, double* z, int n
 
 // alpha = L^-T z  (w is scratch)
 cudaError_t launch_backward_solve(b200bo_handle_s* h, const double* z, double* w, double* alpha, int nblk) {
+  static const bool stepwise = getenv("B200BO_BWD_STEPWISE") != nullptr;       // developer knob: the one-launch-per-block path
+  if (!stepwise && nblk >= 1 && nblk <= h->num_sms) {
+    bwd_persistent_kernel<<<nblk, 512, 0, h->stream>>>(h->dL, h->ld, h->dLinv, z, alpha, nblk, h->dflags, ++h->solve_epoch);
+    h->launches++;
+    return cudaGetLastError();
+  }
   cudaMemcpyAsync(w, z, sizeof(double) * nblk * NB, cudaMemcpyDeviceToDevice, h->stream);
   for (int i = nblk; i >= 1; --i) {
     const int grid = (i < nblk) ? i : 1;
