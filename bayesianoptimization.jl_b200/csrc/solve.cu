@@ -122,13 +122,17 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict_
 // N = 4096).  Deadlock-free: a CTA only waits on CTAs with a SMALLER blockIdx (dispatched no later than itself), nblk <= 148 CTAs
 // of 512 threads are co-resident, and the spin is bounded (trap).  512 threads: thread (c, qd) covers rows 32 qd .. +31 of every
 // block for column c; fixed summation order => deterministic.
-__global__ void __launch_bounds__(512, 1) bwd_persistent_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ Linv,
+// FWD = true is the forward solve z = L^-1 w with the same code: CTA b owns row block b, walks i = 0 .. b-1 and reads the blocks
+// L[b][i] through the MIRRORED upper triangle (element (i*128 + r, b*128 + c) = L[b*128 + c][i*128 + r]), so the address pattern,
+// the coalescing and the in-thread reduction are identical; `Minv` is LinvT there.
+template <bool FWD>
+__global__ void __launch_bounds__(512, 1) tri_persistent_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ Linv,
                                                                 const double* __restrict__ z, double* __restrict__ alpha, int nblk,
                                                                 int* __restrict__ flags, int epoch) {
   __shared__ double sh[NB];
   __shared__ double part[4][NB];
   const int tid = threadIdx.x, c = tid & 127, qd = tid >> 7;
-  const int cb = nblk - 1 - (int)blockIdx.x;
+  const int cb = FWD ? (int)blockIdx.x : nblk - 1 - (int)blockIdx.x;
   double dv[32], v[32];
   {
     const double* MT = Linv + (int64_t)cb * NB * NB;
@@ -136,7 +140,8 @@ __global__ void __launch_bounds__(512, 1) bwd_persistent_kernel(const double* __
     for (int u = 0; u < 32; ++u) dv[u] = ldcg1_issue(MT + (qd * 32 + u) * NB + c);
   }
   double acc = 0.0;
-  for (int i = nblk - 1; i > cb; --i) {
+  for (int it = 0; it < (FWD ? cb : nblk - 1 - cb); ++it) {
+    const int i = FWD ? it : nblk - 1 - it;
     const double* Lc = L + ((int64_t)i * NB + qd * 32) * ld + (int64_t)cb * NB + c;
 #pragma unroll
     for (int u = 0; u < 32; ++u) v[u] = ldcg1_issue(Lc + (int64_t)u * ld);       // in flight while the flag is awaited
@@ -207,6 +212,12 @@ cudaError_t launch_fwd_step(b200bo_handle_s* h, cudaStream_t st, int i, int nblk
 
 // z = L^-1 w  (w is overwritten), nblk blocks of the current factor
 cudaError_t launch_forward_solve(b200bo_handle_s* h, double* w, double* z, int nblk) {
+  static const bool stepwise = getenv("B200BO_BWD_STEPWISE") != nullptr;       // developer knob: the one-launch-per-block path
+  if (!stepwise && nblk >= 1 && nblk <= h->num_sms) {
+    tri_persistent_kernel<true><<<nblk, 512, 0, h->stream>>>(h->dL, h->ld, h->dLinvT, w, z, nblk, h->dflags, ++h->solve_epoch);
+    h->launches++;
+    return cudaGetLastError();
+  }
   for (int i = -1; i < nblk - 1; ++i) {
     const int grid = i < 0 ? 1 : nblk - i - 1;
     fwd_step_kernel<<<grid, 256, 0, h->stream>>>(h->dL, h->ld, h->dLinvT, w, z, i);
@@ -219,7 +230,7 @@ cudaError_t launch_forward_solve(b200bo_handle_s* h, double* w, double* z, int n
 cudaError_t launch_backward_solve(b200bo_handle_s* h, const double* z, double* w, double* alpha, int nblk) {
   static const bool stepwise = getenv("B200BO_BWD_STEPWISE") != nullptr;       // developer knob: the one-launch-per-block path
   if (!stepwise && nblk >= 1 && nblk <= h->num_sms) {
-    bwd_persistent_kernel<<<nblk, 512, 0, h->stream>>>(h->dL, h->ld, h->dLinv, z, alpha, nblk, h->dflags, ++h->solve_epoch);
+    tri_persistent_kernel<false><<<nblk, 512, 0, h->stream>>>(h->dL, h->ld, h->dLinv, z, alpha, nblk, h->dflags, ++h->solve_epoch);
     h->launches++;
     return cudaGetLastError();
   }
