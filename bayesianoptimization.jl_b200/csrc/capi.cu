@@ -44,6 +44,8 @@ void free_device(b200bo_handle_s* h) {
   h->dinfo = nullptr; h->dcta_best = nullptr; h->dbest = nullptr;
 }
 
+int32_t sync_inv_ell(b200bo_handle_s* h);
+
 int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   cap = std::max<int64_t>(NB, (cap + NB - 1) / NB * NB);
   free_device(h);
@@ -61,7 +63,7 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   CU(cudaMalloc(&h->dflags, sizeof(int) * (cap / NB)));
   CU(cudaMemsetAsync(h->dflags, 0, sizeof(int) * (cap / NB), h->stream));
   h->solve_epoch = 0;
-  CU(cudaMalloc(&h->dinv_ell, sizeof(double) * h->D));
+  CU(cudaMalloc(&h->dinv_ell, sizeof(double) * 2 * h->D));
   CU(cudaMalloc(&h->dL, sizeof(double) * cap * cap));
   CU(cudaMalloc(&h->dLinv, sizeof(double) * nb * NB * NB));
   CU(cudaMalloc(&h->dLinvT, sizeof(double) * nb * NB * NB));
@@ -80,7 +82,7 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   CU(cudaMemsetAsync(h->dalpha, 0, sizeof(double) * cap, h->stream));
   CU(cudaMemsetAsync(h->dy, 0, sizeof(double) * cap, h->stream));
   CU(make_tensor_maps(h));
-  return B200BO_OK;
+  return sync_inv_ell(h);
 }
 
 int32_t ensure_io(b200bo_handle_s* h, int64_t bytes) {
@@ -92,18 +94,42 @@ int32_t ensure_io(b200bo_handle_s* h, int64_t bytes) {
   return B200BO_OK;
 }
 
+// [inv_ell (D) | centre (D)]: the centre (mid-range of the observations, in x units) only shifts the inputs of K1's Gram-form
+// distances (kmat.cu), whose rounding error grows with |z|^2; every other kernel works with coordinate differences
 void upload_inv_ell(b200bo_handle_s* h, std::vector<double>& ie) {
-  ie.resize(h->D);
-  for (int d = 0; d < h->D; ++d) ie[d] = exp(-(h->iso ? h->hp.ll[0] : h->hp.ll[d]));
+  const int D = h->D;
+  ie.assign(2 * D, 0.0);
+  for (int d = 0; d < D; ++d) ie[d] = exp(-(h->iso ? h->hp.ll[0] : h->hp.ll[d]));
+  const int64_t N = std::min<int64_t>(h->N, (int64_t)(h->hX.size() / D));
+  for (int d = 0; d < D && N > 0; ++d) {
+    double lo = h->hX[d], hi = lo;
+    for (int64_t i = 1; i < N; ++i) { const double x = h->hX[i * D + d]; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+    const double c = 0.5 * (lo + hi);
+    ie[D + d] = std::isfinite(c) ? c : 0.0;
+  }
+}
+
+// dinv_ell always holds the inverse length-scales of the current parameters (an empty model evaluates the prior through K6, which
+// multiplies its zero gradient accumulators by them: they must be finite from the first call on)
+int32_t sync_inv_ell(b200bo_handle_s* h) {
+  if (!h->dinv_ell) return B200BO_OK;
+  std::vector<double> ie;
+  upload_inv_ell(h, ie);
+  CU(cudaMemcpyAsync(h->dinv_ell, ie.data(), sizeof(double) * 2 * h->D, cudaMemcpyHostToDevice, h->stream));   // pageable source: staged before return
+  return B200BO_OK;
 }
 
 // Sigma assembly + Cholesky (with the make_posdef! jitter rule) + alpha + mll on the current data and params.
+int32_t upload_data(b200bo_handle_s* h);
+
 int32_t refit(b200bo_handle_s* h) {
   h->jitter = 0;
+  h->acq_ready = 0;                     // W = L^-1 and its int8 slices (acq_i8.cu) belong to the previous factor
+  if (h->need_upload) { const int32_t rc = upload_data(h); if (rc) return rc; }
   if (h->N == 0) { h->fitted = true; h->mll = 0.0; h->Np = 0; return B200BO_OK; }
   std::vector<double> ie;
   upload_inv_ell(h, ie);
-  CU(cudaMemcpyAsync(h->dinv_ell, ie.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->dinv_ell, ie.data(), sizeof(double) * 2 * h->D, cudaMemcpyHostToDevice, h->stream));
   CU(launch_scale_inputs(h, 0, h->Np));
   const double sf2 = exp(2.0 * h->hp.lsigma);
   double noise = exp(2.0 * h->hp.lognoise) + std::numeric_limits<double>::epsilon();   // quirk 10
@@ -156,6 +182,7 @@ int32_t upload_data(b200bo_handle_s* h) {
     }
   }
   h->fitted = false;
+  h->need_upload = false;
   return B200BO_OK;
 }
 
@@ -207,7 +234,15 @@ B200BO_API int32_t b200bo_create(b200bo_handle_t* out, int32_t device, int32_t D
   }
   for (auto& e : h->ev) cudaEventCreate(&e);
   int32_t rc = alloc_device(h, capacity);
-  if (rc != B200BO_OK) { g_err = h->err; free_device(h); cudaStreamDestroy(h->stream); delete h; return rc; }
+  if (rc != B200BO_OK) {
+    g_err = h->err;
+    free_device(h);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(h->stream2);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return rc;
+  }
   h->fitted = true;   // empty model: prior
   *out = h;
   return B200BO_OK;
@@ -261,7 +296,8 @@ B200BO_API int32_t b200bo_set_params(b200bo_handle_t h, const double* th, int32_
   for (auto& l : h->hp.ll) l = th[i++];
   h->hp.lsigma = th[i++];
   h->fitted = (h->N == 0);
-  return B200BO_OK;
+  cudaSetDevice(h->device);
+  return sync_inv_ell(h);
 }
 
 B200BO_API int32_t b200bo_get_params(b200bo_handle_t h, double* th, int32_t P) {
@@ -286,33 +322,56 @@ B200BO_API int32_t b200bo_fit(b200bo_handle_t h, const double* X, const double* 
   return refit(h);
 }
 
+// one elastic step per new point; *ok = false when positive definiteness is lost (the caller refactors with the jitter rule)
+static int32_t append_elastic(b200bo_handle_t h, const double* Xn, const double* yn, int64_t m, bool* ok) {
+  const int64_t D = h->D;
+  *ok = true;
+  for (int64_t j = 0; j < m && *ok; ++j) {
+    const int64_t N = h->N;
+    CU(cudaMemcpyAsync(h->dX + N * D, Xn + j * D, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dy + N, yn + j, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_scale_inputs(h, N, N + 1));
+    CU(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+    CU(launch_append_one(h, h->noise_total));          // advances h->N / h->Np
+    int info = 0;
+    double sc[2];
+    CU(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(sc, h->dscal, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (info != 0) *ok = false;
+    else h->mll = -0.5 * (sc[1] + sc[0] + (double)h->N * 1.8378770664093453);
+  }
+  return B200BO_OK;
+}
+
 B200BO_API int32_t b200bo_append(b200bo_handle_t h, const double* Xn, const double* yn, int64_t m) {
   if (!h || m < 0 || (m > 0 && (!Xn || !yn))) return fail(h, B200BO_ERR_ARG, "bad arguments to append");
+  if (m == 0) return B200BO_OK;
   cudaSetDevice(h->device);
-  const int64_t D = h->D;
+  const int64_t D = h->D, N0 = (int64_t)h->hy.size();
   // Elastic path (EXT ElasticPDMats append!): a valid factor, room in the buffers, a handful of new points.
-  const bool elastic = h->fitted && h->N > 0 && m > 0 && m <= 16 && h->N + m <= h->cap;
-  h->hX.insert(h->hX.end(), Xn, Xn + m * D);
-  h->hy.insert(h->hy.end(), yn, yn + m);
+  const bool elastic = h->fitted && h->N > 0 && m <= 16 && h->N + m <= h->cap;
   if (elastic) {
     bool ok = true;
-    for (int64_t j = 0; j < m && ok; ++j) {
-      const int64_t N = h->N;
-      CU(cudaMemcpyAsync(h->dX + N * D, Xn + j * D, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
-      CU(cudaMemcpyAsync(h->dy + N, yn + j, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      CU(launch_scale_inputs(h, N, N + 1));
-      CU(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
-      CU(launch_append_one(h, h->noise_total));          // advances h->N / h->Np
-      int info = 0;
-      double sc[2];
-      CU(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaMemcpyAsync(sc, h->dscal, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
-      if (info != 0) ok = false;                          // lost positive definiteness: refactor with the jitter rule
-      else h->mll = -0.5 * (sc[1] + sc[0] + (double)h->N * 1.8378770664093453);
+    const int32_t rc = append_elastic(h, Xn, yn, m, &ok);
+    if (rc != B200BO_OK) {
+      // a CUDA error half-way: the host copy was not touched yet; forget the partial device state (h->N is the count every
+      // query reports and sizes caller buffers from) and refactor the old data lazily
+      h->N = N0;
+      h->need_upload = true;
+      h->fitted = false;
+      h->acq_ready = 0;
+      return rc;
     }
-    if (ok) return B200BO_OK;
+    if (ok) {
+      h->hX.insert(h->hX.end(), Xn, Xn + m * D);
+      h->hy.insert(h->hy.end(), yn, yn + m);
+      h->acq_ready = 0;
+      return B200BO_OK;
+    }
   }
+  h->hX.insert(h->hX.end(), Xn, Xn + m * D);
+  h->hy.insert(h->hy.end(), yn, yn + m);
   h->N = (int64_t)h->hy.size();
   int32_t rc = upload_data(h);
   if (rc) return rc;
@@ -342,8 +401,9 @@ B200BO_API int32_t b200bo_maxy(b200bo_handle_t h, double* m) {
 
 B200BO_API int32_t b200bo_get_data(b200bo_handle_t h, double* X, double* y) {
   if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
-  if (X && !h->hX.empty()) memcpy(X, h->hX.data(), sizeof(double) * h->hX.size());
-  if (y && !h->hy.empty()) memcpy(y, h->hy.data(), sizeof(double) * h->hy.size());
+  // exactly the N points b200bo_dims reports (the caller sizes its buffers from that)
+  if (X && h->N > 0) memcpy(X, h->hX.data(), sizeof(double) * h->N * h->D);
+  if (y && h->N > 0) memcpy(y, h->hy.data(), sizeof(double) * h->N);
   return B200BO_OK;
 }
 
@@ -393,7 +453,7 @@ B200BO_API int32_t b200bo_kmat_dev(b200bo_handle_t h, double* dK, int64_t ld) {
   cudaSetDevice(h->device);
   std::vector<double> ie;
   upload_inv_ell(h, ie);
-  CU(cudaMemcpyAsync(h->dinv_ell, ie.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->dinv_ell, ie.data(), sizeof(double) * 2 * h->D, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));   // ie is a host temporary
   CU(launch_scale_inputs(h, 0, h->Np));
   const double noise = exp(2.0 * h->hp.lognoise) + std::numeric_limits<double>::epsilon();

@@ -70,6 +70,8 @@ struct b200bo_handle_s {
   int syrk_ev_used = 0;
   int syrk_engine = -1;      // -1: default (tcgen05 unless B200BO_SYRK_I8=0), 0: DMMA, 1: tcgen05
   bool fitted = false;
+  bool need_upload = false;  // device copies of X / y are stale (a failed elastic append): re-upload before the next refactor
+  int acq_ready = 0;         // bit 0: W = L^-1 sliced for the tcgen05 acquisition path, bit 1: Sigma^-1 sliced (acq_i8.cu)
   double mll = 0.0;
   int jitter = 0;
   int64_t launches = 0;
@@ -120,6 +122,8 @@ cudaError_t launch_ascent(b200bo_handle_s* h, const AcqLaunch& base, double* dX,
 cudaError_t launch_dmma_peak(b200bo_handle_s* h, double* tflops);
 // mll.cu
 cudaError_t launch_kinv(b200bo_handle_s* h);       // kinv.cu: Sigma^-1 into h->dKi by recursive block inversion + W^T W
+cudaError_t launch_linv(b200bo_handle_s* h);       //   first half: W = L^-1 into h->dKi (lower blocks), W^T into h->dWT
+cudaError_t launch_kinv_syrk(b200bo_handle_s* h);  //   second half: Sigma^-1 = W^T W into h->dKi
 cudaError_t launch_kinv_solve(b200bo_handle_s* h); // acq.cu (MODE 1): the same by column solves against I, into h->dV; cross-check only
 cudaError_t launch_dmll(b200bo_handle_s* h, int mask, double* dout /*P*/, const double* Kinv);
 

@@ -95,26 +95,38 @@ __global__ void __launch_bounds__(TG_THREADS, 2) kinv_gemm_kernel(double* __rest
 
 cudaError_t make_map2d(CUtensorMap* m, double* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
-// Sigma^-1 into h->dKi (row-major, leading dimension h->ld, both triangles)
-cudaError_t launch_kinv(b200bo_handle_s* h) {
-  const int nblk = (int)(h->Np / NB);
-  if (nblk == 0) return cudaSuccess;
+static cudaError_t kinv_buffers(b200bo_handle_s* h) {
+  if (h->dKi) return cudaSuccess;
   const uint64_t cap = (uint64_t)h->cap;
-  if (!h->dKi) {
-    cudaError_t e = cudaMalloc(&h->dKi, sizeof(double) * cap * cap);
-    if (e == cudaSuccess) e = cudaMalloc(&h->dWT, sizeof(double) * cap * cap);
-    if (e == cudaSuccess) e = cudaMalloc(&h->dTT, sizeof(double) * cap * cap);
-    if (e == cudaSuccess) e = make_map2d(&h->tmKi64, h->dKi, cap, cap, cap, TG_BN);
-    if (e == cudaSuccess) e = make_map2d(&h->tmWT128, h->dWT, cap, cap, cap, TG_BM);
-    if (e == cudaSuccess) e = make_map2d(&h->tmWT64, h->dWT, cap, cap, cap, TG_BN);
-    if (e == cudaSuccess) e = make_map2d(&h->tmTT128, h->dTT, cap, cap, cap, TG_BM);
-    if (e != cudaSuccess) return e;
+  cudaError_t e = cudaMalloc(&h->dKi, sizeof(double) * cap * cap);
+  if (e == cudaSuccess) e = cudaMalloc(&h->dWT, sizeof(double) * cap * cap);
+  if (e == cudaSuccess) e = cudaMalloc(&h->dTT, sizeof(double) * cap * cap);
+  if (e == cudaSuccess) e = make_map2d(&h->tmKi64, h->dKi, cap, cap, cap, TG_BN);
+  if (e == cudaSuccess) e = make_map2d(&h->tmWT128, h->dWT, cap, cap, cap, TG_BM);
+  if (e == cudaSuccess) e = make_map2d(&h->tmWT64, h->dWT, cap, cap, cap, TG_BN);
+  if (e == cudaSuccess) e = make_map2d(&h->tmTT128, h->dTT, cap, cap, cap, TG_BM);
+  if (e != cudaSuccess) {     // all or nothing: the next call must not find a half-allocated set
+    cudaFree(h->dKi); cudaFree(h->dWT); cudaFree(h->dTT);
+    h->dKi = h->dWT = h->dTT = nullptr;
   }
+  return e;
+}
+
+static KinvMaps kinv_maps(b200bo_handle_s* h) {
   KinvMaps maps;
   maps.L128 = h->tmL; maps.Ki64 = h->tmKi64; maps.WT128 = h->tmWT128; maps.WT64 = h->tmWT64; maps.TT128 = h->tmTT128;
+  return maps;
+}
+
+// W = L^-1 (row-major, lower triangle; blocks above the diagonal blocks are NOT written) into h->dKi and W^T into h->dWT
+cudaError_t launch_linv(b200bo_handle_s* h) {
+  const int nblk = (int)(h->Np / NB);
+  if (nblk == 0) return cudaSuccess;
+  cudaError_t e = kinv_buffers(h);
+  if (e != cudaSuccess) return e;
+  const KinvMaps maps = kinv_maps(h);
   cudaFuncSetAttribute(kinv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
   cudaFuncSetAttribute(kinv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
-  cudaFuncSetAttribute(kinv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
   kinv_seed_kernel<<<dim3(16, nblk), 256, 0, h->stream>>>(h->dLinv, h->dLinvT, h->dKi, h->dWT, h->ld);
   h->launches++;
   for (int s = 1; s < nblk; s *= 2) {
@@ -123,9 +135,25 @@ cudaError_t launch_kinv(b200bo_handle_s* h) {
     kinv_gemm_kernel<1><<<dim3(2 * s, s, npairs), TG_THREADS, TG_SMEM, h->stream>>>(h->dKi, h->dWT, h->dTT, h->ld, s, nblk, maps);
     h->launches += 2;
   }
+  return cudaGetLastError();
+}
+
+// Sigma^-1 = W^T W from h->dWT (launch_linv) into h->dKi (row-major, both triangles; overwrites W)
+cudaError_t launch_kinv_syrk(b200bo_handle_s* h) {
+  const int nblk = (int)(h->Np / NB);
+  if (nblk == 0) return cudaSuccess;
+  const KinvMaps maps = kinv_maps(h);
+  cudaFuncSetAttribute(kinv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
   kinv_gemm_kernel<2><<<nblk * (nblk + 1), TG_THREADS, TG_SMEM, h->stream>>>(h->dKi, h->dWT, h->dTT, h->ld, 0, nblk, maps);
   h->launches++;
   return cudaGetLastError();
+}
+
+// Sigma^-1 into h->dKi (row-major, leading dimension h->ld, both triangles)
+cudaError_t launch_kinv(b200bo_handle_s* h) {
+  cudaError_t e = launch_linv(h);
+  if (e == cudaSuccess) e = launch_kinv_syrk(h);
+  return e;
 }
 
 }  // namespace b200bo

@@ -38,9 +38,10 @@ __global__ void scale_inputs_kernel(const double* __restrict__ X, const double* 
   const int wc = c >> 4, cc = c & 15, gb = 2 * (cc >> 2) + (cc & 1), nt = (cc >> 1) & 1;
   double h = 0.0;
   for (int d = 0; d < D; ++d) {
-    const double z = X[p * D + d] * inv_ell[d];
+    const double x = X[p * D + d];
+    const double z = (x - inv_ell[D + d]) * inv_ell[d];     // K1 only: centred on the mid-range of the data (Gram-form rounding ~ eps |z|^2)
     const int ks = d >> 2, q = d & 3;
-    Z[p * D + d] = z;
+    Z[p * D + d] = x * inv_ell[d];
     Af[(((wr * KS + ks) * 8 + ga) * 4 + q) * 4 + mt] = z;
     Bf[(((wc * KS + ks) * 8 + gb) * 4 + q) * 2 + nt] = z;
     h = fma(z, z, h);
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double* __restrict__
     const double* zb = za + part;
     mbar_wait(&bar[b], (uint32_t)(it >> 1) & 1u);
     double acc[4][2][2];            // [mt][nt][e] = element (row 4 ty + mt, col 4 tx + 2 nt + e)
+    double hsum_hi;                 // largest |z_i|^2/2 + |z_j|^2/2 of the thread's 4 x 4 block: scale of the Gram-form rounding error
     {
       const double2 ha0 = *reinterpret_cast<const double2*>(za + 256 * KS + 4 * ty), ha1 = *reinterpret_cast<const double2*>(za + 256 * KS + 4 * ty + 2);
       const double2 hb0 = *reinterpret_cast<const double2*>(zb + 256 * KS + 4 * tx), hb1 = *reinterpret_cast<const double2*>(zb + 256 * KS + 4 * tx + 2);
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double* __restrict__
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[mt][c >> 1][c & 1] = -(a4[mt] + b4[c]);
+      hsum_hi = fmax(fmax(a4[0], a4[1]), fmax(a4[2], a4[3])) + fmax(fmax(b4[0], b4[1]), fmax(b4[2], b4[3]));
     }
     {
       const double* Ap = za + ((wr * KS * 8 + g) * 4 + q) * 4;
@@ -156,6 +159,34 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double* __restrict__
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+      }
+    }
+    {
+      // (near-)coincident points: z_i.z_j - |z_i|^2/2 - |z_j|^2/2 has cancelled >= 24 bits and its residual is rounding noise of either
+      // sign (exact duplicates are appended by `repetitions` and re-proposed by the search).  Recompute those few elements from the
+      // coordinate differences, as K6 and the elastic append do: r = 0 exactly for duplicates, full precision next to them.
+      double amax = acc[0][0][0];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) amax = fmax(amax, acc[mt][c >> 1][c & 1]);
+      if (__any_sync(0xffffffffu, amax > -0x1p-24 * hsum_hi)) {
+        const double* Ar = za + ((wr * KS * 8 + g) * 4) * 4;
+        const double* Bc = zb + (wc * KS * 8 * 4) * 2;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (!(acc[mt][c >> 1][c & 1] > -0x1p-24 * (za[256 * KS + 4 * ty + mt] + zb[256 * KS + 4 * tx + c]))) continue;
+            const int gb = 2 * q + (c & 1), nt = c >> 1;
+            double r2 = 0.0;
+            for (int d = 0; d < 4 * KS; ++d) {
+              const int ks = d >> 2, qq = d & 3;
+              const double df = Ar[(ks * 32 + qq) * 4 + mt] - Bc[((ks * 8 + gb) * 4 + qq) * 2 + nt];
+              r2 = fma(df, df, r2);
+            }
+            acc[mt][c >> 1][c & 1] = -0.5 * r2;
+          }
       }
     }
     __syncwarp();

@@ -64,7 +64,12 @@ class ScaledLHSIterator:                     # utils.jl:96-98 (a ColumnIterator 
         return (self.data[:, j] for j in range(self.data.shape[1]))
 
 
-class ScaledSobolIterator:                   # utils.jl:64-87: N Sobol points after skipping the first N
+class ScaledSobolIterator:                   # utils.jl:64-87
+    """N points of the (unscrambled, Joe-Kuo) Sobol sequence scaled to the box.  As in the reference, the constructor skips the
+    start of the sequence with Sobol.jl's `skip(seq, N)` (utils.jl:80), which -- `exact=false` -- advances by the largest power of two
+    2^floor(log2(N+1)) <= N+1, not by N; Sobol.jl never emits the origin, hence the extra 1.  Each pass over the iterator draws the
+    NEXT N points of the shared sequence (utils.jl:84-87 calls `next!` on `it.seq`), it does not replay the first pass."""
+
     def __init__(self, lowerbounds, upperbounds, N: int):
         from scipy.stats import qmc
         self.lowerbounds = np.asarray(lowerbounds, float)
@@ -73,17 +78,15 @@ class ScaledSobolIterator:                   # utils.jl:64-87: N Sobol points af
         self._seq = qmc.Sobol(self.lowerbounds.size, scramble=False)
         self._seq.fast_forward(1)                       # Sobol.jl never emits the origin
         if N > 0:
-            self._seq.fast_forward(N)
-        self._pts = None
+            self._seq.fast_forward(1 << int(np.floor(np.log2(N + 1))))
 
     def __len__(self):
         return self.N
 
     def __iter__(self):
-        if self._pts is None:
-            import warnings
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                u = self._seq.random(self.N) if self.N > 0 else np.zeros((0, self.lowerbounds.size))
-            self._pts = self.lowerbounds + u * (self.upperbounds - self.lowerbounds)
-        return (self._pts[j].copy() for j in range(self.N))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            u = self._seq.random(self.N) if self.N > 0 else np.zeros((0, self.lowerbounds.size))
+        pts = self.lowerbounds + u * (self.upperbounds - self.lowerbounds)
+        return (pts[j].copy() for j in range(self.N))

@@ -363,6 +363,86 @@ def test_full_size_properties_config5_shard(bo):
     assert r["best_index"] - off == orc.first_strict_argmax_np(r["values"])
     halves = [g.acquire("TS", (), Xs[:, lo:hi], seed=50, idx_offset=off + lo) for lo, hi in ((0, 1000), (1000, M))]
     assert np.array_equal(np.concatenate([h_["values"] for h_ in halves]), r["values"])
+    # the oracle at the full model size on a subsample of the shard (dpotrf at N = 8192 takes a few seconds on the host)
+    o = orc.GPOracle(D, "SEArd", "MeanConst", ll=ll, lsigma=0.0, lognoise=-2.0, beta=0.0).fit(X, y)
+    assert relmax(g.alpha, o.alpha) < 1e-8 and abs(g.mll - o.mll) < 1e-10 * abs(o.mll)
+    sub = np.sort(np.random.default_rng(52).choice(M, 64, replace=False)); sub[0] = r["best_index"] - off
+    mo, vo = o.predict(Xs[:, sub])
+    assert close(r["mu"][sub], mo, RTOL_POST) and close(r["var"][sub], vo, RTOL_POST)
+    assert close(r["values"][sub], orc.acq_value("TS", (), mo, vo, eps=eps[sub]), RTOL_ACQ)
+
+
+def test_full_size_config4_map_sweep(bo):
+    """BASELINE configs[3] at full size: N=4096, D=8, the 8 x 8 grid of (logNoise, common SEArd length-scale) settings through ONE
+    b200bo_mll_sweep call with gradients; the diagonal of the grid (8 settings, every logNoise and every length-scale once) against
+    the oracle's mll / dmll (closure of optimizemodel!, reference src/models/gp.jl:59-64)."""
+    rng = np.random.default_rng(4)
+    D, N = 8, 4096
+    X = rng.random((D, N)); y = _bumps(X, rng)
+    g = bo.B200GPE(D, mean=bo.MeanConst(0.0), kernel=bo.SEArd(np.zeros(D), 0.0), logNoise=-2.0, capacity=N)
+    g.fit(X, y)
+    th0 = g.get_params()
+    grid = [(ln, l) for ln in np.linspace(-3.0, 0.0, 8) for l in np.linspace(-1.5, 0.5, 8)]
+    Theta = np.stack([np.concatenate([[ln, 0.0], np.full(D, l), [0.0]]) for ln, l in grid], axis=1)     # [logNoise, beta, ll.., lsigma]
+    mll, dmll = g.mll_sweep(Theta)
+    assert mll.shape == (64,) and dmll.shape == (D + 3, 64) and np.all(np.isfinite(mll)) and np.all(np.isfinite(dmll))
+    o = orc.GPOracle(D, "SEArd", "MeanConst", ll=np.zeros(D), lsigma=0.0, lognoise=-2.0, beta=0.0).fit(X, y)
+    for k in range(0, 64, 9):
+        mo, go = o.mll_dmll(Theta[:, k])
+        assert abs(mll[k] - mo) <= 1e-9 * abs(mo), k
+        assert relmax(dmll[:, k], go) < 1e-7, k
+    assert np.array_equal(g.get_params(), th0)                                     # the sweep leaves the model where it was
+    # a sweep of a subset returns the same numbers as the same settings inside the full sweep
+    m2, d2 = g.mll_sweep(Theta[:, [9, 54]])
+    assert np.array_equal(m2, mll[[9, 54]]) and np.array_equal(d2, dmll[:, [9, 54]])
+
+
+@pytest.mark.parametrize("kern", ["SEArd", "Mat52Ard", "Mat12Ard"])
+def test_kmat_uncentred_inputs_small_lengthscale(bo, kern):
+    """K1 takes its distances in Gram form (z_i.z_j - |z_i|^2/2 - |z_j|^2/2), whose rounding error grows with |z|^2.  Branin's box
+    [-5,10] x [0,15] (reference test/branin.jl:1-5) with l = e^-2 puts |z|^2 at ~1.7e4 uncentred: check K element by element (relative, wherever the
+    entry is not negligible) and the posterior against the difference-form oracle."""
+    rng = np.random.default_rng(17)
+    D, N, M = 2, 900, 400
+    lb, ub = np.array([-5.0, 0.0]), np.array([10.0, 15.0])
+    X = lb[:, None] + (ub - lb)[:, None] * rng.random((D, N))
+    y = -orc.branin(X[0], X[1]) / 50.0
+    ll = np.full(D, -2.0)
+    g = bo.B200GPE(D, mean=bo.MeanConst(-1.0), kernel=bo.gp._Kernel(kern, ll, 0.0), logNoise=-2.0, capacity=N)
+    g.fit(X, y)
+    o = orc.GPOracle(D, kern, "MeanConst", ll=ll, lsigma=0.0, lognoise=-2.0, beta=-1.0).fit(X, y)
+    K = g.kmat()
+    S = o.cov(o.X, o.X); S[np.diag_indices(N)] += np.exp(-4.0) + orc.EPS
+    big = S > 1e-8
+    assert float(np.max(np.abs(K - S)[big] / S[big])) < 1e-11 and float(np.max(np.abs(K - S)[~big])) < 1e-18
+    assert relmax(g.alpha, o.alpha) < 1e-9
+    Xs = lb[:, None] + (ub - lb)[:, None] * rng.random((D, M))
+    mu, var = g.predict(Xs)
+    mo, vo = o.predict(Xs)
+    assert close(mu, mo, 1e-9, 1e-12) and close(var, vo, 1e-9, 1e-12)
+
+
+def test_duplicate_points_mat12(bo):
+    """`repetitions > 1` appends hcat(fill(x, rep)) (reference src/BayesianOptimization.jl:194-196) and the search re-proposes points:
+    exact duplicates must give r = 0 exactly in K1 (Mat12: k = exp(-sqrt(r2)) turns a rounding residual of 1e-16 |z|^2 into 1e-8),
+    consistently between a full refit, the elastic append and the oracle."""
+    rng = np.random.default_rng(23)
+    D, N0 = 3, 300
+    X0 = 4.0 + 3.0 * rng.random((D, N0)); y0 = np.sin(X0.sum(0))
+    dup = np.repeat(X0[:, 5:9], 2, axis=1)                                   # every point twice, and each already in the model
+    X = np.hstack([X0, dup]); y = np.concatenate([y0, np.sin(dup.sum(0)) + 0.01 * rng.standard_normal(dup.shape[1])])
+    ll = np.full(D, 0.3)
+    mk = lambda: bo.B200GPE(D, mean=bo.MeanZero(), kernel=bo.gp._Kernel("Mat12Ard", ll, 0.0), logNoise=-2.0, capacity=N0 + 128)
+    ref = mk(); ref.fit(X, y)
+    o = orc.GPOracle(D, "Mat12Ard", "MeanZero", ll=ll, lsigma=0.0, lognoise=-2.0).fit(X, y)
+    K = ref.kmat()
+    S = o.cov(o.X, o.X); S[np.diag_indices(X.shape[1])] += np.exp(-4.0) + orc.EPS
+    assert float(np.max(np.abs(K - S) / S)) < 1e-12
+    assert K[5, N0] == 1.0 and K[5, N0 + 1] == 1.0 and K[N0, N0 + 1] == 1.0   # sf2 * exp(-0) exactly
+    g = mk(); g.fit(X0, y0)
+    bo.update(g, X[:, N0:], y[N0:])                                          # elastic append of the duplicates
+    assert relmax(g.factor, ref.factor) < 1e-11 and relmax(g.factor, o.U) < 1e-11
+    assert relmax(g.alpha, o.alpha) < 1e-9 and abs(g.mll - o.mll) < 1e-10 * abs(o.mll)
 
 
 def test_linearity_in_y_large(bo):

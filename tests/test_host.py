@@ -128,6 +128,13 @@ def test_lhs_and_sobol_iterators():
     assert len(sob) == 10 and pts.shape == (10, 2)
     assert np.all(pts >= [-5.0, 0.0]) and np.all(pts <= [10.0, 15.0]) and len({tuple(p) for p in pts}) == 10
     assert len(b200bo.ScaledSobolIterator([0.0], [1.0], 0)) == 0
+    # Sobol.jl's published 2-D sequence (its README): .5 .5 | .75 .25 | .25 .75 | .375 .375 | .875 .875 | .625 .125 | .125 .625 | ...
+    # skip(seq, 3) is NOT exact: it advances by 2^floor(log2(3+1)) = 4 points, so the iterator starts at the 5th (src/utils.jl:80)
+    s3 = b200bo.ScaledSobolIterator([0.0, 0.0], [1.0, 1.0], 3)
+    assert np.array_equal(np.array(list(s3)), [[0.875, 0.875], [0.625, 0.125], [0.125, 0.625]])
+    assert np.array_equal(np.array(list(s3))[0], [0.1875, 0.3125])       # a second pass continues the sequence (next! on it.seq)
+    s10 = b200bo.ScaledSobolIterator([0.0, 0.0], [1.0, 1.0], 10)         # N = 10 = 5 D: skips 8, not 10
+    assert np.array_equal(next(iter(s10)), [0.6875, 0.8125])
     with pytest.raises(ValueError):
         b200bo.latin_hypercube_sampling([0.0, 1.0], [1.0], 4)
 
