@@ -1,0 +1,662 @@
+// acq_i8.cu -- K6 on the 5th-generation tensor cores: the batched acquisition step as an error-free int8-slice GEMM (tcgen05.mma
+// kind::i8, TMEM accumulators) against the explicit inverse factor.
+//
+// Replaces, per BO iteration, the reference's multi-restart search: acquire_max (src/acquisition.jl:54-68) -> NLopt -> wrap_gradient
+// (:11-17) -> acquisitionfunction(a, model)(x) (src/acquisitionfunctions.jl:4-9) -> mean_var = EXT GP.predict_f (src/models/gp.jl:2-5,8)
+// -> functor a(mu, s2) (acquisitionfunctions.jl:24-27,47-50,96,108,111,141).
+//
+// tcgen05 has no FP64 kind, and a triangular SOLVE per candidate tile chains one block row behind the other.  Both go away with
+//     v = U^-T k*  =  W k*,   W = L^-1  (lower triangular, built once per factor by recursive block inversion, kinv.cu)
+// which is ONE dependency-free GEMM  V[M x N] = K*[M x N] W^T  over all candidates.  FP64 accuracy on an int8 tensor pipe: every
+// operand row is split once into 7 balanced radix-256 digits with a power-of-two scale (W: per row, at fit time; k*: fixed scale
+// 2^ceil(log2 sf2), inside the kernel-evaluation pass), and the product is the 28 EXACT slice products p + q <= 6 accumulated in
+// int32 by anti-diagonal (Ozaki scheme; truncation 2^-51 max|W_i| sf2 per term).  sigma^2 = sf2 - |v|^2 is then a sum of squares, with no
+// cancellation inside; measured against a long-double solve: |d sigma^2| <= 3e-14 at N = 2048 (oracle/ozaki.py, tests/test_oracle.py).
+//
+// Per chunk of CH candidates (CH N 7 bytes of k* slices stay L2-resident), three launches on one stream:
+//   kstar_slice_kernel   k(X_j, x*) for a 128 x 64 block: r^2 by coordinate differences, phi, mu partial = alpha_j' k*, digits -> slices
+//   acq_i8_gemm_kernel   persistent CTAs over (128-candidate tile, 64-row tile of W): TMA (SWIZZLE_128B, 3-D maps over the slices)
+//                        -> 448 x nkb UMMAs 128 x 64 x 32 -> 7 TMEM accumulators -> exact int64 recombination -> per-candidate
+//                        partial sums of v^2 (MODE 0) or w = Sigma^-1 k* itself (MODE 1, the gradient's second product)
+//   acq_finish_kernel    mu, sigma^2 in a fixed summation order, functor + partials, outputs, per-block arg-max (first strict maximum)
+// and, with a gradient, acq_i8_gemm_kernel<1> against the slices of Sigma^-1 + acq_grad_kernel (closed form of SURVEY App. A).
+// Every per-candidate quantity is computed in an order that does not depend on the candidate's position or on its neighbours (the
+// integer products are exact), so a batched call equals the per-point call bit for bit (reference test/acquisitionfunctions.jl:10).
+#include <algorithm>
+#include <cstdlib>
+#include "umma.cuh"
+#include "acqfn.cuh"
+#include "handle.h"
+
+namespace b200bo {
+
+constexpr int A8_S = 7;                  // slices per FP64 value
+constexpr int A8_BM = 128;               // candidates per tile  = UMMA M = TMEM lanes
+constexpr int A8_BN = 64;                // rows of W / Sigma^-1 per tile = UMMA N
+constexpr int A8_ASTAGES = 4;
+constexpr uint32_t A8_A_BYTES = A8_BM * 128, A8_B_BYTES = A8_BN * 128;
+constexpr size_t A8_SMEM = 2 * A8_S * A8_B_BYTES + A8_ASTAGES * A8_A_BYTES + 1024;
+constexpr int A8_THREADS = 320;          // producer warp, MMA warp, 8 epilogue warps
+constexpr int64_t A8_CHUNK_BYTES = 48ll << 20;   // k* slices of one chunk (L2 holds 126 MB)
+
+// byte k of 16 digit words -> one 16-byte vector (element u in byte u)
+__device__ __forceinline__ uint4 gather_byte(const unsigned long long (&dg)[16], int k) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = k < 4 ? (uint32_t)dg[4 * i + u] : (uint32_t)(dg[4 * i + u] >> 32);
+    const uint32_t sel = (uint32_t)(k & 3) | ((uint32_t)(4 + (k & 3)) << 4);     // [x.k, y.k, -, -]
+    const uint32_t t0 = __byte_perm(x[0], x[1], sel), t1 = __byte_perm(x[2], x[3], sel);
+    w[i] = __byte_perm(t0, t1, 0x5410);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- FP64 rows -> 7 int8 slices + per-row scale 2^(e-6).  One warp per row; tri != 0: only columns [0, 128 (row / 128 + 1)) exist. ----
+__global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ A, int64_t lda, int nrows, int ncols_full, int tri,
+                                                         uint8_t* __restrict__ Sl, int64_t pitch, int64_t slice_stride,
+                                                         double* __restrict__ Se) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const int ncols = tri ? (((row >> 7) + 1) << 7) : ncols_full;            // a multiple of 128
+  const double* src = A + (int64_t)row * lda;
+  double m = 0.0;
+  for (int c = 2 * lane; c < ncols; c += 64) {
+    const double2 v = *reinterpret_cast<const double2*>(src + c);
+    m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const int e = (m > 0.0 && m < INFINITY) ? ilogb(m) + 1 : 0;             // |x| < 2^e
+  const double sc = ldexp(1.0, 54 - e);                                   // |x sc| <= 2^54, an integer wherever x has the row's top exponent
+  for (int c0 = 16 * lane; c0 < ncols; c0 += 512) {
+    unsigned long long dg[16];
+#pragma unroll
+    for (int u = 0; u < 16; u += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(src + c0 + u);
+      dg[u] = i8_digits(__double2ll_rn(v.x * sc));
+      dg[u + 1] = i8_digits(__double2ll_rn(v.y * sc));
+    }
+#pragma unroll
+    for (int s = 0; s < A8_S; ++s)
+      *reinterpret_cast<uint4*>(Sl + (int64_t)s * slice_stride + (int64_t)row * pitch + c0) = gather_byte(dg, 6 - s);
+  }
+  if (lane == 0) Se[row] = ldexp(1.0, e - 6);
+}
+
+// ---- k* = k(X, x*) for one 128 (observations) x 64 (candidates) block: values -> digits -> slices, and the partial posterior mean ----
+struct KsArgs {
+  const double* Z; const double* alpha; const double* inv_ell; const double* Xs;
+  uint8_t* Bs; double* MuP;
+  int64_t M, c0, CH, Kp;        // candidates in the call, first candidate of the chunk, chunk capacity (rows per slice), bytes per slice row
+  int N, D;
+  double sf2, qscale;           // qscale = 2^54 / S, S = the fixed power-of-two scale of k*
+};
+
+template <int FAM, int DP>
+__global__ void __launch_bounds__(256) kstar_slice_kernel(const KsArgs a) {
+  extern __shared__ __align__(16) uint8_t ks_smem[];
+  double* zx = reinterpret_cast<double*>(ks_smem);            // [128][DP]
+  double* alb = zx + 128 * DP;                                // [128]
+  double* red = alb + 128;                                    // [8][64]
+  uint8_t* stage = reinterpret_cast<uint8_t*>(red + 8 * 64);  // [7][64 candidates][128 B], 16-byte chunks XOR-swizzled by (candidate & 7)
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int jb = blockIdx.x, D = a.D;
+  const int64_t t0 = (int64_t)blockIdx.y * 64;                // first candidate of the block inside the chunk
+  for (int e = tid; e < 128 * DP; e += 256) {
+    const int m = e / DP, d = e - m * DP;
+    zx[e] = d < D ? a.Z[((int64_t)jb * 128 + m) * D + d] : 0.0;
+  }
+  if (tid < 128) alb[tid] = a.alpha[jb * 128 + tid];
+  __syncthreads();
+  const int j0 = 16 * w;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = lane + 32 * pass;
+    int64_t gi = a.c0 + t0 + n;
+    if (gi >= a.M) gi = a.M - 1;                              // ragged tail: replicate a valid column (never written back)
+    double zc[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) zc[d] = d < D ? a.Xs[gi * D + d] * a.inv_ell[d] : 0.0;
+    unsigned long long dg[16];
+    double mu = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const double* zr = zx + (j0 + j) * DP;
+      double r2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < DP; d += 2) {
+        const double2 x = *reinterpret_cast<const double2*>(zr + d);
+        const double u0 = x.x - zc[d], u1 = x.y - zc[d + 1];
+        r2 = fma(u0, u0, r2);
+        r2 = fma(u1, u1, r2);
+      }
+      const bool live = jb * 128 + j0 + j < a.N;
+      const double ks = live ? a.sf2 * kern_phi<FAM>(r2) : 0.0;
+      mu = fma(alb[j0 + j], ks, mu);
+      dg[j] = i8_digits(__double2ll_rn(ks * a.qscale));
+    }
+    red[w * 64 + n] = mu;
+#pragma unroll
+    for (int s = 0; s < A8_S; ++s)
+      *reinterpret_cast<uint4*>(stage + ((s * 64 + n) << 7) + ((w ^ (n & 7)) << 4)) = gather_byte(dg, 6 - s);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    double mu = red[tid];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) mu += red[k * 64 + tid];
+    a.MuP[(int64_t)jb * a.CH + t0 + tid] = mu;
+  }
+  for (int e = tid; e < A8_S * 64 * 8; e += 256) {            // 8 consecutive threads write one 128-byte row segment
+    const int c = e & 7, n = (e >> 3) & 63, s = e >> 9;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + ((s * 64 + n) << 7) + ((c ^ (n & 7)) << 4));
+    *reinterpret_cast<uint4*>(a.Bs + ((int64_t)s * a.CH + t0 + n) * a.Kp + (int64_t)jb * 128 + 16 * c) = v;
+  }
+}
+
+// ---- the GEMM ----
+struct A8Maps { CUtensorMap A, B; };   // A: k* slices [7][CH][Kp] in 128-row boxes, B: W or Sigma^-1 slices [7][cap][cap] in 64-row boxes
+
+// work items sorted by decreasing length (it descending), dealt to the CTAs in snake order so that every CTA gets the same mix
+__device__ __forceinline__ bool a8_item(int r, int G, int b, int total, int nct, int nit, int& it, int& ct) {
+  const int pos = r * G + ((r & 1) ? G - 1 - b : b);
+  if (pos >= total) return false;
+  it = nit - 1 - pos / nct;
+  ct = pos - (pos / nct) * nct;
+  return true;
+}
+
+// MODE 0: out = SsP[2 nit][CH], partial sums over 32 rows of (W k*)^2; k-blocks 0 .. it/2 (W is lower triangular)
+// MODE 1: out = WgT[Np][CH], w = Sigma^-1 k*; all k-blocks
+template <int MODE>
+__global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double* __restrict__ Be, double sBk, int nct, int nit, int nkb_full,
+                                                                     int64_t CH, double* __restrict__ out,
+                                                                     const __grid_constant__ A8Maps maps) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sB = smem_raw;                                     // [2][7 slices][64 rows x 128 B]
+  uint8_t* sA = smem_raw + 2 * A8_S * A8_B_BYTES;             // [4][128 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + A8_ASTAGES * A8_A_BYTES);
+  uint64_t *afull = bars, *aempty = bars + 4, *bfull = bars + 8, *bempty = bars + 10, *tfull = bars + 12, *tempty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int G = gridDim.x, b = blockIdx.x, total = nct * nit;
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 8);                                     // one arrival per epilogue warp
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                          // ===== TMA producer =====
+      tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B);
+      int as = 0; uint32_t aph = 0, bcnt = 0;
+      int it, ct;
+      for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
+        const int arow = ct * A8_BM, brow = it * A8_BN;
+        const int nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
+        for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
+          const int bs = bcnt & 1;
+          mbar_wait_or_trap(&bempty[bs], ((bcnt >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bfull[bs], A8_S * A8_B_BYTES);
+          for (int q = 0; q < A8_S; ++q) tma_load_3d(sB + (bs * A8_S + q) * A8_B_BYTES, &maps.B, &bfull[bs], kb * 128, brow, q);
+          for (int p = 0; p < A8_S; ++p) {
+            mbar_wait_or_trap(&aempty[as], aph ^ 1u);
+            mbar_arrive_expect_tx(&afull[as], A8_A_BYTES);
+            tma_load_3d(sA + as * A8_A_BYTES, &maps.A, &afull[as], kb * 128, arow, p);
+            if (++as == A8_ASTAGES) { as = 0; aph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                          // ===== MMA issuer =====
+      // D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A8_BN >> 3) << 17) | ((uint32_t)(A8_BM >> 4) << 24);
+      int as = 0; uint32_t aph = 0, bcnt = 0;
+      int it, ct;
+      for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
+        const int nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
+        mbar_wait_or_trap(tempty, ((uint32_t)r & 1u) ^ 1u);   // the epilogue has read the previous item's accumulators
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        uint32_t started = 0;                                 // bit d: accumulator d already holds a product of this item
+        for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
+          const int bs = bcnt & 1;
+          mbar_wait_or_trap(&bfull[bs], (bcnt >> 1) & 1u);
+          for (int p = 0; p < A8_S; ++p) {
+            mbar_wait_or_trap(&afull[as], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint64_t da = umma_desc_sw128(smem_u32(sA + as * A8_A_BYTES));
+            for (int q = 0; q + p < A8_S; ++q) {
+              const int d = p + q;
+              const uint64_t db = umma_desc_sw128(smem_u32(sB + (bs * A8_S + q) * A8_B_BYTES));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)                  // 32 bytes of K per MMA: +2 in the 16-byte start-address field
+                umma_i8(tmem + (uint32_t)(d * A8_BN), da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, ((started >> d) & 1u) | (ks > 0));
+              started |= 1u << d;
+            }
+            umma_commit(&aempty[as]);                         // the A stage is free once these MMAs have read it
+            if (++as == A8_ASTAGES) { as = 0; aph ^= 1u; }
+          }
+          umma_commit(&bempty[bs]);
+        }
+        umma_commit(tfull);                                   // every MMA of the item retired: accumulators complete
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps; warp w reads TMEM lanes 32 (w & 3) .. +31 (= candidates of the tile), columns 32 half .. +31 (= rows of W) =====
+    const int g4 = warp & 3, half = (warp - 2) >> 2;
+    const int m = 32 * g4 + lane;
+    int it, ct;
+    for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
+      const int brow = it * A8_BN + 32 * half;
+      mbar_wait_or_trap(tfull, (uint32_t)r & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      // sum_d a_d 2^(-8d) in two exact 64-bit integer groups (|a_d| < 2^31):  (((a0 256 + a1) 256 + a2) 256 + a3) 2^-24 + ((a4 256 + a5) 256 + a6) 2^-48
+      double acc[32];
+#pragma unroll 1
+      for (int grp = 1; grp >= 0; --grp) {                    // the small group first
+        long long H[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) H[c] = 0;
+        const int nd = grp ? A8_S - 4 : 4;
+#pragma unroll 1
+        for (int dd = 0; dd < nd; ++dd) {
+          uint32_t rr[32];
+          tmem_ld32(tmem + ((uint32_t)(32 * g4) << 16) + (uint32_t)((4 * grp + dd) * A8_BN + 32 * half), rr);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) H[c] = (H[c] << 8) + (long long)(int32_t)rr[c];
+        }
+        if (grp == 0) {                                       // TMEM has been read: the next item's MMAs may overwrite it
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+        }
+        const double wgt = grp ? 0x1p-48 : 0x1p-24;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = grp ? (double)H[c] * wgt : fma((double)H[c], wgt, acc[c]);
+      }
+      if (MODE == 0) {
+        double ss = 0.0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const double v = acc[c] * (sBk * __ldg(Be + brow + c));
+          ss = fma(v, v, ss);
+        }
+        out[(int64_t)(2 * it + half) * CH + (int64_t)ct * A8_BM + m] = ss;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) out[(int64_t)(brow + c) * CH + (int64_t)ct * A8_BM + m] = acc[c] * (sBk * __ldg(Be + brow + c));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ---- scores: one thread per candidate of the chunk ----
+struct FinArgs {
+  const double* MuP; const double* SsP;
+  int64_t CH, M, c0, idx_offset;
+  int nblk, nss;                // partials per candidate: nblk of the mean, nss of |v|^2
+  double sf2, beta;
+  int acq; double p0, p1; unsigned long long seed;
+  double *values, *mu, *var, *amu, *as2;
+  b200bo_best_t* cta_best;      // one per block of the launch
+};
+
+__device__ __forceinline__ void best_merge(double& bv, long long& bi, double v, long long i) {
+  if (i >= 0 && (bi < 0 || v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+}
+
+__global__ void __launch_bounds__(128) acq_finish_kernel(const FinArgs f) {
+  __shared__ double sv[4];
+  __shared__ long long si[4];
+  const int tid = threadIdx.x;
+  const int64_t n = (int64_t)blockIdx.x * 128 + tid, gi = f.c0 + n;
+  double musum = 0.0, ss = 0.0;
+  for (int k = 0; k < f.nblk; ++k) musum += f.MuP[(int64_t)k * f.CH + n];
+  for (int k = 0; k < f.nss; ++k) ss += f.SsP[(int64_t)k * f.CH + n];
+  const double mu = f.beta + musum;
+  const double s2 = fmax(f.sf2 - ss, 0.0);
+  double val = mu, amu = 1.0, as2 = 0.0;
+  if (f.acq >= 0) {
+    const double eps = f.acq == B200BO_ACQ_TS ? philox_normal(f.seed, (unsigned long long)(f.idx_offset + gi)) : 0.0;
+    acq_eval(f.acq, f.p0, f.p1, mu, s2, eps, val, amu, as2);
+  }
+  const bool valid = gi < f.M;
+  if (f.amu) { f.amu[n] = amu; f.as2[n] = as2; }
+  if (valid) {
+    if (f.mu) f.mu[gi] = mu;
+    if (f.var) f.var[gi] = s2;
+    if (f.values) f.values[gi] = val;
+  }
+  // first strict maximum in index order: the largest value, then the lowest index; NaN and -Inf never win (acquire_max: `f > maxf`)
+  double bv = -INFINITY; long long bi = -1;
+  if (valid && f.acq >= 0 && val > -INFINITY) { bv = val; bi = f.idx_offset + gi; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    best_merge(bv, bi, ov, oi);
+  }
+  if ((tid & 31) == 0) { sv[tid >> 5] = bv; si[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < 4; ++k) best_merge(bv, bi, sv[k], si[k]);
+    f.cta_best[blockIdx.x].value = bv; f.cta_best[blockIdx.x].index = bi;
+  }
+}
+
+__global__ void __launch_bounds__(256) argmax_blocks_kernel(const b200bo_best_t* __restrict__ in, int n, b200bo_best_t* __restrict__ out) {
+  __shared__ double sv[8];
+  __shared__ long long si[8];
+  double bv = -INFINITY; long long bi = -1;
+  for (int i = threadIdx.x; i < n; i += 256) best_merge(bv, bi, in[i].value, in[i].index);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    best_merge(bv, bi, ov, oi);
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) best_merge(bv, bi, sv[k], si[k]);
+    out->value = bv; out->index = bi;
+  }
+}
+
+// ---- gradient: grad_d = -1/l_d sum_m (a_mu alpha_m - 2 a_s2 w_m) sf2 psi(r2_m) (z*_d - z_md)    ----
+struct GradArgs {
+  const double* Z; const double* alpha; const double* inv_ell; const double* Xs; const double* WgT; const double* amu; const double* as2;
+  double* grad;
+  int64_t M, c0, CH;
+  int N, D, nblk;
+  double sf2;
+};
+
+template <int FAM, int DP>
+__global__ void __launch_bounds__(256, 1) acq_grad_kernel(const GradArgs a) {
+  extern __shared__ __align__(16) uint8_t gr_smem[];
+  double* zx = reinterpret_cast<double*>(gr_smem);            // [128][DP]
+  double* alb = zx + 128 * DP;                                // [128]
+  double* red = alb + 128;                                    // [8][32][DP + 1]
+  const int tid = threadIdx.x, n = tid & 31, mg = tid >> 5, D = a.D;
+  const int64_t cn = (int64_t)blockIdx.x * 32 + n;
+  int64_t gi = a.c0 + cn;
+  if (gi >= a.M) gi = a.M - 1;
+  double zc[DP], gacc[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) { zc[d] = d < D ? a.Xs[gi * D + d] * a.inv_ell[d] : 0.0; gacc[d] = 0.0; }
+  const double amu = a.amu[cn], as2m2 = -2.0 * a.as2[cn];
+  for (int jb = 0; jb < a.nblk; ++jb) {
+    __syncthreads();
+    for (int e = tid; e < 128 * DP; e += 256) {
+      const int m = e / DP, d = e - m * DP;
+      zx[e] = d < D ? a.Z[((int64_t)jb * 128 + m) * D + d] : 0.0;
+    }
+    if (tid < 128) alb[tid] = a.alpha[jb * 128 + tid];
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+      const int m = 16 * mg + j;
+      const double* zr = zx + m * DP;
+      double u[DP];
+      double r2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < DP; d += 2) {
+        const double2 x = *reinterpret_cast<const double2*>(zr + d);
+        u[d] = x.x - zc[d]; u[d + 1] = x.y - zc[d + 1];
+        r2 = fma(u[d], u[d], r2);
+        r2 = fma(u[d + 1], u[d + 1], r2);
+      }
+      double phi, psi;
+      kern_phi_psi<FAM>(r2, phi, psi);
+      const double w = a.WgT[((int64_t)jb * 128 + m) * a.CH + cn];
+      const bool live = jb * 128 + m < a.N;
+      const double c = live ? fma(amu, alb[m], as2m2 * w) * a.sf2 * psi : 0.0;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) gacc[d] = fma(-c, u[d], gacc[d]);       // c (z* - z_m) = -c u
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < DP; ++d) red[(mg * 32 + n) * (DP + 1) + d] = gacc[d];
+  __syncthreads();
+  for (int e = tid; e < 32 * D; e += 256) {
+    const int nn = e / D, d = e - nn * D;
+    const int64_t g2 = a.c0 + (int64_t)blockIdx.x * 32 + nn;
+    if (g2 >= a.M) continue;
+    double s = red[nn * (DP + 1) + d];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[(k * 32 + nn) * (DP + 1) + d];
+    a.grad[g2 * D + d] = -s * a.inv_ell[d];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+cudaError_t make_map3d_u8(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1);
+
+bool acq_i8_default() {
+  static const bool on = !(getenv("B200BO_ACQ_I8") && atoi(getenv("B200BO_ACQ_I8")) == 0);   // B200BO_ACQ_I8=0 selects the DMMA kernel
+  return on;
+}
+
+static int64_t chunk_of(int64_t Np) {
+  int64_t ch = A8_CHUNK_BYTES / (A8_S * Np) / 128 * 128;
+  return std::max<int64_t>(128, std::min<int64_t>(ch, 8192));
+}
+
+// W = L^-1 (and, for the gradient, Sigma^-1) of the current factor as int8 slices.  Once per factor.
+static cudaError_t ensure_slices(b200bo_handle_s* h, bool want_grad) {
+  const int64_t cap = h->cap;
+  const int Np = (int)h->Np;
+  cudaError_t e = cudaSuccess;
+  if (!(h->acq_ready & 1)) {
+    if (!h->dWs) {
+      e = cudaMalloc(&h->dWs, (size_t)A8_S * cap * cap);
+      if (e == cudaSuccess) e = cudaMalloc(&h->dWe, sizeof(double) * cap);
+      if (e == cudaSuccess) e = make_map3d_u8(&h->tmWsB, h->dWs, (uint64_t)cap, (uint64_t)cap, A8_S, 128, A8_BN);
+      if (e != cudaSuccess) { cudaFree(h->dWs); cudaFree(h->dWe); h->dWs = nullptr; h->dWe = nullptr; return e; }
+    }
+    e = launch_linv(h);                                       // W row-major in h->dKi, W^T in h->dWT
+    if (e != cudaSuccess) return e;
+    slice_rows_kernel<<<(Np + 7) / 8, 256, 0, h->stream>>>(h->dKi, h->ld, Np, Np, 1, reinterpret_cast<uint8_t*>(h->dWs), cap, cap * cap, h->dWe);
+    h->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    h->acq_ready = 1;
+  }
+  if (want_grad && !(h->acq_ready & 2)) {
+    if (!h->dKs) {
+      e = cudaMalloc(&h->dKs, (size_t)A8_S * cap * cap);
+      if (e == cudaSuccess) e = cudaMalloc(&h->dKe, sizeof(double) * cap);
+      if (e == cudaSuccess) e = make_map3d_u8(&h->tmKsB, h->dKs, (uint64_t)cap, (uint64_t)cap, A8_S, 128, A8_BN);
+      if (e != cudaSuccess) { cudaFree(h->dKs); cudaFree(h->dKe); h->dKs = nullptr; h->dKe = nullptr; return e; }
+    }
+    e = launch_kinv_syrk(h);                                  // Sigma^-1 = W^T W into h->dKi (W itself is no longer needed: it is sliced)
+    if (e != cudaSuccess) return e;
+    slice_rows_kernel<<<(Np + 7) / 8, 256, 0, h->stream>>>(h->dKi, h->ld, Np, Np, 0, reinterpret_cast<uint8_t*>(h->dKs), cap, cap * cap, h->dKe);
+    h->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    h->acq_ready |= 2;
+  }
+  return cudaSuccess;
+}
+
+// chunk buffers: k* slices, partial sums, (gradient) w and the functor partials; sized for the current Np
+static cudaError_t ensure_chunk_buffers(b200bo_handle_s* h, int64_t CH, bool want_grad, int64_t nblocks) {
+  const int64_t Np = std::max<int64_t>(h->Np, NB);
+  cudaError_t e = cudaSuccess;
+  const size_t need_bs = (size_t)A8_S * CH * Np;
+  if (need_bs > h->bs_bytes) {
+    cudaFree(h->dBs); h->dBs = nullptr; h->bs_bytes = 0; h->bs_np = 0;
+    if ((e = cudaMalloc(&h->dBs, need_bs)) != cudaSuccess) return e;
+    h->bs_bytes = need_bs;
+  }
+  if (h->bs_np != Np || h->bs_ch != CH) {
+    if ((e = make_map3d_u8(&h->tmBsA, h->dBs, (uint64_t)Np, (uint64_t)CH, A8_S, 128, A8_BM)) != cudaSuccess) return e;
+    h->bs_np = Np; h->bs_ch = CH;
+  }
+  const size_t need_p = sizeof(double) * (size_t)CH * (size_t)(Np / NB + Np / 32 + 2);
+  if (need_p > h->part_bytes) {
+    cudaFree(h->dMuP); h->dMuP = nullptr; h->part_bytes = 0;
+    if ((e = cudaMalloc(&h->dMuP, need_p)) != cudaSuccess) return e;
+    h->part_bytes = need_p;
+  }
+  if (want_grad) {
+    const size_t need_w = sizeof(double) * (size_t)CH * (size_t)Np;
+    if (need_w > h->wg_bytes) {
+      cudaFree(h->dWg); h->dWg = nullptr; h->wg_bytes = 0;
+      if ((e = cudaMalloc(&h->dWg, need_w)) != cudaSuccess) return e;
+      h->wg_bytes = need_w;
+    }
+  }
+  if (nblocks > h->nbest2) {
+    cudaFree(h->dcta_best2); h->dcta_best2 = nullptr; h->nbest2 = 0;
+    if ((e = cudaMalloc(&h->dcta_best2, sizeof(b200bo_best_t) * (size_t)nblocks)) != cudaSuccess) return e;
+    h->nbest2 = nblocks;
+  }
+  return cudaSuccess;
+}
+
+template <int FAM>
+static cudaError_t launch_kstar(b200bo_handle_s* h, const KsArgs& a, int nblk, int ntile64) {
+  const int D = h->D;
+  const int DP = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
+  const size_t smem = sizeof(double) * (128 * DP + 128 + 8 * 64) + A8_S * 64 * 128;
+  const dim3 grid(nblk, ntile64);
+#define B200BO_KS(DPV)                                                                                              \
+  do {                                                                                                              \
+    cudaFuncSetAttribute(kstar_slice_kernel<FAM, DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    kstar_slice_kernel<FAM, DPV><<<grid, 256, smem, h->stream>>>(a);                                                \
+  } while (0)
+  if (DP == 4) B200BO_KS(4); else if (DP == 8) B200BO_KS(8); else if (DP == 16) B200BO_KS(16); else B200BO_KS(32);
+#undef B200BO_KS
+  h->launches++;
+  return cudaGetLastError();
+}
+
+template <int FAM>
+static cudaError_t launch_grad(b200bo_handle_s* h, const GradArgs& a, int nblocks) {
+  const int D = h->D;
+  const int DP = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
+  const size_t smem = sizeof(double) * (128 * DP + 128 + 8 * 32 * (DP + 1));
+#define B200BO_GR(DPV)                                                                                              \
+  do {                                                                                                              \
+    cudaFuncSetAttribute(acq_grad_kernel<FAM, DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    acq_grad_kernel<FAM, DPV><<<nblocks, 256, smem, h->stream>>>(a);                                                \
+  } while (0)
+  if (DP == 4) B200BO_GR(4); else if (DP == 8) B200BO_GR(8); else if (DP == 16) B200BO_GR(16); else B200BO_GR(32);
+#undef B200BO_GR
+  h->launches++;
+  return cudaGetLastError();
+}
+
+// The acquisition step over l.M candidate columns on the tcgen05 path.  Same contract as launch_acquire (acq.cu).
+cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
+  const int64_t M = l.M;
+  if (M == 0) return cudaSuccess;
+  const int64_t Np = h->Np;
+  const int nblk = (int)(Np / NB), nit = (int)(Np / A8_BN);
+  const bool want_grad = l.dgrad != nullptr;
+  cudaError_t e = cudaSuccess;
+  if (nblk > 0 && (e = ensure_slices(h, want_grad)) != cudaSuccess) return e;
+  const int64_t CHmax = chunk_of(std::max<int64_t>(Np, NB));
+  const int64_t CH = std::min<int64_t>(CHmax, (M + 127) / 128 * 128);
+  const int64_t nchunks = (M + CH - 1) / CH;
+  const int64_t nblocks_total = nchunks * (CH / 128);
+  if ((e = ensure_chunk_buffers(h, CH, want_grad, nblocks_total)) != cudaSuccess) return e;
+  double* dSsP = h->dMuP + (size_t)CH * (size_t)(std::max<int64_t>(Np, NB) / NB);
+  double* dAmu = dSsP + (size_t)CH * (size_t)(std::max<int64_t>(Np, NB) / 32);
+  double* dAs2 = dAmu + CH;
+  const double sf2 = exp(2.0 * h->hp.lsigma);
+  int e2 = 0;
+  frexp(sf2, &e2);                                            // sf2 = f 2^e2, f in [0.5, 1): S = 2^e2 > sf2
+  const double S = ldexp(1.0, e2);
+  const double qscale = ldexp(1.0, 54 - e2), sBk = ldexp(1.0, e2 - 6);
+  (void)S;
+  A8Maps mapsW, mapsK;
+  mapsW.A = h->tmBsA; mapsW.B = h->tmWsB;
+  mapsK.A = h->tmBsA; mapsK.B = h->tmKsB;
+  cudaFuncSetAttribute(acq_i8_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  cudaFuncSetAttribute(acq_i8_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  int64_t blk0 = 0;
+  for (int64_t c0 = 0; c0 < M; c0 += CH) {
+    const int64_t mc = std::min<int64_t>(CH, M - c0);
+    const int64_t mcp = (mc + 127) / 128 * 128;
+    const int nct = (int)(mcp / A8_BM);
+    if (nblk > 0) {
+      KsArgs k;
+      k.Z = h->dZ; k.alpha = h->dalpha; k.inv_ell = h->dinv_ell; k.Xs = l.dXs; k.Bs = reinterpret_cast<uint8_t*>(h->dBs); k.MuP = h->dMuP;
+      k.M = M; k.c0 = c0; k.CH = CH; k.Kp = Np; k.N = (int)h->N; k.D = h->D; k.sf2 = sf2; k.qscale = qscale;
+      switch (h->fam) {
+        case FAM_SE: e = launch_kstar<FAM_SE>(h, k, nblk, (int)(mcp / 64)); break;
+        case FAM_MAT12: e = launch_kstar<FAM_MAT12>(h, k, nblk, (int)(mcp / 64)); break;
+        case FAM_MAT32: e = launch_kstar<FAM_MAT32>(h, k, nblk, (int)(mcp / 64)); break;
+        default: e = launch_kstar<FAM_MAT52>(h, k, nblk, (int)(mcp / 64)); break;
+      }
+      if (e != cudaSuccess) return e;
+      const int total = nct * nit;
+      const int grid = std::min(total, h->num_sms);
+      acq_i8_gemm_kernel<0><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
+      h->launches++;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    FinArgs f;
+    f.MuP = h->dMuP; f.SsP = dSsP; f.CH = CH; f.M = M; f.c0 = c0; f.idx_offset = l.idx_offset;
+    f.nblk = nblk; f.nss = 2 * nit; f.sf2 = sf2; f.beta = h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0;
+    f.acq = l.acq_kind; f.p0 = l.p0; f.p1 = l.p1; f.seed = l.seed;
+    f.values = l.dvalues; f.mu = l.dmu; f.var = l.dvar; f.amu = want_grad ? dAmu : nullptr; f.as2 = want_grad ? dAs2 : nullptr;
+    f.cta_best = h->dcta_best2 + blk0;
+    acq_finish_kernel<<<(unsigned)(mcp / 128), 128, 0, h->stream>>>(f);
+    h->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    blk0 += mcp / 128;
+    if (want_grad) {
+      if (nblk == 0) {
+        if ((e = cudaMemsetAsync(l.dgrad + c0 * h->D, 0, sizeof(double) * mc * h->D, h->stream)) != cudaSuccess) return e;
+        continue;
+      }
+      const int total = nct * nit;
+      const int grid = std::min(total, h->num_sms);
+      acq_i8_gemm_kernel<1><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dKe, sBk, nct, nit, nblk, CH, h->dWg, mapsK);
+      h->launches++;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      GradArgs g;
+      g.Z = h->dZ; g.alpha = h->dalpha; g.inv_ell = h->dinv_ell; g.Xs = l.dXs; g.WgT = h->dWg; g.amu = dAmu; g.as2 = dAs2; g.grad = l.dgrad;
+      g.M = M; g.c0 = c0; g.CH = CH; g.N = (int)h->N; g.D = h->D; g.nblk = nblk; g.sf2 = sf2;
+      const int nb = (int)((mc + 31) / 32);
+      switch (h->fam) {
+        case FAM_SE: e = launch_grad<FAM_SE>(h, g, nb); break;
+        case FAM_MAT12: e = launch_grad<FAM_MAT12>(h, g, nb); break;
+        case FAM_MAT32: e = launch_grad<FAM_MAT32>(h, g, nb); break;
+        default: e = launch_grad<FAM_MAT52>(h, g, nb); break;
+      }
+      if (e != cudaSuccess) return e;
+    }
+  }
+  if (l.dbest && l.acq_kind >= 0) {
+    argmax_blocks_kernel<<<1, 256, 0, h->stream>>>(h->dcta_best2, (int)blk0, l.dbest);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace b200bo
