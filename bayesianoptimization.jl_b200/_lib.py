@@ -74,6 +74,7 @@ PROTOTYPES = {
     "b200bo_launch_count": [_H, C.POINTER(C.c_int64)],
     "b200bo_fp64_peak_tflops": [_H, _dp],
     "b200bo_set_syrk_engine": [_H, C.c_int32],
+    "b200bo_set_acq_engine": [_H, C.c_int32],
     "b200bo_version": [],
 }
 _RESTYPES = {"b200bo_last_error": C.c_char_p}

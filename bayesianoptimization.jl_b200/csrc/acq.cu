@@ -449,6 +449,9 @@ size_t acq_smem_bytes(int D) {
 }
 
 cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& l) {
+  // engine 1 (default): error-free int8-slice GEMM against W = L^-1 on tcgen05 (acq_i8.cu); its int32 accumulators hold 7 N 2^14 < 2^31
+  const bool i8 = h->acq_engine < 0 ? acq_i8_default() : h->acq_engine == 1;
+  if (i8 && h->Np <= 16384) return launch_acquire_i8(h, l);
   AcqArgs a;
   a.L = h->dL; a.ld = h->ld; a.Linv = h->dLinv; a.LinvT = h->dLinvT;
   a.Z = h->dZ; a.alpha = h->dalpha; a.inv_ell = h->dinv_ell; a.Xs = l.dXs; a.V = h->dV;

@@ -39,6 +39,9 @@ void free_device(b200bo_handle_s* h) {
   cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dZk); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dz); cudaFree(h->dflags); cudaFree(h->dinv_ell);
   cudaFree(h->dL); cudaFree(h->dLinv); cudaFree(h->dLinvT); cudaFree(h->dV); cudaFree(h->dKi); cudaFree(h->dWT); cudaFree(h->dTT); cudaFree(h->dSl); cudaFree(h->dSe); cudaFree(h->dscal); cudaFree(h->dinfo);
   cudaFree(h->dcta_best); cudaFree(h->dbest); cudaFree(h->dpart);
+  cudaFree(h->dWs); cudaFree(h->dKs); cudaFree(h->dBs); cudaFree(h->dWe); cudaFree(h->dKe); cudaFree(h->dMuP); cudaFree(h->dWg); cudaFree(h->dcta_best2);
+  h->dWs = h->dKs = h->dBs = nullptr; h->dWe = h->dKe = h->dMuP = h->dWg = nullptr; h->dcta_best2 = nullptr;
+  h->bs_bytes = h->part_bytes = h->wg_bytes = 0; h->bs_np = h->bs_ch = h->nbest2 = 0; h->acq_ready = 0;
   h->dz = nullptr; h->dflags = nullptr; h->dKi = h->dWT = h->dTT = nullptr; h->dSl = nullptr; h->dSe = nullptr;
   h->dX = h->dZ = h->dZk = h->dy = h->dw = h->dalpha = h->dinv_ell = h->dL = h->dLinv = h->dLinvT = h->dV = h->dscal = h->dpart = nullptr;
   h->dinfo = nullptr; h->dcta_best = nullptr; h->dbest = nullptr;
@@ -737,6 +740,12 @@ B200BO_API int32_t b200bo_fp64_peak_tflops(b200bo_handle_t h, double* tflops) {
 B200BO_API int32_t b200bo_set_syrk_engine(b200bo_handle_t h, int32_t engine) {
   if (!h || engine < 0 || engine > 2) return fail(h, B200BO_ERR_ARG, "engine must be 0 (DMMA), 1 (tcgen05, 128 x 64 tiles) or 2 (tcgen05, 128 x 128 tiles, two passes)");
   h->syrk_engine = engine;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_set_acq_engine(b200bo_handle_t h, int32_t engine) {
+  if (!h || engine < 0 || engine > 1) return fail(h, B200BO_ERR_ARG, "engine must be 0 (DMMA blocked solve) or 1 (tcgen05 int8-slice product)");
+  h->acq_engine = engine;
   return B200BO_OK;
 }
 

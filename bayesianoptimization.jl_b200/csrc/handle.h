@@ -49,6 +49,15 @@ struct b200bo_handle_s {
   double* dSe = nullptr;     // [cap] per-row scale 2^(e-6) of the slices
   int i8_nkb = 4;            // 128-column k-blocks in the current slices (= inner panels per outer panel)
   CUtensorMap tmSlA, tmSlB;
+  // K6 on tcgen05 (acq_i8.cu): int8 slices of W = L^-1 and (gradient) Sigma^-1 of the current factor, [7][cap][cap] + row scales; the
+  // per-chunk k* slices [7][CH][Np], partial sums, w = Sigma^-1 k* and per-block bests
+  void *dWs = nullptr, *dKs = nullptr, *dBs = nullptr;
+  double *dWe = nullptr, *dKe = nullptr, *dMuP = nullptr, *dWg = nullptr;
+  b200bo_best_t* dcta_best2 = nullptr;
+  size_t bs_bytes = 0, part_bytes = 0, wg_bytes = 0;
+  int64_t bs_np = 0, bs_ch = 0, nbest2 = 0;
+  CUtensorMap tmWsB, tmKsB, tmBsA;
+  int acq_engine = -1;       // -1: default (tcgen05 unless B200BO_ACQ_I8=0), 0: DMMA solve (acq.cu), 1: tcgen05 int8-slice GEMM (acq_i8.cu)
   int64_t nslots = 0;
   double* dscal = nullptr;   // small scalar outputs (logdet, r'alpha, ...)
   int* dinfo = nullptr;      // non-PD flag
@@ -112,7 +121,9 @@ struct AcqLaunch {
   double *dvalues = nullptr, *dgrad = nullptr, *dmu = nullptr, *dvar = nullptr;
   b200bo_best_t* dbest = nullptr;
 };
-cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& a);
+cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& a);       // dispatches on h->acq_engine
+cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& a);    // acq_i8.cu
+bool acq_i8_default();
 size_t acq_smem_bytes(int D);
 // search.cu
 cudaError_t launch_lhs(b200bo_handle_s* h, double* dXs, int64_t n_total, int64_t offset, int64_t n_local, unsigned long long seed,

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double* __restrict__
           for (int nt = 0; nt < 2; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
     }
-    {
+    if (FAM != FAM_SE) {   // exp(-r^2/2) passes a residual of 1e-13 through unchanged; the Matern families take its square root
       // (near-)coincident points: z_i.z_j - |z_i|^2/2 - |z_j|^2/2 has cancelled >= 24 bits and its residual is rounding noise of either
       // sign (exact duplicates are appended by `repetitions` and re-proposed by the search).  Recompute those few elements from the
       // coordinate differences, as K6 and the elastic append do: r = 0 exactly for duplicates, full precision next to them.

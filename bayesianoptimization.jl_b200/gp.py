@@ -174,6 +174,10 @@ class B200GPE:
         """1 = tcgen05 int8-slice trailing updates (default), 0 = DMMA tile GEMM; takes effect at the next fit."""
         check(lib.b200bo_set_syrk_engine(self._h, int(engine)), self._h)
 
+    def set_acq_engine(self, engine: int) -> None:
+        """1 = acquisition step as an int8-slice GEMM against L^-1 on tcgen05 (default), 0 = blocked DMMA solves (A/B tests)."""
+        check(lib.b200bo_set_acq_engine(self._h, int(engine)), self._h)
+
     @property
     def launch_count(self) -> int:
         n = C.c_int64()

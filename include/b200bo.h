@@ -157,6 +157,9 @@ B200BO_API int32_t b200bo_fp64_peak_tflops(b200bo_handle_t h, double* tflops);  
    2 = the same on 128 x 128 tiles in two passes (experimental, no faster), 0 = DMMA tile GEMM.
    Both are FP64-accurate; the switch exists so that tests and benches can compare them in one process. */
 B200BO_API int32_t b200bo_set_syrk_engine(b200bo_handle_t h, int32_t engine);
+/* engine of the acquisition step (K6): 1 = error-free int8-slice product against the explicit inverse factor on tcgen05 (default),
+   0 = blocked triangular solves on the FP64 tensor pipe (DMMA).  Both are FP64-accurate; the switch exists for in-process A/B tests. */
+B200BO_API int32_t b200bo_set_acq_engine(b200bo_handle_t h, int32_t engine);
 B200BO_API int32_t b200bo_version(void);
 
 #ifdef __cplusplus

@@ -157,6 +157,29 @@ def test_trailing_update_engines_agree(bo, N, D):
     assert relmax(res[1][0], res[0][0]) < 1e-12 and relmax(res[2][0], res[0][0]) < 1e-12
 
 
+@pytest.mark.parametrize("kern,D,N,M", [("Mat52Ard", 6, 2048, 3000), ("SEArd", 32, 1500, 700), ("Mat12Iso", 3, 130, 129), ("SEArd", 2, 700, 4500)])
+def test_acquisition_engines_agree(bo, kern, D, N, M):
+    """K6 on tcgen05 (int8-slice GEMM against W = L^-1, the default) and on the FP64 tensor pipe (blocked DMMA solves) against the
+    oracle and against each other; candidates include training points, where sigma^2 = k** - v'v cancels most."""
+    rng, o, g, X, y = make_pair(bo, kern, "MeanConst", D, N, seed=31 * N + D)
+    Xs = rng.random((D, M)); Xs[:, :40] = X[:, :40]; Xs[:, 40:60] = X[:, 40:60] + 1e-8
+    mo, vo = o.predict(Xs)
+    tau = float(np.quantile(y, 0.9))
+    a, gr = orc.acq_grad(o, "EI", (tau,), Xs)
+    out = {}
+    for eng in (1, 0):
+        g.set_acq_engine(eng)
+        r = g.acquire("EI", (tau,), Xs, want_grad=True, want_mu_var=True)
+        assert close(r["mu"], mo, RTOL_POST) and close(r["var"], vo, RTOL_POST, 1e-13) and close(r["values"], a, RTOL_ACQ), eng
+        assert r["best_index"] == orc.first_strict_argmax_np(a), eng
+        assert relmax(r["grad"], gr) < 1e-8, eng
+        r2 = g.acquire("EI", (tau,), Xs)                                    # value-only launch: same bits, same selection
+        assert np.array_equal(r2["values"], r["values"]) and r2["best_index"] == r["best_index"], eng
+        out[eng] = r
+    assert np.max(np.abs(out[1]["var"] - out[0]["var"])) < 1e-12 * o.sf2 and relmax(out[1]["mu"], out[0]["mu"]) < 1e-12
+    assert relmax(out[1]["grad"], out[0]["grad"]) < 1e-9
+
+
 @pytest.mark.parametrize("N", [1920, 2560, 4096])
 def test_factor_many_panels(bo, N):
     """blocked Cholesky with many 128-panels (persistent trailing update walks several tiles per CTA, look-ahead streams)."""

@@ -306,3 +306,36 @@ def test_sliced_forward_solve_keeps_posterior_accuracy():
     vref = np.maximum(sf ** 2 - np.sum(Vref * Vref, axis=0), 0.0)
     assert np.abs(V - Vref).max() <= 1e-13 * sf
     assert np.all(np.abs(var - vo) <= 1e-9 * np.abs(vo) + 1e-13) and np.all(np.abs(vref - vo) <= 1e-9 * np.abs(vo) + 1e-13)
+
+
+def test_integer_digit_rule_of_the_tcgen05_acquisition_path():
+    """csrc/umma.cuh i8_digits + csrc/acq_i8.cu gather_byte restated: digits fit int8 (top digit in [-64, 64]) and rebuild the 55-bit integer."""
+    from oracle import ozaki
+    rng = np.random.default_rng(5)
+    q = np.concatenate([rng.integers(-2 ** 54, 2 ** 54, 4000), [0, 1, -1, 2 ** 54, -2 ** 54, 127, 128, -128, -129, 2 ** 47, 2 ** 48 - 1, -(2 ** 48)]])
+    d = ozaki.int_digits(q)
+    assert np.all(d[1:] >= -128) and np.all(d[1:] <= 127) and np.all(np.abs(d[0]) <= 64)
+    back = sum(int(1) * d[s].astype(object) * (1 << (8 * (6 - s))) for s in range(7))
+    assert np.all(back == q.astype(object))
+    A = rng.standard_normal((16, 256)) * np.exp(rng.normal(0, 3, (16, 1)))
+    D, sc = ozaki.slice_rows_int(A)
+    rec = sum(D[s] * 2.0 ** (-8 * s) for s in range(6, -1, -1)) * sc[:, None]
+    assert np.all(np.abs(rec - A) <= 2.0 ** -54 * np.abs(A).max(axis=1, keepdims=True))
+
+
+def test_explicit_inverse_sliced_product_keeps_posterior_accuracy():
+    """The arithmetic of K6 on tcgen05 (csrc/acq_i8.cu) on the CPU: sigma^2 from the explicit inverse factor through 7 x 7 int8 slices
+    (28 exact products, anti-diagonal int32 accumulators) against the LAPACK triangular solve of the restated predict_f -- on random
+    candidates, next to training points and ON training points (where k** - v'v cancels most)."""
+    import scipy.linalg as sl
+    from oracle import ozaki
+    rng = np.random.default_rng(12)
+    for kern, D, N, lognoise in (("Mat52Ard", 6, 512, -2.0), ("SEArd", 3, 384, -3.0), ("Mat12Ard", 2, 256, -2.0)):
+        X = rng.random((D, N)); y = np.sin(3 * X.sum(0))
+        o = orc.GPOracle(D, kern, "MeanZero", ll=np.full(D, -0.7), lsigma=0.3, lognoise=lognoise).fit(X, y)
+        Xs = rng.random((D, 96)); Xs[:, :24] = X[:, :24]; Xs[:, 24:48] = X[:, 24:48] + 1e-7
+        Ks = o.cov(Xs, o.X)                                                      # [cands][N]
+        mo, vo = o.predict(Xs)
+        got = ozaki.posterior_var_i8(o.U.T.copy(), Ks, o.sf2)
+        assert np.all(np.abs(got - vo) <= 1e-9 * np.abs(vo) + 1e-13), kern
+        assert np.max(np.abs(got - vo)) < 2e-13 * o.sf2, kern
