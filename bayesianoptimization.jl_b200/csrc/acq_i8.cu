@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include "umma.cuh"
+#include "umma_issue.cuh"
 #include "acqfn.cuh"
 #include "handle.h"
 
@@ -33,9 +34,8 @@ namespace b200bo {
 constexpr int A8_S = 7;                  // slices per FP64 value
 constexpr int A8_BM = 128;               // candidates per tile  = UMMA M = TMEM lanes
 constexpr int A8_BN = 64;                // rows of W / Sigma^-1 per tile = UMMA N
-constexpr int A8_ASTAGES = 4;
 constexpr uint32_t A8_A_BYTES = A8_BM * 128, A8_B_BYTES = A8_BN * 128;
-constexpr size_t A8_SMEM = 2 * A8_S * A8_B_BYTES + A8_ASTAGES * A8_A_BYTES + 1024;
+constexpr size_t A8_SMEM = 2 * A8_S * A8_B_BYTES + A8_S * A8_A_BYTES + 1024;      // 224 KB of operand stages + barriers
 constexpr int A8_THREADS = 320;          // producer warp, MMA warp, 8 epilogue warps
 constexpr int64_t A8_CHUNK_BYTES = 48ll << 20;   // k* slices of one chunk (L2 holds 126 MB)
 
@@ -176,17 +176,17 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
                                                                      int64_t CH, double* __restrict__ out,
                                                                      const __grid_constant__ A8Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* sB = smem_raw;                                     // [2][7 slices][64 rows x 128 B]
-  uint8_t* sA = smem_raw + 2 * A8_S * A8_B_BYTES;             // [4][128 rows x 128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + A8_ASTAGES * A8_A_BYTES);
-  uint64_t *afull = bars, *aempty = bars + 4, *bfull = bars + 8, *bempty = bars + 10, *tfull = bars + 12, *tempty = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint8_t* sB = smem_raw;                                     // [2][7 slices][64 rows x 128 B]: W / Sigma^-1, double buffered per k-block
+  uint8_t* sA = smem_raw + 2 * A8_S * A8_B_BYTES;             // [7 slices][128 rows x 128 B]: k*, stage p = slice p of the current k-block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + A8_S * A8_A_BYTES);
+  uint64_t *afull = bars, *aempty = bars + 7, *bfull = bars + 14, *bempty = bars + 16, *tfull = bars + 18, *tempty = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int G = gridDim.x, b = blockIdx.x, total = nct * nit;
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < A8_S; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 8);                                     // one arrival per epilogue warp
@@ -204,21 +204,20 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
   if (warp == 0) {
     if (lane == 0) {                                          // ===== TMA producer =====
       tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B);
-      int as = 0; uint32_t aph = 0, bcnt = 0;
+      uint32_t kcnt = 0;                                      // k-blocks so far: B buffer kcnt & 1, phase of every A stage kcnt & 1
       int it, ct;
       for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
         const int arow = ct * A8_BM, brow = it * A8_BN;
         const int nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
-        for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
-          const int bs = bcnt & 1;
-          mbar_wait_or_trap(&bempty[bs], ((bcnt >> 1) & 1u) ^ 1u);
+        for (int kb = 0; kb < nkb; ++kb, ++kcnt) {
+          const int bs = kcnt & 1;
+          mbar_wait_or_trap(&bempty[bs], ((kcnt >> 1) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&bfull[bs], A8_S * A8_B_BYTES);
           for (int q = 0; q < A8_S; ++q) tma_load_3d(sB + (bs * A8_S + q) * A8_B_BYTES, &maps.B, &bfull[bs], kb * 128, brow, q);
           for (int p = 0; p < A8_S; ++p) {
-            mbar_wait_or_trap(&aempty[as], aph ^ 1u);
-            mbar_arrive_expect_tx(&afull[as], A8_A_BYTES);
-            tma_load_3d(sA + as * A8_A_BYTES, &maps.A, &afull[as], kb * 128, arow, p);
-            if (++as == A8_ASTAGES) { as = 0; aph ^= 1u; }
+            mbar_wait_or_trap(&aempty[p], (kcnt & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&afull[p], A8_A_BYTES);
+            tma_load_3d(sA + p * A8_A_BYTES, &maps.A, &afull[p], kb * 128, arow, p);
           }
         }
       }
@@ -227,31 +226,25 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
     if (lane == 0) {                                          // ===== MMA issuer =====
       // D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A8_BN >> 3) << 17) | ((uint32_t)(A8_BM >> 4) << 24);
-      int as = 0; uint32_t aph = 0, bcnt = 0;
+      const uint64_t dA0 = umma_desc_sw128(smem_u32(sA)), dB0 = umma_desc_sw128(smem_u32(sB));
+      uint32_t kcnt = 0;
       int it, ct;
       for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
         const int nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
         mbar_wait_or_trap(tempty, ((uint32_t)r & 1u) ^ 1u);   // the epilogue has read the previous item's accumulators
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        uint32_t started = 0;                                 // bit d: accumulator d already holds a product of this item
-        for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
-          const int bs = bcnt & 1;
-          mbar_wait_or_trap(&bfull[bs], (bcnt >> 1) & 1u);
-          for (int p = 0; p < A8_S; ++p) {
-            mbar_wait_or_trap(&afull[as], aph);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint64_t da = umma_desc_sw128(smem_u32(sA + as * A8_A_BYTES));
-            for (int q = 0; q + p < A8_S; ++q) {
-              const int d = p + q;
-              const uint64_t db = umma_desc_sw128(smem_u32(sB + (bs * A8_S + q) * A8_B_BYTES));
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)                  // 32 bytes of K per MMA: +2 in the 16-byte start-address field
-                umma_i8(tmem + (uint32_t)(d * A8_BN), da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, ((started >> d) & 1u) | (ks > 0));
-              started |= 1u << d;
-            }
-            umma_commit(&aempty[as]);                         // the A stage is free once these MMAs have read it
-            if (++as == A8_ASTAGES) { as = 0; aph ^= 1u; }
-          }
+        for (int kb = 0; kb < nkb; ++kb, ++kcnt) {
+          const uint32_t bs = kcnt & 1u, aph = kcnt & 1u, acc = kb > 0;
+          const uint64_t db = dB0 + (uint64_t)(bs * ((A8_S * A8_B_BYTES) >> 4));
+          mbar_wait_or_trap(&bfull[bs], (kcnt >> 1) & 1u);
+          // slice p of k*: one asm block issues its 4 (7 - p) MMAs (umma_issue.cuh); tcgen05.commit frees the stage behind them
+#define A8_ISSUE(P)                                                                                               \
+          mbar_wait_or_trap(&afull[P], aph);                                                                      \
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");                                       \
+          umma_i8_issue<P, A8_BN, (A8_B_BYTES >> 4), 1>(tmem, dA0 + (uint64_t)((P) * (A8_A_BYTES >> 4)), db, idesc, (P) ? 1u : acc); \
+          umma_commit(&aempty[P]);
+          A8_ISSUE(0) A8_ISSUE(1) A8_ISSUE(2) A8_ISSUE(3) A8_ISSUE(4) A8_ISSUE(5) A8_ISSUE(6)
+#undef A8_ISSUE
           umma_commit(&bempty[bs]);
         }
         umma_commit(tfull);                                   // every MMA of the item retired: accumulators complete

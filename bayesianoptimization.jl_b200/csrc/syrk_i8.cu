@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "umma.cuh"
+#include "umma_issue.cuh"
 #include "handle.h"
 
 namespace b200bo {
@@ -141,7 +142,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         mbar_wait_or_trap(tempty, (it & 1u) ^ 1u);            // the epilogue has read the previous tile's accumulators
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        uint32_t started = 0;                                 // bit d: accumulator d already holds a product of this tile
         for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
           const int bs = bcnt & 1;
           mbar_wait_or_trap(&bfull[bs], (bcnt >> 1) & 1u);
@@ -149,13 +149,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
             mbar_wait_or_trap(&afull[as], aph);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint64_t da = umma_desc_sw128(smem_u32(sA + as * I8_A_BYTES));
-            for (int q = 0; q + p < I8_S; ++q) {
-              const int d = p + q;
-              const uint64_t db = umma_desc_sw128(smem_u32(sB + (bs * I8_S + q) * I8_B_BYTES));
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)                  // 32 bytes of K per MMA: +2 in the 16-byte start-address field
-                umma_i8(tmem + (uint32_t)(d * I8_BN), da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, ((started >> d) & 1u) | (ks > 0));
-              started |= 1u << d;
+            const uint64_t db = umma_desc_sw128(smem_u32(sB + bs * I8_S * I8_B_BYTES));
+            const uint32_t acc = (kb > 0) || (p > 0);         // slice p > 0 always finds its accumulators started by slice p - 1
+            // one asm block per slice issues its 4 (7 - p) MMAs with immediate descriptor offsets (umma_issue.cuh)
+            switch (p) {
+              case 0: umma_i8_issue<0, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 1: umma_i8_issue<1, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 2: umma_i8_issue<2, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 3: umma_i8_issue<3, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 4: umma_i8_issue<4, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 5: umma_i8_issue<5, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              default: umma_i8_issue<6, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
             }
             umma_commit(&aempty[as]);                         // the A stage is free once these MMAs have read it
             if (++as == I8_ASTAGES) { as = 0; aph ^= 1u; }
