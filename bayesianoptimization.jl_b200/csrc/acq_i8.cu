@@ -23,6 +23,7 @@
 // Every per-candidate quantity is computed in an order that does not depend on the candidate's position or on its neighbours (the
 // integer products are exact), so a batched call equals the per-point call bit for bit (reference test/acquisitionfunctions.jl:10).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include "umma.cuh"
 #include "umma_issue.cuh"
@@ -171,7 +172,10 @@ __device__ __forceinline__ bool a8_item(int r, int G, int b, int total, int nct,
 
 // MODE 0: out = SsP[2 nit][CH], partial sums over 32 rows of (W k*)^2; k-blocks 0 .. it/2 (W is lower triangular)
 // MODE 1: out = WgT[Np][CH], w = Sigma^-1 k*; all k-blocks
-template <int MODE>
+// TS: the k* slices reach the MMAs through tensor memory (tcgen05.cp into two 32-column buffers behind the accumulators) instead of
+// being re-read from shared memory by each of the up to 7 MMAs per k-step that use them: the shared-memory port (128 B/clk), which
+// bounds the SS form at 840 KB per k-block, carries 504 KB.
+template <int MODE, bool TS>
 __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double* __restrict__ Be, double sBk, int nct, int nit, int nkb_full,
                                                                      int64_t CH, double* __restrict__ out,
                                                                      const __grid_constant__ A8Maps maps) {
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
   const int G = gridDim.x, b = blockIdx.x, total = nct * nit;
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    for (int s = 0; s < A8_S; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < 3; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 8);                                     // one arrival per epilogue warp
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {                                          // ===== TMA producer =====
+    if (elect_one()) {                                        // ===== TMA producer =====
       tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B);
       uint32_t kcnt = 0;                                      // k-blocks so far: B buffer kcnt & 1, phase of every A stage kcnt & 1
       int it, ct;
@@ -214,41 +218,63 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
           mbar_wait_or_trap(&bempty[bs], ((kcnt >> 1) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&bfull[bs], A8_S * A8_B_BYTES);
           for (int q = 0; q < A8_S; ++q) tma_load_3d(sB + (bs * A8_S + q) * A8_B_BYTES, &maps.B, &bfull[bs], kb * 128, brow, q);
-          for (int p = 0; p < A8_S; ++p) {
-            mbar_wait_or_trap(&aempty[p], (kcnt & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&afull[p], A8_A_BYTES);
-            tma_load_3d(sA + p * A8_A_BYTES, &maps.A, &afull[p], kb * 128, arow, p);
+          for (int g = 0; g < 3; ++g) {                         // slices {0,1}, {2,3}, {4,5,6}: one full/empty barrier pair per group
+            const int p0 = 2 * g, p1 = g == 2 ? A8_S : 2 * g + 2;
+            mbar_wait_or_trap(&aempty[g], (kcnt & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&afull[g], (uint32_t)(p1 - p0) * A8_A_BYTES);
+            for (int p = p0; p < p1; ++p) tma_load_3d(sA + p * A8_A_BYTES, &maps.A, &afull[g], kb * 128, arow, p);
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                          // ===== MMA issuer =====
+    if (elect_one()) {                                        // ===== MMA issuer =====
       // D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A8_BN >> 3) << 17) | ((uint32_t)(A8_BM >> 4) << 24);
       const uint64_t dA0 = umma_desc_sw128(smem_u32(sA)), dB0 = umma_desc_sw128(smem_u32(sB));
       uint32_t kcnt = 0;
       int it, ct;
+#ifdef A8_PROF
+      long long w_t = 0, w_a = 0, w_b = 0, w_a0 = 0, w_ap[7] = {0,0,0,0,0,0,0}, t_all = clock64(), tq; int nitems = 0;
+#define A8_TIMED(acc_, stmt) do { tq = clock64(); stmt; acc_ += clock64() - tq; } while (0)
+#define A8_EXTRA(P) { const long long dt_ = clock64() - tq; w_ap[P] += dt_; if (kb == 0) w_a0 += dt_; }
+#else
+#define A8_TIMED(acc_, stmt) do { stmt; } while (0)
+#define A8_EXTRA(P)
+#endif
       for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
         const int nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
-        mbar_wait_or_trap(tempty, ((uint32_t)r & 1u) ^ 1u);   // the epilogue has read the previous item's accumulators
+#ifdef A8_PROF
+        ++nitems;
+#endif
+        A8_TIMED(w_t, mbar_wait_or_trap(tempty, ((uint32_t)r & 1u) ^ 1u));   // the epilogue has read the previous item's accumulators
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         for (int kb = 0; kb < nkb; ++kb, ++kcnt) {
           const uint32_t bs = kcnt & 1u, aph = kcnt & 1u, acc = kb > 0;
           const uint64_t db = dB0 + (uint64_t)(bs * ((A8_S * A8_B_BYTES) >> 4));
-          mbar_wait_or_trap(&bfull[bs], (kcnt >> 1) & 1u);
+          A8_TIMED(w_b, mbar_wait_or_trap(&bfull[bs], (kcnt >> 1) & 1u));
           // slice p of k*: one asm block issues its 4 (7 - p) MMAs (umma_issue.cuh); tcgen05.commit frees the stage behind them
+#define A8_WAIT(G)                                                                                                \
+          A8_TIMED(w_a, mbar_wait_or_trap(&afull[G], aph)); A8_EXTRA(G)                                           \
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #define A8_ISSUE(P)                                                                                               \
-          mbar_wait_or_trap(&afull[P], aph);                                                                      \
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");                                       \
-          umma_i8_issue<P, A8_BN, (A8_B_BYTES >> 4), 1>(tmem, dA0 + (uint64_t)((P) * (A8_A_BYTES >> 4)), db, idesc, (P) ? 1u : acc); \
-          umma_commit(&aempty[P]);
-          A8_ISSUE(0) A8_ISSUE(1) A8_ISSUE(2) A8_ISSUE(3) A8_ISSUE(4) A8_ISSUE(5) A8_ISSUE(6)
+          if (TS) umma_i8_issue_ts<P, A8_BN, (A8_B_BYTES >> 4), 1>(tmem, tmem + 448u + 32u * ((P) & 1), dA0 + (uint64_t)((P) * (A8_A_BYTES >> 4)), db, idesc, (P) ? 1u : acc); \
+          else umma_i8_issue<P, A8_BN, (A8_B_BYTES >> 4), 1>(tmem, dA0 + (uint64_t)((P) * (A8_A_BYTES >> 4)), db, idesc, (P) ? 1u : acc);
+
+          A8_WAIT(0) A8_ISSUE(0) A8_ISSUE(1) umma_commit(&aempty[0]);
+          A8_WAIT(1) A8_ISSUE(2) A8_ISSUE(3) umma_commit(&aempty[1]);
+          A8_WAIT(2) A8_ISSUE(4) A8_ISSUE(5) A8_ISSUE(6) umma_commit(&aempty[2]);
 #undef A8_ISSUE
+#undef A8_WAIT
           umma_commit(&bempty[bs]);
         }
         umma_commit(tfull);                                   // every MMA of the item retired: accumulators complete
       }
+#ifdef A8_PROF
+      if (b == 0 && kcnt > 0)
+        printf("acq_i8_gemm<%d> CTA0: %u k-blocks %d items, %lld cycles per k-block; waits per k-block: TMEM %lld, A %lld (of which first k-block of an item %lld; by slice %lld %lld %lld %lld %lld %lld %lld), B %lld\n", MODE,
+               kcnt, nitems, (clock64() - t_all) / kcnt, w_t / kcnt, w_a / kcnt, w_a0 / kcnt, w_ap[0] / kcnt, w_ap[1] / kcnt, w_ap[2] / kcnt, w_ap[3] / kcnt, w_ap[4] / kcnt, w_ap[5] / kcnt, w_ap[6] / kcnt, w_b / kcnt);
+#endif
     }
   } else {
     // ===== epilogue: 8 warps; warp w reads TMEM lanes 32 (w & 3) .. +31 (= candidates of the tile), columns 32 half .. +31 (= rows of W) =====
@@ -317,14 +343,21 @@ __device__ __forceinline__ void best_merge(double& bv, long long& bi, double v, 
   if (i >= 0 && (bi < 0 || v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
 }
 
-__global__ void __launch_bounds__(128) acq_finish_kernel(const FinArgs f) {
-  __shared__ double sv[4];
-  __shared__ long long si[4];
-  const int tid = threadIdx.x;
-  const int64_t n = (int64_t)blockIdx.x * 128 + tid, gi = f.c0 + n;
+// 256 threads = 32 candidates x 8 partial-sum classes: class g adds the partials k = g, g + 8, ... in ascending order, the eight class
+// sums are then added in ascending g (a fixed tree, the same for every candidate wherever it sits in the batch)
+__global__ void __launch_bounds__(256) acq_finish_kernel(const FinArgs f) {
+  __shared__ double smu[8][32], sss[8][32];
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int64_t n = (int64_t)blockIdx.x * 32 + lane, gi = f.c0 + n;
   double musum = 0.0, ss = 0.0;
-  for (int k = 0; k < f.nblk; ++k) musum += f.MuP[(int64_t)k * f.CH + n];
-  for (int k = 0; k < f.nss; ++k) ss += f.SsP[(int64_t)k * f.CH + n];
+  for (int k = g; k < f.nblk; k += 8) musum += f.MuP[(int64_t)k * f.CH + n];
+  for (int k = g; k < f.nss; k += 8) ss += f.SsP[(int64_t)k * f.CH + n];
+  smu[g][lane] = musum; sss[g][lane] = ss;
+  __syncthreads();
+  if (g != 0) return;
+  musum = smu[0][lane]; ss = sss[0][lane];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) { musum += smu[k][lane]; ss += sss[k][lane]; }
   const double mu = f.beta + musum;
   const double s2 = fmax(f.sf2 - ss, 0.0);
   double val = mu, amu = 1.0, as2 = 0.0;
@@ -348,12 +381,7 @@ __global__ void __launch_bounds__(128) acq_finish_kernel(const FinArgs f) {
     const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
     best_merge(bv, bi, ov, oi);
   }
-  if ((tid & 31) == 0) { sv[tid >> 5] = bv; si[tid >> 5] = bi; }
-  __syncthreads();
-  if (tid == 0) {
-    for (int k = 1; k < 4; ++k) best_merge(bv, bi, sv[k], si[k]);
-    f.cta_best[blockIdx.x].value = bv; f.cta_best[blockIdx.x].index = bi;
-  }
+  if (lane == 0) { f.cta_best[blockIdx.x].value = bv; f.cta_best[blockIdx.x].index = bi; }
 }
 
 __global__ void __launch_bounds__(256) argmax_blocks_kernel(const b200bo_best_t* __restrict__ in, int n, b200bo_best_t* __restrict__ out) {
@@ -573,7 +601,7 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
   const int64_t CHmax = chunk_of(std::max<int64_t>(Np, NB));
   const int64_t CH = std::min<int64_t>(CHmax, (M + 127) / 128 * 128);
   const int64_t nchunks = (M + CH - 1) / CH;
-  const int64_t nblocks_total = nchunks * (CH / 128);
+  const int64_t nblocks_total = nchunks * (CH / 32);
   if ((e = ensure_chunk_buffers(h, CH, want_grad, nblocks_total)) != cudaSuccess) return e;
   double* dSsP = h->dMuP + (size_t)CH * (size_t)(std::max<int64_t>(Np, NB) / NB);
   double* dAmu = dSsP + (size_t)CH * (size_t)(std::max<int64_t>(Np, NB) / 32);
@@ -587,8 +615,11 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
   A8Maps mapsW, mapsK;
   mapsW.A = h->tmBsA; mapsW.B = h->tmWsB;
   mapsK.A = h->tmBsA; mapsK.B = h->tmKsB;
-  cudaFuncSetAttribute(acq_i8_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
-  cudaFuncSetAttribute(acq_i8_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  static const bool ts = getenv("B200BO_ACQ_TS") && atoi(getenv("B200BO_ACQ_TS")) == 1;   // developer knob: 1 = A through tensor memory (measured slower: the tcgen05.cp copies cost more than the A-collector reuse saves)
+  cudaFuncSetAttribute(acq_i8_gemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  cudaFuncSetAttribute(acq_i8_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  cudaFuncSetAttribute(acq_i8_gemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  cudaFuncSetAttribute(acq_i8_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
   int64_t blk0 = 0;
   for (int64_t c0 = 0; c0 < M; c0 += CH) {
     const int64_t mc = std::min<int64_t>(CH, M - c0);
@@ -607,7 +638,8 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
       if (e != cudaSuccess) return e;
       const int total = nct * nit;
       const int grid = std::min(total, h->num_sms);
-      acq_i8_gemm_kernel<0><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
+      if (ts) acq_i8_gemm_kernel<0, true><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
+      else acq_i8_gemm_kernel<0, false><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
       h->launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -617,10 +649,10 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
     f.acq = l.acq_kind; f.p0 = l.p0; f.p1 = l.p1; f.seed = l.seed;
     f.values = l.dvalues; f.mu = l.dmu; f.var = l.dvar; f.amu = want_grad ? dAmu : nullptr; f.as2 = want_grad ? dAs2 : nullptr;
     f.cta_best = h->dcta_best2 + blk0;
-    acq_finish_kernel<<<(unsigned)(mcp / 128), 128, 0, h->stream>>>(f);
+    acq_finish_kernel<<<(unsigned)(mcp / 32), 256, 0, h->stream>>>(f);
     h->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    blk0 += mcp / 128;
+    blk0 += mcp / 32;
     if (want_grad) {
       if (nblk == 0) {
         if ((e = cudaMemsetAsync(l.dgrad + c0 * h->D, 0, sizeof(double) * mc * h->D, h->stream)) != cudaSuccess) return e;
@@ -628,7 +660,8 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
       }
       const int total = nct * nit;
       const int grid = std::min(total, h->num_sms);
-      acq_i8_gemm_kernel<1><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dKe, sBk, nct, nit, nblk, CH, h->dWg, mapsK);
+      if (ts) acq_i8_gemm_kernel<1, true><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dKe, sBk, nct, nit, nblk, CH, h->dWg, mapsK);
+      else acq_i8_gemm_kernel<1, false><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dKe, sBk, nct, nit, nblk, CH, h->dWg, mapsK);
       h->launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       GradArgs g;

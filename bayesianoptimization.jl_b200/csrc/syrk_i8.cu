@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {                                          // ===== TMA producer =====
+    if (elect_one()) {                                        // ===== TMA producer =====
       tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B);
       int as = 0; uint32_t aph = 0, bcnt = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                          // ===== MMA issuer =====
+    if (elect_one()) {                                        // ===== MMA issuer =====
       // D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
       int as = 0; uint32_t aph = 0, bcnt = 0, it = 0;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8w_kernel(double* __restr
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {                                          // ===== TMA producer =====
+    if (elect_one()) {                                        // ===== TMA producer =====
       tma_prefetch_desc(&map);
       int as = 0; uint32_t aph = 0, bgen = 0;                 // bgen: bit q = parity of the number of loads into slot q so far
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8w_kernel(double* __restr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                          // ===== MMA issuer =====
+    if (elect_one()) {                                        // ===== MMA issuer =====
       // D = s32, A = B = signed 8-bit, both K-major, N = 128, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8W_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
       int as = 0; uint32_t aph = 0, bgen = 0, ev = 0;         // ev: accumulator hand-overs so far (two per tile)

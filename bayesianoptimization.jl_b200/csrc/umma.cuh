@@ -6,6 +6,15 @@
 
 namespace b200bo {
 
+// One lane of a CONVERGED warp (elect.sync).  Unlike `lane == 0`, ptxas can prove that a region guarded by this predicate runs on a
+// single thread, so every tcgen05.mma / cp.async.bulk.tensor inside compiles to one UTCIMMA / UTMALDG; behind `lane == 0` each of
+// them is wrapped in an election loop (ELECT / PLOP3 / BRA.U.ANY, ~8 dependent scalar instructions = 45-60 cycles per 32-cycle MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- tcgen05 plumbing ----
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {   // K-major, SWIZZLE_128B, 8-row groups 1024 B apart (version 1)
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
