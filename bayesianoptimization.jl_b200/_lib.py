@@ -13,14 +13,14 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200bo.so")
 
-OK, ERR_ARG, ERR_CUDA, ERR_NOTPD, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5
+OK, ERR_ARG, ERR_CUDA, ERR_NOTPD, ERR_STATE, ERR_ALLOC, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 
 KERNEL_KINDS = {"SEIso": 0, "SEArd": 1, "Mat12Iso": 2, "Mat12Ard": 3, "Mat32Iso": 4, "Mat32Ard": 5, "Mat52Iso": 6,
                 "Mat52Ard": 7}
 MEAN_KINDS = {"MeanZero": 0, "MeanConst": 1}
 ACQ_KINDS = {"PI": 0, "EI": 1, "UCB": 2, "TS": 3, "MI": 4, "MaxMean": 5}
 MASK_NOISE, MASK_MEAN, MASK_KERN = 1, 2, 4
-T_KMAT, T_CHOL, T_SYRK, T_ALPHA, T_ACQ, T_MLL = range(6)
+T_KMAT, T_CHOL, T_SYRK, T_ALPHA, T_ACQ, T_MLL, T_ACQ_GEMM = range(7)
 
 
 class Best(C.Structure):
@@ -40,6 +40,11 @@ _H = C.c_void_p
 PROTOTYPES = {
     "b200bo_create": [C.POINTER(_H), C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32],
     "b200bo_destroy": [_H],
+    "b200bo_create_multi": [C.POINTER(_H), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_int32, C.c_int32],
+    "b200bo_num_gpus": [_H, C.POINTER(C.c_int32)],
+    "b200bo_comm_unique_id": [C.c_char_p],
+    "b200bo_comm_init_rank": [_H, C.c_int32, C.c_int32, C.c_char_p],
+    "b200bo_comm_destroy": [_H],
     "b200bo_last_error": [_H],
     "b200bo_set_stream": [_H, C.c_void_p],
     "b200bo_sync": [_H],
@@ -75,6 +80,8 @@ PROTOTYPES = {
     "b200bo_fp64_peak_tflops": [_H, _dp],
     "b200bo_set_syrk_engine": [_H, C.c_int32],
     "b200bo_set_acq_engine": [_H, C.c_int32],
+    "b200bo_i8_peak_tops": [_H, _dp],
+    "b200bo_set_knob": [_H, C.c_char_p, C.c_int64],
     "b200bo_version": [],
 }
 _RESTYPES = {"b200bo_last_error": C.c_char_p}

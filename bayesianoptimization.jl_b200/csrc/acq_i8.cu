@@ -38,7 +38,7 @@ constexpr int A8_BN = 64;                // rows of W / Sigma^-1 per tile = UMMA
 constexpr uint32_t A8_A_BYTES = A8_BM * 128, A8_B_BYTES = A8_BN * 128;
 constexpr size_t A8_SMEM = 2 * A8_S * A8_B_BYTES + A8_S * A8_A_BYTES + 1024;      // 224 KB of operand stages + barriers
 constexpr int A8_THREADS = 320;          // producer warp, MMA warp, 8 epilogue warps
-constexpr int64_t A8_CHUNK_BYTES = 48ll << 20;   // k* slices of one chunk (L2 holds 126 MB)
+constexpr int64_t A8_CHUNK_BYTES = 64ll << 20;   // k* slices of one chunk; two chunks are in flight (L2 holds 126 MB)
 
 // byte k of 16 digit words -> one 16-byte vector (element u in byte u)
 __device__ __forceinline__ uint4 gather_byte(const unsigned long long (&dg)[16], int k) {
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 struct KsArgs {
   const double* Z; const double* alpha; const double* inv_ell; const double* Xs;
   uint8_t* Bs; double* MuP;
+  double* G;                    // gradient launches: sf2 psi(r2) [Np][CH] (psi = -2 dphi/dr2), so that the gradient pass evaluates no kernel
   int64_t M, c0, CH, Kp;        // candidates in the call, first candidate of the chunk, chunk capacity (rows per slice), bytes per slice row
   int N, D;
   double sf2, qscale;           // qscale = 2^54 / S, S = the fixed power-of-two scale of k*
@@ -135,7 +136,10 @@ __global__ void __launch_bounds__(256) kstar_slice_kernel(const KsArgs a) {
         r2 = fma(u1, u1, r2);
       }
       const bool live = jb * 128 + j0 + j < a.N;
-      const double ks = live ? a.sf2 * kern_phi<FAM>(r2) : 0.0;
+      double phi, psi = 0.0;
+      if (a.G) kern_phi_psi<FAM>(r2, phi, psi); else phi = kern_phi<FAM>(r2);      // the same phi either way, bit for bit
+      const double ks = live ? a.sf2 * phi : 0.0;
+      if (a.G) __stcs(a.G + ((int64_t)jb * 128 + j0 + j) * a.CH + t0 + n, live ? a.sf2 * psi : 0.0);
       mu = fma(alb[j0 + j], ks, mu);
       dg[j] = i8_digits(__double2ll_rn(ks * a.qscale));
     }
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
         out[(int64_t)(2 * it + half) * CH + (int64_t)ct * A8_BM + m] = ss;
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) out[(int64_t)(brow + c) * CH + (int64_t)ct * A8_BM + m] = acc[c] * (sBk * __ldg(Be + brow + c));
+        for (int c = 0; c < 32; ++c) __stcs(out + (int64_t)(brow + c) * CH + (int64_t)ct * A8_BM + m, acc[c] * (sBk * __ldg(Be + brow + c)));   // read once, by the gradient pass
       }
     }
   }
@@ -404,20 +408,23 @@ __global__ void __launch_bounds__(256) argmax_blocks_kernel(const b200bo_best_t*
 }
 
 // ---- gradient: grad_d = -1/l_d sum_m (a_mu alpha_m - 2 a_s2 w_m) sf2 psi(r2_m) (z*_d - z_md)    ----
+// w = Sigma^-1 k* comes from the second slice product (WgT [Np][CH]), sf2 psi from the kernel-evaluation pass (G [Np][CH]): this pass
+// is D + 3 FMAs per (observation, candidate) pair.  Block = 32 candidates (lanes: coalesced rows of WgT / G) x 4 groups of observations;
+// blockIdx.y takes a contiguous range of 128-blocks and leaves a partial sum, which grad_reduce_kernel adds in ascending order.
 struct GradArgs {
-  const double* Z; const double* alpha; const double* inv_ell; const double* Xs; const double* WgT; const double* amu; const double* as2;
+  const double* Z; const double* alpha; const double* inv_ell; const double* Xs; const double* WgT; const double* G; const double* amu; const double* as2;
+  double* part;                 // [splits][CH][D]
   double* grad;
   int64_t M, c0, CH;
-  int N, D, nblk;
-  double sf2;
+  int N, D, nblk, nsplit;
 };
 
-template <int FAM, int DP>
-__global__ void __launch_bounds__(256, 1) acq_grad_kernel(const GradArgs a) {
+template <int DP>
+__global__ void __launch_bounds__(128) acq_grad_kernel(const GradArgs a) {
   extern __shared__ __align__(16) uint8_t gr_smem[];
   double* zx = reinterpret_cast<double*>(gr_smem);            // [128][DP]
   double* alb = zx + 128 * DP;                                // [128]
-  double* red = alb + 128;                                    // [8][32][DP + 1]
+  double* red = alb + 128;                                    // [4][32][DP + 1]
   const int tid = threadIdx.x, n = tid & 31, mg = tid >> 5, D = a.D;
   const int64_t cn = (int64_t)blockIdx.x * 32 + n;
   int64_t gi = a.c0 + cn;
@@ -426,49 +433,49 @@ __global__ void __launch_bounds__(256, 1) acq_grad_kernel(const GradArgs a) {
 #pragma unroll
   for (int d = 0; d < DP; ++d) { zc[d] = d < D ? a.Xs[gi * D + d] * a.inv_ell[d] : 0.0; gacc[d] = 0.0; }
   const double amu = a.amu[cn], as2m2 = -2.0 * a.as2[cn];
-  for (int jb = 0; jb < a.nblk; ++jb) {
+  const int per = (a.nblk + a.nsplit - 1) / a.nsplit;
+  const int jb0 = blockIdx.y * per, jb1 = min(a.nblk, jb0 + per);
+  for (int jb = jb0; jb < jb1; ++jb) {
     __syncthreads();
-    for (int e = tid; e < 128 * DP; e += 256) {
+    for (int e = tid; e < 128 * DP; e += 128) {
       const int m = e / DP, d = e - m * DP;
       zx[e] = d < D ? a.Z[((int64_t)jb * 128 + m) * D + d] : 0.0;
     }
-    if (tid < 128) alb[tid] = a.alpha[jb * 128 + tid];
+    alb[tid] = a.alpha[jb * 128 + tid];
     __syncthreads();
-#pragma unroll 1
-    for (int j = 0; j < 16; ++j) {
-      const int m = 16 * mg + j;
+    const double* wp = a.WgT + ((int64_t)jb * 128 + 32 * mg) * a.CH + cn;
+    const double* gp = a.G + ((int64_t)jb * 128 + 32 * mg) * a.CH + cn;
+#pragma unroll 2
+    for (int j = 0; j < 32; ++j) {
+      const int m = 32 * mg + j;
+      const double c = fma(amu, alb[m], as2m2 * __ldcs(wp + (int64_t)j * a.CH)) * __ldcs(gp + (int64_t)j * a.CH);   // G is zero in the padding rows
       const double* zr = zx + m * DP;
-      double u[DP];
-      double r2 = 0.0;
 #pragma unroll
       for (int d = 0; d < DP; d += 2) {
         const double2 x = *reinterpret_cast<const double2*>(zr + d);
-        u[d] = x.x - zc[d]; u[d + 1] = x.y - zc[d + 1];
-        r2 = fma(u[d], u[d], r2);
-        r2 = fma(u[d + 1], u[d + 1], r2);
+        gacc[d] = fma(c, zc[d] - x.x, gacc[d]);
+        gacc[d + 1] = fma(c, zc[d + 1] - x.y, gacc[d + 1]);
       }
-      double phi, psi;
-      kern_phi_psi<FAM>(r2, phi, psi);
-      const double w = a.WgT[((int64_t)jb * 128 + m) * a.CH + cn];
-      const bool live = jb * 128 + m < a.N;
-      const double c = live ? fma(amu, alb[m], as2m2 * w) * a.sf2 * psi : 0.0;
-#pragma unroll
-      for (int d = 0; d < DP; ++d) gacc[d] = fma(-c, u[d], gacc[d]);       // c (z* - z_m) = -c u
     }
   }
   __syncthreads();
 #pragma unroll
   for (int d = 0; d < DP; ++d) red[(mg * 32 + n) * (DP + 1) + d] = gacc[d];
   __syncthreads();
-  for (int e = tid; e < 32 * D; e += 256) {
+  for (int e = tid; e < 32 * D; e += 128) {
     const int nn = e / D, d = e - nn * D;
-    const int64_t g2 = a.c0 + (int64_t)blockIdx.x * 32 + nn;
-    if (g2 >= a.M) continue;
-    double s = red[nn * (DP + 1) + d];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) s += red[(k * 32 + nn) * (DP + 1) + d];
-    a.grad[g2 * D + d] = -s * a.inv_ell[d];
+    const double s = ((red[nn * (DP + 1) + d] + red[(32 + nn) * (DP + 1) + d]) + red[(64 + nn) * (DP + 1) + d]) + red[(96 + nn) * (DP + 1) + d];
+    a.part[((int64_t)blockIdx.y * a.CH + (int64_t)blockIdx.x * 32 + nn) * D + d] = s;
   }
+}
+
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const GradArgs a, int64_t mc) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= mc * a.D) return;
+  const int64_t cn = e / a.D; const int d = (int)(e - cn * a.D);
+  double s = 0.0;
+  for (int k = 0; k < a.nsplit; ++k) s += a.part[((int64_t)k * a.CH + cn) * a.D + d];
+  a.grad[(a.c0 + cn) * a.D + d] = -s * a.inv_ell[d];
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
@@ -479,8 +486,9 @@ bool acq_i8_default() {
   return on;
 }
 
-static int64_t chunk_of(int64_t Np) {
-  int64_t ch = A8_CHUNK_BYTES / (A8_S * Np) / 128 * 128;
+static int64_t chunk_of(int64_t Np, int64_t knob_mb) {
+  const int64_t budget = knob_mb > 0 ? (knob_mb << 20) : A8_CHUNK_BYTES;
+  int64_t ch = budget / (A8_S * Np) / 128 * 128;
   return std::max<int64_t>(128, std::min<int64_t>(ch, 8192));
 }
 
@@ -520,28 +528,30 @@ static cudaError_t ensure_slices(b200bo_handle_s* h, bool want_grad) {
   return cudaSuccess;
 }
 
-// chunk buffers: k* slices, partial sums, (gradient) w and the functor partials; sized for the current Np
+// chunk buffers, TWO sets (consecutive chunks alternate between two stream lanes): k* slices, partial sums, (gradient) w / sf2 psi /
+// partial gradients; sized for the current Np
 static cudaError_t ensure_chunk_buffers(b200bo_handle_s* h, int64_t CH, bool want_grad, int64_t nblocks) {
   const int64_t Np = std::max<int64_t>(h->Np, NB);
   cudaError_t e = cudaSuccess;
-  const size_t need_bs = (size_t)A8_S * CH * Np;
-  if (need_bs > h->bs_bytes) {
+  const size_t lane_bs = (size_t)A8_S * CH * Np;
+  if (2 * lane_bs > h->bs_bytes) {
     cudaFree(h->dBs); h->dBs = nullptr; h->bs_bytes = 0; h->bs_np = 0;
-    if ((e = cudaMalloc(&h->dBs, need_bs)) != cudaSuccess) return e;
-    h->bs_bytes = need_bs;
+    if ((e = cudaMalloc(&h->dBs, 2 * lane_bs)) != cudaSuccess) return e;
+    h->bs_bytes = 2 * lane_bs;
   }
   if (h->bs_np != Np || h->bs_ch != CH) {
-    if ((e = make_map3d_u8(&h->tmBsA, h->dBs, (uint64_t)Np, (uint64_t)CH, A8_S, 128, A8_BM)) != cudaSuccess) return e;
+    for (int ln = 0; ln < 2; ++ln)
+      if ((e = make_map3d_u8(&h->tmBsA[ln], static_cast<uint8_t*>(h->dBs) + ln * lane_bs, (uint64_t)Np, (uint64_t)CH, A8_S, 128, A8_BM)) != cudaSuccess) return e;
     h->bs_np = Np; h->bs_ch = CH;
   }
-  const size_t need_p = sizeof(double) * (size_t)CH * (size_t)(Np / NB + Np / 32 + 2);
+  const size_t need_p = 2 * sizeof(double) * (size_t)CH * (size_t)(Np / NB + Np / 32 + 2);
   if (need_p > h->part_bytes) {
     cudaFree(h->dMuP); h->dMuP = nullptr; h->part_bytes = 0;
     if ((e = cudaMalloc(&h->dMuP, need_p)) != cudaSuccess) return e;
     h->part_bytes = need_p;
   }
   if (want_grad) {
-    const size_t need_w = sizeof(double) * (size_t)CH * (size_t)Np;
+    const size_t need_w = 2 * sizeof(double) * (size_t)CH * (size_t)(2 * Np + 16 * h->D);      // w = Sigma^-1 k*, sf2 psi, <= 16 partial gradients
     if (need_w > h->wg_bytes) {
       cudaFree(h->dWg); h->dWg = nullptr; h->wg_bytes = 0;
       if ((e = cudaMalloc(&h->dWg, need_w)) != cudaSuccess) return e;
@@ -553,11 +563,13 @@ static cudaError_t ensure_chunk_buffers(b200bo_handle_s* h, int64_t CH, bool wan
     if ((e = cudaMalloc(&h->dcta_best2, sizeof(b200bo_best_t) * (size_t)nblocks)) != cudaSuccess) return e;
     h->nbest2 = nblocks;
   }
+  for (auto& ev : h->acq_ev)
+    if (!ev && (e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 template <int FAM>
-static cudaError_t launch_kstar(b200bo_handle_s* h, const KsArgs& a, int nblk, int ntile64) {
+static cudaError_t launch_kstar(b200bo_handle_s* h, cudaStream_t st, const KsArgs& a, int nblk, int ntile64) {
   const int D = h->D;
   const int DP = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
   const size_t smem = sizeof(double) * (128 * DP + 128 + 8 * 64) + A8_S * 64 * 128;
@@ -565,7 +577,7 @@ static cudaError_t launch_kstar(b200bo_handle_s* h, const KsArgs& a, int nblk, i
 #define B200BO_KS(DPV)                                                                                              \
   do {                                                                                                              \
     cudaFuncSetAttribute(kstar_slice_kernel<FAM, DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-    kstar_slice_kernel<FAM, DPV><<<grid, 256, smem, h->stream>>>(a);                                                \
+    kstar_slice_kernel<FAM, DPV><<<grid, 256, smem, st>>>(a);                                                \
   } while (0)
   if (DP == 4) B200BO_KS(4); else if (DP == 8) B200BO_KS(8); else if (DP == 16) B200BO_KS(16); else B200BO_KS(32);
 #undef B200BO_KS
@@ -573,109 +585,138 @@ static cudaError_t launch_kstar(b200bo_handle_s* h, const KsArgs& a, int nblk, i
   return cudaGetLastError();
 }
 
-template <int FAM>
-static cudaError_t launch_grad(b200bo_handle_s* h, const GradArgs& a, int nblocks) {
+static cudaError_t launch_grad(b200bo_handle_s* h, cudaStream_t st, const GradArgs& a, int nblocks, int64_t mc) {
   const int D = h->D;
   const int DP = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
-  const size_t smem = sizeof(double) * (128 * DP + 128 + 8 * 32 * (DP + 1));
-#define B200BO_GR(DPV)                                                                                              \
-  do {                                                                                                              \
-    cudaFuncSetAttribute(acq_grad_kernel<FAM, DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    acq_grad_kernel<FAM, DPV><<<nblocks, 256, smem, h->stream>>>(a);                                                \
+  const size_t smem = sizeof(double) * (128 * DP + 128 + 4 * 32 * (DP + 1));
+  const dim3 grid(nblocks, a.nsplit);
+#define B200BO_GR(DPV)                                                                                         \
+  do {                                                                                                         \
+    cudaFuncSetAttribute(acq_grad_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    acq_grad_kernel<DPV><<<grid, 128, smem, st>>>(a);                                                   \
   } while (0)
   if (DP == 4) B200BO_GR(4); else if (DP == 8) B200BO_GR(8); else if (DP == 16) B200BO_GR(16); else B200BO_GR(32);
 #undef B200BO_GR
-  h->launches++;
+  grad_reduce_kernel<<<(unsigned)((mc * D + 255) / 256), 256, 0, st>>>(a, mc);
+  h->launches += 2;
   return cudaGetLastError();
+}
+
+// bench instrumentation (knob "acq_gemm_timing"): an event before and after every slice-product launch
+static void gemm_event(b200bo_handle_s* h, cudaStream_t st) {
+  if (!h->acq_time_gemm) return;
+  if (h->gemm_ev_used == (int)h->gemm_ev.size()) { cudaEvent_t ev; if (cudaEventCreate(&ev) != cudaSuccess) return; h->gemm_ev.push_back(ev); }
+  cudaEventRecord(h->gemm_ev[h->gemm_ev_used++], st);
 }
 
 // The acquisition step over l.M candidate columns on the tcgen05 path.  Same contract as launch_acquire (acq.cu).
 cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
   const int64_t M = l.M;
   if (M == 0) return cudaSuccess;
-  const int64_t Np = h->Np;
+  const int64_t Np = h->Np, Npb = std::max<int64_t>(Np, NB);
   const int nblk = (int)(Np / NB), nit = (int)(Np / A8_BN);
   const bool want_grad = l.dgrad != nullptr;
   cudaError_t e = cudaSuccess;
   if (nblk > 0 && (e = ensure_slices(h, want_grad)) != cudaSuccess) return e;
-  const int64_t CHmax = chunk_of(std::max<int64_t>(Np, NB));
-  const int64_t CH = std::min<int64_t>(CHmax, (M + 127) / 128 * 128);
-  const int64_t nchunks = (M + CH - 1) / CH;
+  // chunks of equal size, at most the L2 budget each; consecutive chunks run on two stream lanes with their own buffers, so the
+  // kernel-evaluation pass and the scores of one chunk fill the SMs that the slice product of the other leaves idle at its tail
+  const int64_t CHmax = chunk_of(Npb, h->acq_chunk_mb);
+  int64_t nchunks = (M + CHmax - 1) / CHmax;
+  const int64_t CH = std::min<int64_t>(CHmax, ((M + nchunks - 1) / nchunks + 127) / 128 * 128);
+  nchunks = (M + CH - 1) / CH;
   const int64_t nblocks_total = nchunks * (CH / 32);
   if ((e = ensure_chunk_buffers(h, CH, want_grad, nblocks_total)) != cudaSuccess) return e;
-  double* dSsP = h->dMuP + (size_t)CH * (size_t)(std::max<int64_t>(Np, NB) / NB);
-  double* dAmu = dSsP + (size_t)CH * (size_t)(std::max<int64_t>(Np, NB) / 32);
-  double* dAs2 = dAmu + CH;
+  const size_t lane_bs = (size_t)A8_S * CH * Npb, lane_p = (size_t)CH * (size_t)(Npb / NB + Npb / 32 + 2), lane_w = (size_t)CH * (size_t)(2 * Npb + 16 * h->D);
   const double sf2 = exp(2.0 * h->hp.lsigma);
   int e2 = 0;
-  frexp(sf2, &e2);                                            // sf2 = f 2^e2, f in [0.5, 1): S = 2^e2 > sf2
-  const double S = ldexp(1.0, e2);
+  frexp(sf2, &e2);                                            // sf2 = f 2^e2, f in [0.5, 1): the fixed scale of k* is S = 2^e2 > sf2
   const double qscale = ldexp(1.0, 54 - e2), sBk = ldexp(1.0, e2 - 6);
-  (void)S;
-  A8Maps mapsW, mapsK;
-  mapsW.A = h->tmBsA; mapsW.B = h->tmWsB;
-  mapsK.A = h->tmBsA; mapsK.B = h->tmKsB;
   static const bool ts = getenv("B200BO_ACQ_TS") && atoi(getenv("B200BO_ACQ_TS")) == 1;   // developer knob: 1 = A through tensor memory (measured slower: the tcgen05.cp copies cost more than the A-collector reuse saves)
+  const bool one_lane = h->acq_lanes == 1 || h->acq_time_gemm;
+  h->gemm_ev_used = 0;
   cudaFuncSetAttribute(acq_i8_gemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
   cudaFuncSetAttribute(acq_i8_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
   cudaFuncSetAttribute(acq_i8_gemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
   cudaFuncSetAttribute(acq_i8_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  const bool two = nchunks > 1 && !one_lane && h->stream2 != nullptr;
+  cudaStream_t lanes[2] = {h->stream, two ? h->stream2 : h->stream};
+  if (two) {                                                  // lane 1 starts behind everything already queued on the handle's stream
+    if ((e = cudaEventRecord(h->acq_ev[0], h->stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(h->stream2, h->acq_ev[0], 0)) != cudaSuccess) return e;
+  }
   int64_t blk0 = 0;
-  for (int64_t c0 = 0; c0 < M; c0 += CH) {
+  int64_t ci = 0;
+  for (int64_t c0 = 0; c0 < M; c0 += CH, ++ci) {
+    const int ln = two ? (int)(ci & 1) : 0;
+    cudaStream_t st = lanes[ln];
+    uint8_t* dBs = static_cast<uint8_t*>(h->dBs) + ln * lane_bs;
+    double* dMuP = h->dMuP + ln * lane_p;
+    double* dSsP = dMuP + (size_t)CH * (size_t)(Npb / NB);
+    double* dAmu = dSsP + (size_t)CH * (size_t)(Npb / 32);
+    double* dAs2 = dAmu + CH;
+    double* dWg = want_grad ? h->dWg + ln * lane_w : nullptr;
+    A8Maps mapsW, mapsK;
+    mapsW.A = h->tmBsA[ln]; mapsW.B = h->tmWsB;
+    mapsK.A = h->tmBsA[ln]; mapsK.B = h->tmKsB;
     const int64_t mc = std::min<int64_t>(CH, M - c0);
     const int64_t mcp = (mc + 127) / 128 * 128;
     const int nct = (int)(mcp / A8_BM);
     if (nblk > 0) {
       KsArgs k;
-      k.Z = h->dZ; k.alpha = h->dalpha; k.inv_ell = h->dinv_ell; k.Xs = l.dXs; k.Bs = reinterpret_cast<uint8_t*>(h->dBs); k.MuP = h->dMuP;
+      k.Z = h->dZ; k.alpha = h->dalpha; k.inv_ell = h->dinv_ell; k.Xs = l.dXs; k.Bs = dBs; k.MuP = dMuP;
+      k.G = want_grad ? dWg + (size_t)CH * (size_t)Np : nullptr;
       k.M = M; k.c0 = c0; k.CH = CH; k.Kp = Np; k.N = (int)h->N; k.D = h->D; k.sf2 = sf2; k.qscale = qscale;
       switch (h->fam) {
-        case FAM_SE: e = launch_kstar<FAM_SE>(h, k, nblk, (int)(mcp / 64)); break;
-        case FAM_MAT12: e = launch_kstar<FAM_MAT12>(h, k, nblk, (int)(mcp / 64)); break;
-        case FAM_MAT32: e = launch_kstar<FAM_MAT32>(h, k, nblk, (int)(mcp / 64)); break;
-        default: e = launch_kstar<FAM_MAT52>(h, k, nblk, (int)(mcp / 64)); break;
+        case FAM_SE: e = launch_kstar<FAM_SE>(h, st, k, nblk, (int)(mcp / 64)); break;
+        case FAM_MAT12: e = launch_kstar<FAM_MAT12>(h, st, k, nblk, (int)(mcp / 64)); break;
+        case FAM_MAT32: e = launch_kstar<FAM_MAT32>(h, st, k, nblk, (int)(mcp / 64)); break;
+        default: e = launch_kstar<FAM_MAT52>(h, st, k, nblk, (int)(mcp / 64)); break;
       }
       if (e != cudaSuccess) return e;
       const int total = nct * nit;
       const int grid = std::min(total, h->num_sms);
-      if (ts) acq_i8_gemm_kernel<0, true><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
-      else acq_i8_gemm_kernel<0, false><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
+      gemm_event(h, st);
+      if (ts) acq_i8_gemm_kernel<0, true><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
+      else acq_i8_gemm_kernel<0, false><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
+      gemm_event(h, st);
       h->launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     FinArgs f;
-    f.MuP = h->dMuP; f.SsP = dSsP; f.CH = CH; f.M = M; f.c0 = c0; f.idx_offset = l.idx_offset;
+    f.MuP = dMuP; f.SsP = dSsP; f.CH = CH; f.M = M; f.c0 = c0; f.idx_offset = l.idx_offset;
     f.nblk = nblk; f.nss = 2 * nit; f.sf2 = sf2; f.beta = h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0;
     f.acq = l.acq_kind; f.p0 = l.p0; f.p1 = l.p1; f.seed = l.seed;
     f.values = l.dvalues; f.mu = l.dmu; f.var = l.dvar; f.amu = want_grad ? dAmu : nullptr; f.as2 = want_grad ? dAs2 : nullptr;
     f.cta_best = h->dcta_best2 + blk0;
-    acq_finish_kernel<<<(unsigned)(mcp / 32), 256, 0, h->stream>>>(f);
+    acq_finish_kernel<<<(unsigned)(mcp / 32), 256, 0, st>>>(f);
     h->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     blk0 += mcp / 32;
     if (want_grad) {
       if (nblk == 0) {
-        if ((e = cudaMemsetAsync(l.dgrad + c0 * h->D, 0, sizeof(double) * mc * h->D, h->stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(l.dgrad + c0 * h->D, 0, sizeof(double) * mc * h->D, st)) != cudaSuccess) return e;
         continue;
       }
       const int total = nct * nit;
       const int grid = std::min(total, h->num_sms);
-      if (ts) acq_i8_gemm_kernel<1, true><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dKe, sBk, nct, nit, nblk, CH, h->dWg, mapsK);
-      else acq_i8_gemm_kernel<1, false><<<grid, A8_THREADS, A8_SMEM, h->stream>>>(h->dKe, sBk, nct, nit, nblk, CH, h->dWg, mapsK);
+      gemm_event(h, st);
+      if (ts) acq_i8_gemm_kernel<1, true><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dKe, sBk, nct, nit, nblk, CH, dWg, mapsK);
+      else acq_i8_gemm_kernel<1, false><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dKe, sBk, nct, nit, nblk, CH, dWg, mapsK);
+      gemm_event(h, st);
       h->launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       GradArgs g;
-      g.Z = h->dZ; g.alpha = h->dalpha; g.inv_ell = h->dinv_ell; g.Xs = l.dXs; g.WgT = h->dWg; g.amu = dAmu; g.as2 = dAs2; g.grad = l.dgrad;
-      g.M = M; g.c0 = c0; g.CH = CH; g.N = (int)h->N; g.D = h->D; g.nblk = nblk; g.sf2 = sf2;
+      g.Z = h->dZ; g.alpha = h->dalpha; g.inv_ell = h->dinv_ell; g.Xs = l.dXs; g.WgT = dWg; g.G = dWg + (size_t)CH * (size_t)Np;
+      g.amu = dAmu; g.as2 = dAs2; g.part = dWg + 2 * (size_t)CH * (size_t)Np; g.grad = l.dgrad;
+      g.M = M; g.c0 = c0; g.CH = CH; g.N = (int)h->N; g.D = h->D; g.nblk = nblk;
       const int nb = (int)((mc + 31) / 32);
-      switch (h->fam) {
-        case FAM_SE: e = launch_grad<FAM_SE>(h, g, nb); break;
-        case FAM_MAT12: e = launch_grad<FAM_MAT12>(h, g, nb); break;
-        case FAM_MAT32: e = launch_grad<FAM_MAT32>(h, g, nb); break;
-        default: e = launch_grad<FAM_MAT52>(h, g, nb); break;
-      }
-      if (e != cudaSuccess) return e;
+      g.nsplit = std::max(1, std::min(std::min(nblk, 16), (3 * h->num_sms + nb - 1) / nb));
+      if ((e = launch_grad(h, st, g, nb, mc)) != cudaSuccess) return e;
     }
+  }
+  if (two) {                                                  // join: the handle's stream continues behind lane 1
+    if ((e = cudaEventRecord(h->acq_ev[1], h->stream2)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(h->stream, h->acq_ev[1], 0)) != cudaSuccess) return e;
   }
   if (l.dbest && l.acq_kind >= 0) {
     argmax_blocks_kernel<<<1, 256, 0, h->stream>>>(h->dcta_best2, (int)blk0, l.dbest);

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <limits>
 #include <new>
+#include <thread>
 #include "common.cuh"
 #include "handle.h"
 
@@ -198,6 +199,27 @@ int32_t check_acq(b200bo_handle_t h, int32_t kind, int32_t n_params, bool grad) 
   return B200BO_OK;
 }
 
+// every replica of a multi handle: the parent first
+std::vector<b200bo_handle_s*> all_replicas(b200bo_handle_s* h) {
+  std::vector<b200bo_handle_s*> v{h};
+  v.insert(v.end(), h->replicas.begin(), h->replicas.end());
+  return v;
+}
+
+// run f(replica, rank) on every replica, the children on their own host threads (the entries block on their streams)
+template <class F>
+int32_t on_replicas(b200bo_handle_s* h, F f) {
+  const std::vector<b200bo_handle_s*> reps = all_replicas(h);
+  std::vector<int32_t> rc(reps.size(), B200BO_OK);
+  std::vector<std::thread> th;
+  for (size_t r = 1; r < reps.size(); ++r) th.emplace_back([&, r] { rc[r] = f(reps[r], (int)r); });
+  rc[0] = f(reps[0], 0);
+  for (auto& t : th) t.join();
+  for (size_t r = 0; r < reps.size(); ++r)
+    if (rc[r] != B200BO_OK) { if (r > 0) h->err = "replica " + std::to_string(r) + ": " + reps[r]->err; return rc[r]; }
+  return B200BO_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -253,8 +275,12 @@ B200BO_API int32_t b200bo_create(b200bo_handle_t* out, int32_t device, int32_t D
 
 B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
   if (!h) return B200BO_OK;
+  for (auto* r : h->replicas) b200bo_destroy(r);
+  h->replicas.clear();
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  nccl_destroy(h);
+  cudaFree(h->drec); h->drec = nullptr;
   free_device(h);
   if (h->dio) cudaFree(h->dio);
   if (h->dlbub) cudaFree(h->dlbub);
@@ -262,9 +288,71 @@ B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
   for (auto& e : h->syrk_ev) cudaEventDestroy(e);
   for (auto& e : h->la_ev) cudaEventDestroy(e);
   for (auto& e : h->fw_ev) cudaEventDestroy(e);
+  for (auto& e : h->acq_ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->gemm_ev) cudaEventDestroy(e);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_create_multi(b200bo_handle_t* out, int32_t n_gpus, const int32_t* devices, int32_t D, int64_t capacity,
+                                       int32_t kernel_kind, int32_t mean_kind) {
+  if (!out) return fail(nullptr, B200BO_ERR_ARG, "null handle pointer");
+  *out = nullptr;
+  if (n_gpus < 1 || n_gpus > 64) return fail(nullptr, B200BO_ERR_ARG, "n_gpus must be in 1..64");
+  b200bo_handle_t h = nullptr;
+  int32_t rc = b200bo_create(&h, devices ? devices[0] : 0, D, capacity, kernel_kind, mean_kind);
+  if (rc != B200BO_OK) return rc;
+  for (int r = 1; r < n_gpus; ++r) {
+    b200bo_handle_t c = nullptr;
+    rc = b200bo_create(&c, devices ? devices[r] : r, D, capacity, kernel_kind, mean_kind);
+    if (rc != B200BO_OK) { b200bo_destroy(h); return rc; }
+    c->is_replica = true;
+    h->replicas.push_back(c);
+  }
+  if (n_gpus > 1) {
+    std::string err;
+    if (nccl_init_all(all_replicas(h), &err) != 0) { b200bo_destroy(h); return fail(nullptr, B200BO_ERR_NCCL, err); }
+    for (auto* r : all_replicas(h)) {
+      cudaSetDevice(r->device);
+      if (comm_buffers(r, n_gpus) != cudaSuccess) { b200bo_destroy(h); return fail(nullptr, B200BO_ERR_CUDA, "exchange buffers"); }
+    }
+    cudaSetDevice(h->device);
+  }
+  *out = h;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_num_gpus(b200bo_handle_t h, int32_t* n) {
+  if (!h || !n) return fail(h, B200BO_ERR_ARG, "null argument");
+  *n = h->replicas.empty() ? h->comm_world : 1 + (int32_t)h->replicas.size();
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_comm_unique_id(uint8_t* id128) {
+  if (!id128) return fail(nullptr, B200BO_ERR_ARG, "null argument");
+  std::string err;
+  if (nccl_unique_id(id128, &err) != 0) return fail(nullptr, B200BO_ERR_NCCL, err);
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_comm_init_rank(b200bo_handle_t h, int32_t world, int32_t rank, const uint8_t* id128) {
+  if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(h, B200BO_ERR_ARG, "bad arguments to comm_init_rank");
+  if (!h->replicas.empty()) return fail(h, B200BO_ERR_STATE, "a multi handle already owns its communicators");
+  if (h->comm) return fail(h, B200BO_ERR_STATE, "a communicator is already attached");
+  cudaSetDevice(h->device);
+  std::string err;
+  if (nccl_init_rank(h, world, rank, id128, &err) != 0) return fail(h, B200BO_ERR_NCCL, err);
+  CU(comm_buffers(h, world));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_comm_destroy(b200bo_handle_t h) {
+  if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  nccl_destroy(h);
   return B200BO_OK;
 }
 
@@ -291,6 +379,7 @@ B200BO_API int32_t b200bo_num_params(b200bo_handle_t h, int32_t* P) {
 
 B200BO_API int32_t b200bo_set_params(b200bo_handle_t h, const double* th, int32_t P) {
   if (!h || !th) return fail(h, B200BO_ERR_ARG, "null argument");
+  for (auto* r : h->replicas) { const int32_t rc = b200bo_set_params(r, th, P); if (rc) return fail(h, rc, r->err); }
   if (P != num_params(h)) return fail(h, B200BO_ERR_ARG, "parameter vector has the wrong length");
   for (int i = 0; i < P; ++i) if (!isfinite(th[i])) return fail(h, B200BO_ERR_ARG, "non-finite hyper-parameter");
   int i = 0;
@@ -316,6 +405,18 @@ B200BO_API int32_t b200bo_get_params(b200bo_handle_t h, double* th, int32_t P) {
 
 B200BO_API int32_t b200bo_fit(b200bo_handle_t h, const double* X, const double* y, int64_t N) {
   if (!h || N < 0 || (N > 0 && (!X || !y))) return fail(h, B200BO_ERR_ARG, "bad arguments to fit");
+  if (!h->replicas.empty()) {     // every replica factors the same data: identical kernels on identical inputs, identical bits
+    std::vector<b200bo_handle_s*> kids;
+    kids.swap(h->replicas);
+    std::vector<int32_t> rc(kids.size() + 1, B200BO_OK);
+    std::vector<std::thread> th;
+    for (size_t r = 0; r < kids.size(); ++r) th.emplace_back([&, r] { rc[r + 1] = b200bo_fit(kids[r], X, y, N); });
+    rc[0] = b200bo_fit(h, X, y, N);
+    for (auto& t : th) t.join();
+    h->replicas.swap(kids);
+    for (size_t r = 0; r < rc.size(); ++r) if (rc[r]) return r ? fail(h, rc[r], h->replicas[r - 1]->err) : rc[r];
+    return B200BO_OK;
+  }
   cudaSetDevice(h->device);
   h->hX.assign(X, X + N * h->D);
   h->hy.assign(y, y + N);
@@ -350,6 +451,18 @@ static int32_t append_elastic(b200bo_handle_t h, const double* Xn, const double*
 B200BO_API int32_t b200bo_append(b200bo_handle_t h, const double* Xn, const double* yn, int64_t m) {
   if (!h || m < 0 || (m > 0 && (!Xn || !yn))) return fail(h, B200BO_ERR_ARG, "bad arguments to append");
   if (m == 0) return B200BO_OK;
+  if (!h->replicas.empty()) {
+    std::vector<b200bo_handle_s*> kids;
+    kids.swap(h->replicas);
+    std::vector<int32_t> rc(kids.size() + 1, B200BO_OK);
+    std::vector<std::thread> th;
+    for (size_t r = 0; r < kids.size(); ++r) th.emplace_back([&, r] { rc[r + 1] = b200bo_append(kids[r], Xn, yn, m); });
+    rc[0] = b200bo_append(h, Xn, yn, m);
+    for (auto& t : th) t.join();
+    h->replicas.swap(kids);
+    for (size_t r = 0; r < rc.size(); ++r) if (rc[r]) return r ? fail(h, rc[r], h->replicas[r - 1]->err) : rc[r];
+    return B200BO_OK;
+  }
   cudaSetDevice(h->device);
   const int64_t D = h->D, N0 = (int64_t)h->hy.size();
   // Elastic path (EXT ElasticPDMats append!): a valid factor, room in the buffers, a handful of new points.
@@ -383,8 +496,7 @@ B200BO_API int32_t b200bo_append(b200bo_handle_t h, const double* Xn, const doub
 
 B200BO_API int32_t b200bo_refit(b200bo_handle_t h) {
   if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
-  cudaSetDevice(h->device);
-  return refit(h);
+  return on_replicas(h, [](b200bo_handle_s* r, int) { cudaSetDevice(r->device); return refit(r); });
 }
 
 B200BO_API int32_t b200bo_dims(b200bo_handle_t h, int32_t* D, int64_t* N) {
@@ -482,8 +594,10 @@ B200BO_API int32_t b200bo_kmat(b200bo_handle_t h, double* K) {
   return B200BO_OK;
 }
 
-B200BO_API int32_t b200bo_acquire_dev(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* dXs, int64_t M, uint64_t seed,
-                           int64_t idx_offset, double* dvalues, double* dgrad, double* dmu, double* dvar, b200bo_best_t* dbest) {
+// enqueue the acquisition step; with a communicator attached the local best is packed into this rank's exchange record and, when
+// `exchange` is set (one process per GPU), gathered from all ranks and merged: *dbest then holds the GLOBAL best on every rank
+static int32_t acquire_dev_impl(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* dXs, int64_t M, uint64_t seed,
+                                int64_t idx_offset, double* dvalues, double* dgrad, double* dmu, double* dvar, b200bo_best_t* dbest, bool exchange) {
   if (!h || M < 0 || (M > 0 && !dXs)) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire");
   int32_t rc = check_acq(h, kind, np, dgrad != nullptr);
   if (rc) return rc;
@@ -501,8 +615,25 @@ B200BO_API int32_t b200bo_acquire_dev(b200bo_handle_t h, int32_t kind, const dou
     CU(cudaStreamSynchronize(h->stream));
   }
   CU(launch_acquire(h, l));
+  if (h->comm && dbest) {
+    CU(comm_buffers(h, h->comm_world));
+    CU(launch_pack_best(h, dbest, dXs, idx_offset));
+    if (exchange) {
+      std::string err;
+      if (nccl_allgather_records(h, &err) != 0) return fail(h, B200BO_ERR_NCCL, err);
+      double* merged = h->drec + (size_t)B200BO_REC_DOUBLES * (size_t)(1 + h->comm_world);
+      CU(launch_merge_best(h, h->comm_world, reinterpret_cast<b200bo_best_t*>(merged), merged + 2));
+      CU(cudaMemcpyAsync(dbest, merged, sizeof(b200bo_best_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+  }
   CU(cudaEventRecord(h->ev[5], h->stream));
   return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_acquire_dev(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* dXs, int64_t M, uint64_t seed,
+                           int64_t idx_offset, double* dvalues, double* dgrad, double* dmu, double* dvar, b200bo_best_t* dbest) {
+  const bool exchange = h && h->comm && h->replicas.empty() && !h->is_replica;
+  return acquire_dev_impl(h, kind, p, np, dXs, M, seed, idx_offset, dvalues, dgrad, dmu, dvar, dbest, exchange);
 }
 
 B200BO_API int32_t b200bo_predict_dev(b200bo_handle_t h, const double* dXs, int64_t M, double* dmu, double* dvar) {
@@ -518,16 +649,15 @@ B200BO_API int32_t b200bo_predict_dev(b200bo_handle_t h, const double* dXs, int6
   return B200BO_OK;
 }
 
-B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* Xs, int64_t M, uint64_t seed,
-                       int64_t idx_offset, double* values, double* grad, double* mu, double* var, b200bo_best_t* best, double* best_x) {
-  if (!h || M < 0 || (M > 0 && !Xs)) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire");
-  int32_t rc = check_acq(h, kind, np, grad != nullptr);
-  if (rc) return rc;
+// host-pointer acquisition on ONE device: stage the candidates, enqueue (no synchronisation); outputs are copied back asynchronously
+static int32_t acquire_host_enqueue(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* Xs, int64_t M, uint64_t seed,
+                                    int64_t idx_offset, double* values, double* grad, double* mu, double* var, bool exchange,
+                                    b200bo_best_t** dbest_out) {
   cudaSetDevice(h->device);
   const int64_t D = h->D;
   // staging layout: Xs [M*D] | values [M] | mu [M] | var [M] | grad [M*D] | best
   const int64_t nd = M * D + 3 * M + (grad ? M * D : 0) + 2;
-  rc = ensure_io(h, sizeof(double) * nd);
+  int32_t rc = ensure_io(h, sizeof(double) * nd);
   if (rc) return rc;
   double* dXs = h->dio;
   double* dval = dXs + M * D;
@@ -536,7 +666,7 @@ B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t kind, const double*
   double* dgrad = grad ? dvar + M : nullptr;
   b200bo_best_t* dbest = reinterpret_cast<b200bo_best_t*>(dvar + M + (grad ? M * D : 0));
   if (M > 0) CU(cudaMemcpyAsync(dXs, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, h->stream));
-  rc = b200bo_acquire_dev(h, kind, p, np, dXs, M, seed, idx_offset, dval, dgrad, mu ? dmu : nullptr, var ? dvar : nullptr, dbest);
+  rc = acquire_dev_impl(h, kind, p, np, dXs, M, seed, idx_offset, dval, dgrad, mu ? dmu : nullptr, var ? dvar : nullptr, dbest, exchange);
   if (rc) return rc;
   if (M > 0) {
     if (values) CU(cudaMemcpyAsync(values, dval, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
@@ -544,13 +674,71 @@ B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t kind, const double*
     if (var) CU(cudaMemcpyAsync(var, dvar, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
     if (grad) CU(cudaMemcpyAsync(grad, dgrad, sizeof(double) * M * D, cudaMemcpyDeviceToHost, h->stream));
   }
+  *dbest_out = dbest;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* Xs, int64_t M, uint64_t seed,
+                       int64_t idx_offset, double* values, double* grad, double* mu, double* var, b200bo_best_t* best, double* best_x) {
+  if (!h || M < 0 || (M > 0 && !Xs)) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire");
+  int32_t rc = check_acq(h, kind, np, grad != nullptr);
+  if (rc) return rc;
+  const int64_t D = h->D;
   b200bo_best_t hb = {-INFINITY, -1};
-  CU(cudaMemcpyAsync(&hb, dbest, sizeof(hb), cudaMemcpyDeviceToHost, h->stream));
+  if (!h->replicas.empty()) {
+    // ---- one process, several GPUs: contiguous column blocks, one host thread per replica, ONE grouped all-gather, merge on device 0 ----
+    const std::vector<b200bo_handle_s*> reps = all_replicas(h);
+    const int R = (int)reps.size();
+    std::vector<b200bo_best_t*> dbest(R, nullptr);
+    rc = on_replicas(h, [&](b200bo_handle_s* r, int k) {
+      int64_t lo, hi; shard_bounds(M, R, k, &lo, &hi);
+      return acquire_host_enqueue(r, kind, p, np, Xs + lo * D, hi - lo, seed, idx_offset + lo, values ? values + lo : nullptr, grad ? grad + lo * D : nullptr,
+                                  mu ? mu + lo : nullptr, var ? var + lo : nullptr, false, &dbest[k]);
+    });
+    if (rc) return rc;
+    std::string err;
+    if (nccl_allgather_group(reps, &err) != 0) return fail(h, B200BO_ERR_NCCL, err);
+    cudaSetDevice(h->device);
+    double* merged = h->drec + (size_t)B200BO_REC_DOUBLES * (size_t)(1 + R);
+    CU(launch_merge_best(h, R, reinterpret_cast<b200bo_best_t*>(merged), merged + 2));
+    double hm[B200BO_REC_DOUBLES];
+    CU(cudaMemcpyAsync(hm, merged, sizeof(double) * (2 + D), cudaMemcpyDeviceToHost, h->stream));
+    for (auto* r : reps) { cudaSetDevice(r->device); CU(cudaStreamSynchronize(r->stream)); }
+    cudaSetDevice(h->device);
+    cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
+    memcpy(&hb, hm, sizeof(hb));
+    if (best) *best = hb;
+    if (best_x && hb.index >= 0) memcpy(best_x, hm + 2, sizeof(double) * D);
+    return B200BO_OK;
+  }
+  const bool exchange = h->comm && !h->is_replica;
+  b200bo_best_t* dbest = nullptr;
+  rc = acquire_host_enqueue(h, kind, p, np, Xs, M, seed, idx_offset, values, grad, mu, var, exchange, &dbest);
+  if (rc) return rc;
+  double hm[B200BO_REC_DOUBLES];
+  if (exchange) {     // the global best and ITS point (the winner may live on another rank)
+    CU(cudaMemcpyAsync(hm, h->drec + (size_t)B200BO_REC_DOUBLES * (size_t)(1 + h->comm_world), sizeof(double) * (2 + D), cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    CU(cudaMemcpyAsync(&hb, dbest, sizeof(hb), cudaMemcpyDeviceToHost, h->stream));
+  }
   CU(cudaStreamSynchronize(h->stream));
   cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
+  if (exchange) {
+    memcpy(&hb, hm, sizeof(hb));
+    if (best_x && hb.index >= 0) memcpy(best_x, hm + 2, sizeof(double) * D);
+  } else if (best_x && hb.index >= 0) {
+    memcpy(best_x, Xs + (hb.index - idx_offset) * D, sizeof(double) * D);
+  }
   if (best) *best = hb;
-  if (best_x && hb.index >= 0) memcpy(best_x, Xs + (hb.index - idx_offset) * D, sizeof(double) * D);
   return B200BO_OK;
+}
+
+// host-side merge of per-replica bests (the sharded search helpers): largest value, then lowest global index
+static void merge_host(b200bo_best_t& acc, double* acc_x, const b200bo_best_t& b, const double* bx, int D) {
+  if (b.index >= 0 && b.value == b.value && (acc.index < 0 || b.value > acc.value || (b.value == acc.value && b.index < acc.index))) {
+    acc = b;
+    if (acc_x && bx) memcpy(acc_x, bx, sizeof(double) * D);
+  }
 }
 
 static int32_t upload_bounds(b200bo_handle_t h, const double* lb, const double* ub) {
@@ -586,6 +774,25 @@ B200BO_API int32_t b200bo_acquire_lhs(b200bo_handle_t h, int32_t kind, const dou
   if (!h || n_total < 0 || offset < 0 || n_local < 0 || offset + n_local > n_total) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire_lhs");
   int32_t rc = check_acq(h, kind, np, false);
   if (rc) return rc;
+  if (!h->replicas.empty()) {     // every replica generates and scores its own block of the ONE global design
+    const int R = 1 + (int)h->replicas.size();
+    std::vector<b200bo_best_t> bs(R, b200bo_best_t{-INFINITY, -1});
+    std::vector<double> bx((size_t)R * h->D, 0.0);
+    rc = on_replicas(h, [&](b200bo_handle_s* r, int k) {
+      int64_t lo, hi; shard_bounds(n_local, R, k, &lo, &hi);
+      std::vector<b200bo_handle_s*> none;
+      none.swap(r->replicas);
+      const int32_t e = b200bo_acquire_lhs(r, kind, p, np, lb, ub, n_total, offset + lo, hi - lo, lhs_seed, ts_seed, values ? values + lo : nullptr, &bs[k],
+                                           bx.data() + (size_t)k * r->D);
+      none.swap(r->replicas);
+      return e;
+    });
+    if (rc) return rc;
+    b200bo_best_t acc = {-INFINITY, -1};
+    for (int k = 0; k < R; ++k) merge_host(acc, best_x, bs[k], bx.data() + (size_t)k * h->D, h->D);
+    if (best) *best = acc;
+    return B200BO_OK;
+  }
   cudaSetDevice(h->device);
   rc = upload_bounds(h, lb, ub);
   if (rc) return rc;
@@ -617,6 +824,25 @@ B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t kind, const 
   if (!h || M < 0 || (M > 0 && !Xs) || steps < 0 || !(step0 > 0.0)) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire_ascent");
   int32_t rc = check_acq(h, kind, np, true);
   if (rc) return rc;
+  if (!h->replicas.empty()) {
+    const int R = 1 + (int)h->replicas.size();
+    std::vector<b200bo_best_t> bs(R, b200bo_best_t{-INFINITY, -1});
+    std::vector<double> bx((size_t)R * h->D, 0.0);
+    rc = on_replicas(h, [&](b200bo_handle_s* r, int k) {
+      int64_t lo, hi; shard_bounds(M, R, k, &lo, &hi);
+      std::vector<b200bo_handle_s*> none;
+      none.swap(r->replicas);
+      const int32_t e = b200bo_acquire_ascent(r, kind, p, np, Xs + lo * r->D, hi - lo, lb, ub, steps, step0, idx_offset + lo, Xout ? Xout + lo * r->D : nullptr,
+                                              values ? values + lo : nullptr, &bs[k], bx.data() + (size_t)k * r->D);
+      none.swap(r->replicas);
+      return e;
+    });
+    if (rc) return rc;
+    b200bo_best_t acc = {-INFINITY, -1};
+    for (int k = 0; k < R; ++k) merge_host(acc, best_x, bs[k], bx.data() + (size_t)k * h->D, h->D);
+    if (best) *best = acc;
+    return B200BO_OK;
+  }
   cudaSetDevice(h->device);
   rc = upload_bounds(h, lb, ub);
   if (rc) return rc;
@@ -653,6 +879,17 @@ B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t kind, const 
 
 B200BO_API int32_t b200bo_predict(b200bo_handle_t h, const double* Xs, int64_t M, double* mu, double* var) {
   if (!h || M < 0 || (M > 0 && (!Xs || !mu || !var))) return fail(h, B200BO_ERR_ARG, "bad arguments to predict");
+  if (!h->replicas.empty()) {
+    const int R = 1 + (int)h->replicas.size();
+    return on_replicas(h, [&](b200bo_handle_s* r, int k) {
+      int64_t lo, hi; shard_bounds(M, R, k, &lo, &hi);
+      std::vector<b200bo_handle_s*> none;
+      none.swap(r->replicas);
+      const int32_t e = b200bo_predict(r, Xs + lo * r->D, hi - lo, mu + lo, var + lo);
+      none.swap(r->replicas);
+      return e;
+    });
+  }
   cudaSetDevice(h->device);
   const int64_t D = h->D;
   int32_t rc = ensure_io(h, sizeof(double) * (M * D + 2 * M + 2));
@@ -680,6 +917,17 @@ B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int3
   const int Pexp = (m_noise ? 1 : 0) + (m_mean ? 1 : 0) + (m_kern ? nl + 1 : 0);
   if (P != Pexp) return fail(h, B200BO_ERR_ARG, "Theta has the wrong number of rows for this mask");
   if (h->N == 0) return fail(h, B200BO_ERR_STATE, "mll needs observations");
+  if (!h->replicas.empty()) {     // the settings shard over the replicas in contiguous blocks
+    const int R = 1 + (int)h->replicas.size();
+    return on_replicas(h, [&](b200bo_handle_s* r, int k) {
+      int64_t lo, hi; shard_bounds(S, R, k, &lo, &hi);
+      std::vector<b200bo_handle_s*> none;
+      none.swap(r->replicas);
+      const int32_t e = hi > lo ? b200bo_mll_sweep(r, Theta + lo * P, P, (int32_t)(hi - lo), mask, mll + lo, dmll ? dmll + lo * P : nullptr) : B200BO_OK;
+      none.swap(r->replicas);
+      return e;
+    });
+  }
   cudaSetDevice(h->device);
   const Hyper saved = h->hp;
   int32_t rc = B200BO_OK;
@@ -722,6 +970,13 @@ B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int3
 
 B200BO_API int32_t b200bo_last_timing_ms(b200bo_handle_t h, int32_t which, float* ms) {
   if (!h || !ms || which < 0 || which >= B200BO_T_COUNT) return fail(h, B200BO_ERR_ARG, "bad arguments to last_timing_ms");
+  if (which == B200BO_T_ACQ_GEMM) {
+    cudaSetDevice(h->device);
+    float sum = 0.f;
+    if (h->gemm_ev_used > 0 && cudaEventSynchronize(h->gemm_ev[h->gemm_ev_used - 1]) == cudaSuccess)
+      for (int i = 0; i + 1 < h->gemm_ev_used; i += 2) { float t = 0.f; cudaEventElapsedTime(&t, h->gemm_ev[i], h->gemm_ev[i + 1]); sum += t; }
+    h->timing[which] = sum;
+  }
   if (which == B200BO_T_ACQ) {   // the _dev entries do not synchronise; resolve the event pair on demand
     cudaSetDevice(h->device);
     if (cudaEventSynchronize(h->ev[5]) == cudaSuccess) cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
@@ -740,12 +995,32 @@ B200BO_API int32_t b200bo_fp64_peak_tflops(b200bo_handle_t h, double* tflops) {
 B200BO_API int32_t b200bo_set_syrk_engine(b200bo_handle_t h, int32_t engine) {
   if (!h || engine < 0 || engine > 2) return fail(h, B200BO_ERR_ARG, "engine must be 0 (DMMA), 1 (tcgen05, 128 x 64 tiles) or 2 (tcgen05, 128 x 128 tiles, two passes)");
   h->syrk_engine = engine;
+  for (auto* r : h->replicas) r->syrk_engine = engine;
   return B200BO_OK;
 }
 
 B200BO_API int32_t b200bo_set_acq_engine(b200bo_handle_t h, int32_t engine) {
   if (!h || engine < 0 || engine > 1) return fail(h, B200BO_ERR_ARG, "engine must be 0 (DMMA blocked solve) or 1 (tcgen05 int8-slice product)");
   h->acq_engine = engine;
+  for (auto* r : h->replicas) r->acq_engine = engine;
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_i8_peak_tops(b200bo_handle_t h, double* tops) {
+  if (!h || !tops) return fail(h, B200BO_ERR_ARG, "null argument");
+  cudaSetDevice(h->device);
+  CU(launch_i8_peak(h, tops));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_set_knob(b200bo_handle_t h, const char* name, int64_t value) {
+  if (!h || !name) return fail(h, B200BO_ERR_ARG, "null argument");
+  const std::string k(name);
+  if (k == "acq_lanes") { if (value < 1 || value > 2) return fail(h, B200BO_ERR_ARG, "acq_lanes must be 1 or 2"); h->acq_lanes = (int)value; }
+  else if (k == "acq_chunk_mb") { if (value < 0) return fail(h, B200BO_ERR_ARG, "acq_chunk_mb must be >= 0"); h->acq_chunk_mb = value; }
+  else if (k == "acq_gemm_timing") h->acq_time_gemm = value != 0;
+  else return fail(h, B200BO_ERR_ARG, "unknown knob: " + k);
+  for (auto* r : h->replicas) b200bo_set_knob(r, name, value);
   return B200BO_OK;
 }
 

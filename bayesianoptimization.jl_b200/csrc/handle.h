@@ -18,6 +18,8 @@ struct Hyper {               // current hyper-parameters (EXT GaussianProcesses.
 
 }  // namespace b200bo
 
+#define B200BO_REC_DOUBLES 34   // exchange record of one rank: best value, global index (int64 bits), the winning point (D <= 32)
+
 struct b200bo_handle_s {
   int device = 0, D = 0, kernel_kind = 0, mean_kind = 0, fam = 0;
   bool iso = false;
@@ -56,7 +58,13 @@ struct b200bo_handle_s {
   b200bo_best_t* dcta_best2 = nullptr;
   size_t bs_bytes = 0, part_bytes = 0, wg_bytes = 0;
   int64_t bs_np = 0, bs_ch = 0, nbest2 = 0;
-  CUtensorMap tmWsB, tmKsB, tmBsA;
+  CUtensorMap tmWsB, tmKsB, tmBsA[2];
+  cudaEvent_t acq_ev[2] = {nullptr, nullptr};   // fork / join of the two chunk lanes
+  int acq_lanes = 2;         // chunk lanes of the tcgen05 acquisition path (1: everything on the handle's stream)
+  int64_t acq_chunk_mb = 0;  // 0: default L2 budget per chunk
+  bool acq_time_gemm = false;   // time every slice-product launch with CUDA events (forces one lane): B200BO_T_ACQ_GEMM
+  std::vector<cudaEvent_t> gemm_ev;
+  int gemm_ev_used = 0;
   int acq_engine = -1;       // -1: default (tcgen05 unless B200BO_ACQ_I8=0), 0: DMMA solve (acq.cu), 1: tcgen05 int8-slice GEMM (acq_i8.cu)
   int64_t nslots = 0;
   double* dscal = nullptr;   // small scalar outputs (logdet, r'alpha, ...)
@@ -78,6 +86,14 @@ struct b200bo_handle_s {
   std::vector<cudaEvent_t> syrk_ev;   // start/stop pairs around every trailing-update launch of the last factorisation
   int syrk_ev_used = 0;
   int syrk_engine = -1;      // -1: default (tcgen05 unless B200BO_SYRK_I8=0), 0: DMMA, 1: tcgen05
+  // multi-GPU (multi.cu): a communicator over the ranks of this model (one process per GPU: b200bo_comm_init_rank; one process for all
+  // GPUs: b200bo_create_multi, whose parent handle owns one child replica per further device)
+  void* comm = nullptr;      // ncclComm_t
+  int comm_world = 1, comm_rank = 0;
+  double* drec = nullptr;    // [own record | gathered records | merged best + point]
+  int rec_world = 0;
+  std::vector<b200bo_handle_s*> replicas;   // children of a multi handle (the parent itself is rank 0)
+  bool is_replica = false;   // a child of a multi handle
   bool fitted = false;
   bool need_upload = false;  // device copies of X / y are stale (a failed elastic append): re-upload before the next refactor
   int acq_ready = 0;         // bit 0: W = L^-1 sliced for the tcgen05 acquisition path, bit 1: Sigma^-1 sliced (acq_i8.cu)
@@ -129,8 +145,21 @@ size_t acq_smem_bytes(int D);
 cudaError_t launch_lhs(b200bo_handle_s* h, double* dXs, int64_t n_total, int64_t offset, int64_t n_local, unsigned long long seed,
                        const double* d_lbub);
 cudaError_t launch_ascent(b200bo_handle_s* h, const AcqLaunch& base, double* dX, double* dwork, const double* d_lbub, int steps, double s0);
+// multi.cu
+const char* nccl_load_error();
+cudaError_t comm_buffers(b200bo_handle_s* h, int world);
+cudaError_t launch_pack_best(b200bo_handle_s* h, const b200bo_best_t* dbest, const double* dXs, int64_t idx_offset);
+cudaError_t launch_merge_best(b200bo_handle_s* h, int world, b200bo_best_t* dout, double* dout_x);
+int nccl_allgather_records(b200bo_handle_s* h, std::string* err);
+int nccl_allgather_group(const std::vector<b200bo_handle_s*>& reps, std::string* err);
+int nccl_unique_id(uint8_t* id128, std::string* err);
+int nccl_init_rank(b200bo_handle_s* h, int world, int rank, const uint8_t* id128, std::string* err);
+int nccl_init_all(const std::vector<b200bo_handle_s*>& reps, std::string* err);
+void nccl_destroy(b200bo_handle_s* h);
+void shard_bounds(int64_t total, int R, int r, int64_t* lo, int64_t* hi);
 // peak.cu
 cudaError_t launch_dmma_peak(b200bo_handle_s* h, double* tflops);
+cudaError_t launch_i8_peak(b200bo_handle_s* h, double* tops);
 // mll.cu
 cudaError_t launch_kinv(b200bo_handle_s* h);       // kinv.cu: Sigma^-1 into h->dKi by recursive block inversion + W^T W
 cudaError_t launch_linv(b200bo_handle_s* h);       //   first half: W = L^-1 into h->dKi (lower blocks), W^T into h->dWT

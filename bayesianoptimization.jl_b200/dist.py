@@ -42,6 +42,26 @@ def allreduce_best(value: float, index: int, device=None):
     return select_best(vals.cpu().numpy(), idxs.cpu().numpy())
 
 
+def comm_attach(model, device=None):
+    """One process per GPU: give the library its own NCCL communicator over the ranks of the default process group (rank 0 draws
+    the ncclUniqueId, torch.distributed carries its 128 bytes).  Afterwards model.acquire() is a collective that returns the global
+    best: the 272 B/rank all-gather and the deterministic merge happen inside libb200bo, on the handle's stream."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return False
+    ws, rank = dist.get_world_size(), dist.get_rank()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(_lib.lib.b200bo_comm_unique_id(buf))
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=device)
+    dist.broadcast(t, src=0)
+    model.comm_init_rank(ws, rank, bytes(t.cpu().numpy().tobytes()))
+    return True
+
+
 def acquire_sharded(model, kind: str, params, Xs: np.ndarray, seed: int = 0, device=None, **kw):
     """Each rank scores its block of the SAME candidate matrix; returns the global (best_value, best_index, best_x)."""
     import torch.distributed as dist

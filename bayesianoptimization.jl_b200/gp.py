@@ -53,7 +53,8 @@ def Mat52Ard(ll, lsigma): return _Kernel("Mat52Ard", ll, lsigma)
 class B200GPE:
     """ElasticGPE-shaped GP whose factor, alpha and data live in B200 HBM."""
 
-    def __init__(self, D: int, mean=None, kernel=None, logNoise: float = -2.0, capacity: int = 3000, device: int = 0):
+    def __init__(self, D: int, mean=None, kernel=None, logNoise: float = -2.0, capacity: int = 3000, device: int = 0, n_gpus=None,
+                 devices=None):
         mean = MeanZero() if mean is None else mean
         kernel = SEArd(np.zeros(D), 0.0) if kernel is None else kernel
         if not kernel.kind.endswith("Iso") and kernel.ll.size != D:
@@ -61,8 +62,14 @@ class B200GPE:
         self.D = int(D)
         self.mean_kind, self.kernel_kind = mean.kind, kernel.kind
         self._h = C.c_void_p()
-        check(lib.b200bo_create(C.byref(self._h), device, self.D, int(capacity), _lib.KERNEL_KINDS[kernel.kind],
-                                _lib.MEAN_KINDS[mean.kind]))
+        if n_gpus is None and devices is None:
+            check(lib.b200bo_create(C.byref(self._h), device, self.D, int(capacity), _lib.KERNEL_KINDS[kernel.kind],
+                                    _lib.MEAN_KINDS[mean.kind]))
+        else:       # ONE process, several GPUs: replicas of the model behind one handle (b200bo_create_multi)
+            devs = list(devices) if devices is not None else list(range(int(n_gpus)))
+            arr = (C.c_int32 * len(devs))(*devs)
+            check(lib.b200bo_create_multi(C.byref(self._h), len(devs), arr, self.D, int(capacity), _lib.KERNEL_KINDS[kernel.kind],
+                                          _lib.MEAN_KINDS[mean.kind]))
         theta = [float(logNoise), *mean.params, *kernel.ll.tolist(), kernel.lsigma]
         self.set_params(np.array(theta, float))
 
@@ -173,6 +180,29 @@ class B200GPE:
     def set_syrk_engine(self, engine: int) -> None:
         """1 = tcgen05 int8-slice trailing updates (default), 0 = DMMA tile GEMM; takes effect at the next fit."""
         check(lib.b200bo_set_syrk_engine(self._h, int(engine)), self._h)
+
+    def i8_peak_tops(self) -> float:
+        v = C.c_double()
+        check(lib.b200bo_i8_peak_tops(self._h, C.byref(v)), self._h)
+        return v.value
+
+    def set_knob(self, name: str, value: int) -> None:
+        check(lib.b200bo_set_knob(self._h, name.encode(), int(value)), self._h)
+
+    @property
+    def num_gpus(self) -> int:
+        n = C.c_int32()
+        check(lib.b200bo_num_gpus(self._h, C.byref(n)), self._h)
+        return n.value
+
+    def comm_init_rank(self, world: int, rank: int, unique_id: bytes) -> None:
+        """one process per GPU: attach an NCCL communicator over the `world` handles that hold replicas of this model; from then on
+        acquire() / b200bo_acquire_dev return the GLOBAL best (collective call)."""
+        assert len(unique_id) == 128
+        check(lib.b200bo_comm_init_rank(self._h, int(world), int(rank), unique_id), self._h)
+
+    def comm_destroy(self) -> None:
+        check(lib.b200bo_comm_destroy(self._h), self._h)
 
     def set_acq_engine(self, engine: int) -> None:
         """1 = acquisition step as an int8-slice GEMM against L^-1 on tcgen05 (default), 0 = blocked DMMA solves (A/B tests)."""

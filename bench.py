@@ -3,15 +3,15 @@
 
 A "step" is one pass of the hot path over one batch of synthetic candidates: b200bo_acquire on M candidate
 columns against a resident N-observation GP factor (k*, both triangular solves, mu, sigma^2, score, arg-max; the
-one-off fit is outside the step).  Default workload = BASELINE.json configs[1] (Hartmann-6, D=6,
-N=2048, Mat52Ard, UCB/Brochu, M=65536 LHS candidates per GPU).
+one-off fit is outside the step).  Default workload = the metric text of BASELINE.json (N=2048, D=8, SEArd, EI,
+M=65536 LHS candidates per GPU); side blocks: configs[1] (cfg2), configs[2] with gradient (cfg3), configs[4] shard (cfg5), configs[3] (MAP sweep).
 
   python bench.py --gpus N --steps K --warmup W        (N>1: launched by torch.distributed.run, one rank per GPU)
   python bench.py --impl reference ...                 (CPU restatement of the reference path on the host cores)
 
 `value`  : device-resident inputs, per-step CUDA-event pairs on the launching stream, max over ranks.
 `e2e`    : the public host-pointer API (pinned host candidates -> H2D -> fused launch -> D2H best -> rank exchange).
-`roofline`: dominant kernel (acq_fused_kernel) in FP64-equivalent TFLOP/s against the self-measured DMMA peak.
+`roofline`: dominant kernel (acq_i8_gemm_kernel, tcgen05 kind::i8) in int8 TOP/s against the self-measured UTCIMMA peak.
 """
 from __future__ import annotations
 
@@ -154,6 +154,147 @@ def run_reference(args, w):
                       "gpu_launches": 0}))
 
 
+def roofline_i8(w, M, gemm_ms, step_ms, peak_i8, peak_fp64, peaks, traffic):
+    """dominant kernel = acq_i8_gemm_kernel (tcgen05.mma kind::i8).  Algorithmic work per candidate (DESIGN.md 4, K6): the value path is
+    W k* over the lower triangle = N^2/2 multiply-adds per slice product x 28 products (p + q <= 6) = 28 N^2 int8 ops (2 per MAC); a
+    gradient launch adds the full product Sigma^-1 k* = 56 N^2."""
+    N = float(w["N"])
+    ops = 28.0 * N * N + (56.0 * N * N if w["grad"] else 0.0)
+    fp64_flops = N * N + (2.0 * N * N if w["grad"] else 0.0)
+    ach = ops * M / (gemm_ms * 1e-3) * 1e-12
+    bf16 = peaks.get("bf16_tflops")
+    return {"kernel": "acq_i8_gemm_kernel (tcgen05.mma.cta_group::1.kind::i8, 128x64x32, TMEM accumulators)", "bound": "tensor",
+            "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8, "traffic": traffic,
+            "ops": "int8 multiply-adds of the 28 error-free slice products, 2 ops each (achieved and peak are int8 TOP/s)",
+            "peak_source": "self-measured tcgen05.mma kind::i8 rate of this GPU (b200bo_i8_peak_tops: back-to-back 128x256x32 MMAs on "
+                           "resident operands, all SMs); MEASURED_PEAKS.json has no int8 figure" +
+                           (f" -- its bf16 burst figure x 2 would be {2 * bf16:.0f}" if bf16 else ""),
+            "algorithmic_int8_ops_per_candidate": ops, "launch_ms_sum_per_step": gemm_ms,
+            "launch_timing": "CUDA-event pairs around every acq_i8_gemm_kernel launch of one step on the launching stream (one chunk lane)",
+            "step_view": {"achieved": ops * M / (step_ms * 1e-3) * 1e-12, "frac": ops * M / (step_ms * 1e-3) * 1e-12 / peak_i8,
+                          "note": "same ops over the WHOLE step (kernel evaluation, scores and arg-max included)"},
+            "fp64_equivalent": {"flops_per_candidate": fp64_flops, "achieved_tflops": fp64_flops * M / (step_ms * 1e-3) * 1e-12,
+                                "dmma_peak_tflops": peak_fp64,
+                                "note": "the FP64 flops the replaced triangular solves would need, over the whole step; the round-1 DMMA kernel "
+                                        "ran at 0.85 of the self-measured DMMA peak"}}
+
+
+def run_gpu_workload(ctx, w, steps, warmup, want_fit_side=True):
+    """one workload on this rank's GPU: device-resident arm, end-to-end arm, slice-product timing pass."""
+    import torch
+    import b200bo
+    from b200bo import _lib
+    dist, dev, stream, world, rank, flush = ctx["dist"], ctx["dev"], ctx["stream"], ctx["world"], ctx["rank"], ctx["flush"]
+    D, N, M = w["D"], w["N"], w["M"]
+    X, y, ll = synth(w)
+    model = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.0), kernel=b200bo.gp._Kernel(w["kernel"], ll, 0.0), logNoise=-2.0, capacity=N,
+                           device=ctx["local_rank"])
+    model.fit(X, y)                                  # one-off fit (identical, replicated on every rank)
+    model.fit(X, y)                                  # second fit: warm timings for the side metrics
+    fit_ms = {k: model.timing_ms(v) for k, v in dict(kmat=_lib.T_KMAT, chol=_lib.T_CHOL, syrk=_lib.T_SYRK, alpha=_lib.T_ALPHA).items()}
+    par = np.array(acq_params(w, y), float)
+    kind = _lib.ACQ_KINDS[w["acq"]]
+    _lib.check(_lib.lib.b200bo_set_stream(model._h, C.c_void_p(stream.cuda_stream)), model._h)
+    if world > 1:
+        from b200bo.dist import comm_attach
+        comm_attach(model, device=dev)               # the library's own communicator: the all-gather + merge run inside libb200bo
+
+    # ---- device-resident arm -----------------------------------------------------------------------------------
+    Xs_host = torch.from_numpy(candidates(w, rank).T.copy()).pin_memory()          # [M][D] == D x M column-major, pinned
+    dXs = Xs_host.to(dev)
+    dbest = torch.zeros(2, dtype=torch.float64, device=dev)                        # b200bo_best_t {f64 value; i64 index}: the GLOBAL best
+    dgrad = torch.empty((M, D), dtype=torch.float64, device=dev) if w["grad"] else None
+    pp = par.ctypes.data_as(C.POINTER(C.c_double)) if par.size else None
+    offset = rank * M
+
+    def step_dev():
+        # fused launch(es) + (N > 1) the ONE exchange step: a 272 B/rank ncclAllGather and the merge, all enqueued by the library
+        _lib.check(_lib.lib.b200bo_acquire_dev(model._h, kind, pp, par.size, C.c_void_p(dXs.data_ptr()), M, 50, offset, None,
+                                               C.c_void_p(dgrad.data_ptr()) if dgrad is not None else None, None, None,
+                                               C.c_void_p(dbest.data_ptr())), model._h)
+
+    for _ in range(warmup):
+        step_dev(); flush.zero_()
+    torch.cuda.synchronize(dev)
+    launches0 = model.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    for e0, e1 in evs:
+        e0.record(stream); step_dev(); e1.record(stream)
+        flush.zero_()                                                              # L2 flush between timed steps
+        torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    launches = (model.launch_count - launches0) // steps
+    t_dev = sum(e0.elapsed_time(e1) for e0, e1 in evs) * 1e-3
+    gb = dbest.cpu().numpy()
+    best_v, best_i = float(gb[0]), int(gb.view(np.int64)[1])
+
+    # ---- slice-product timing pass (roofline numerator): event pairs around every acq_i8_gemm_kernel launch, one chunk lane ----
+    model.set_knob("acq_gemm_timing", 1)
+    gemm_ms = []
+    for _ in range(3):
+        step_dev(); torch.cuda.synchronize(dev)
+        gemm_ms.append(model.timing_ms(_lib.T_ACQ_GEMM))
+        flush.zero_(); torch.cuda.synchronize(dev)
+    model.set_knob("acq_gemm_timing", 0)
+    gemm_ms = float(np.median(gemm_ms))
+
+    # ---- end-to-end arm: public host API, pinned host candidates, H2D + D2H inside the timed region -------------
+    Xs_np = Xs_host.numpy().T                                                      # D x M view of the pinned buffer (F-order)
+    def step_e2e():
+        r = model.acquire(w["acq"], par, Xs_np, seed=50, idx_offset=offset, want_values=False, want_grad=w["grad"])
+        return r["best_value"], r["best_index"]                                    # global on every rank (library-side exchange)
+    for _ in range(warmup):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        bv_e2e, bi_e2e = step_e2e()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+
+    tt = torch.tensor([t_dev, t_e2e, gemm_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, gemm_ms = (float(v) for v in tt.cpu())
+    out = dict(model=model, X=X, y=y, ll=ll, par=par, t_dev=t_dev, t_e2e=t_e2e, gemm_ms=gemm_ms, launches=int(launches), fit_ms=fit_ms,
+               best=(best_v, best_i, float(bv_e2e), int(bi_e2e)))
+    if world > 1:
+        model.comm_destroy()
+    return out
+
+
+def line_for(w, r, steps, world, peaks, traffic_key):
+    """value / e2e / roofline of one measured workload"""
+    model, M, D = r["model"], w["M"], w["D"]
+    total = M * world
+    step_ms = r["t_dev"] / steps * 1e3
+    if "peak_i8" not in peaks:
+        peaks["peak_i8"] = model.i8_peak_tops(); peaks["peak_fp64"] = model.fp64_peak_tflops()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(traffic_key, {}).get("bytes_per_step")
+    except Exception:
+        pass
+    d2h = 16 + 8 * D + (8 * D * M if w["grad"] else 0)
+    return {"value": total * steps / r["t_dev"], "ms_per_step": step_ms,
+            "e2e": {"value": total * steps / r["t_e2e"], "unit": "candidates/s", "h2d_bytes_per_step": int(8 * D * M * world),
+                    "d2h_bytes_per_step": int(d2h * world), "ms_per_step": r["t_e2e"] / steps * 1e3},
+            "gpu_launches": r["launches"],
+            "roofline": roofline_i8(w, M, r["gemm_ms"], step_ms, peaks["peak_i8"], peaks["peak_fp64"], peaks, traffic),
+            "best": {"value": r["best"][0], "index": r["best"][1], "e2e_value": r["best"][2], "e2e_index": r["best"][3]}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,6 +303,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="metric", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the cfg3 / cfg5 side blocks and the N=4096 fit metrics")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
@@ -192,115 +334,31 @@ def main():
             os.close(saved)
     import b200bo
     from b200bo import _lib
-    from b200bo.dist import allreduce_best, select_best
 
-    D, N, M = w["D"], w["N"], w["M"]
-    X, y, ll = synth(w)
-    model = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.0), kernel=b200bo.gp._Kernel(w["kernel"], ll, 0.0), logNoise=-2.0, capacity=N,
-                           device=local_rank)
-    model.fit(X, y)                                  # one-off fit (identical, replicated on every rank)
-    model.fit(X, y)                                  # second fit: warm timings for the side metrics
-    fit_ms = {k: model.timing_ms(v) for k, v in dict(kmat=_lib.T_KMAT, chol=_lib.T_CHOL, syrk=_lib.T_SYRK, alpha=_lib.T_ALPHA).items()}
-    par = np.array(acq_params(w, y), float)
-    kind = _lib.ACQ_KINDS[w["acq"]]
-    stream = torch.cuda.Stream(dev)                 # a real (non-default) stream shared by torch, NCCL ordering and the library
+    stream = torch.cuda.Stream(dev)                 # a real (non-default) stream shared by torch and the library (NCCL included)
     torch.cuda.set_stream(stream)
-    _lib.check(_lib.lib.b200bo_set_stream(model._h, C.c_void_p(stream.cuda_stream)), model._h)
-
-    # ---- device-resident arm -----------------------------------------------------------------------------------
-    Xs_host = torch.from_numpy(candidates(w, rank).T.copy()).pin_memory()          # [M][D] == D x M column-major, pinned
-    dXs = Xs_host.to(dev)
-    dbest = torch.zeros(2, dtype=torch.float64, device=dev)                        # b200bo_best_t {f64 value; i64 index}
-    dgrad = torch.empty((M, D), dtype=torch.float64, device=dev) if w["grad"] else None
-    gathered = torch.zeros((world, 2), dtype=torch.float64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                  # > 126 MB L2
-    pp = par.ctypes.data_as(C.POINTER(C.c_double)) if par.size else None
-    offset = rank * M
-
-    def step_dev():
-        _lib.check(_lib.lib.b200bo_acquire_dev(model._h, kind, pp, par.size, C.c_void_p(dXs.data_ptr()), M, 50, offset, None,
-                                               C.c_void_p(dgrad.data_ptr()) if dgrad is not None else None, None, None,
-                                               C.c_void_p(dbest.data_ptr())), model._h)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), dbest)                  # the ONE exchange step: 16 B per rank
-        else:
-            gathered.copy_(dbest.view(1, 2))
-
+    ctx = dict(dist=dist, dev=dev, stream=stream, world=world, rank=rank, local_rank=local_rank,
+               flush=torch.empty(256 << 20, dtype=torch.uint8, device=dev))        # > 126 MB L2
+    saved_out = None
+    if world > 1:                                   # NCCL banner of the library's own communicator: keep stdout clean
+        sys.stdout.flush(); saved_out = os.dup(1); os.dup2(2, 1)
     clk = ClockSampler(local_rank)
     clk.__enter__()                                  # sampled from the warm-up to the end of the e2e arm (all under load)
-    for _ in range(args.warmup):
-        step_dev(); flush.zero_()
-    torch.cuda.synchronize(dev)
-    launches0 = model.launch_count
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms = []
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    for e0, e1 in evs:
-        e0.record(stream); step_dev(); e1.record(stream)
-        flush.zero_()                                                              # L2 flush between timed steps
-        torch.cuda.synchronize(dev)
-        kern_ms.append(model.timing_ms(_lib.T_ACQ))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    launches = model.launch_count - launches0
-    t_dev = sum(e0.elapsed_time(e1) for e0, e1 in evs) * 1e-3
-    g = gathered.cpu().numpy()
-    best_v, best_i = select_best(g[:, 0], g[:, 1].view(np.int64))
-
-    # ---- end-to-end arm: public host API, pinned host candidates, H2D + D2H inside the timed region -------------
-    Xs_np = Xs_host.numpy().T                                                      # D x M view of the pinned buffer (F-order)
-    def step_e2e():
-        r = model.acquire(w["acq"], par, Xs_np, seed=50, idx_offset=offset, want_values=False, want_grad=False)
-        return allreduce_best(r["best_value"], r["best_index"], device=dev)
-    for _ in range(args.warmup):
-        step_e2e()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        bv_e2e, bi_e2e = step_e2e()
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    t_e2e = e0.elapsed_time(e1) * 1e-3
+    r = run_gpu_workload(ctx, w, args.steps, args.warmup)
     clk.__exit__(None, None, None)
-
-    # ---- max over ranks ------------------------------------------------------------------------------------------
-    tt = torch.tensor([t_dev, t_e2e, float(np.mean(kern_ms)) * 1e-3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e, t_kern = (float(v) for v in tt.cpu())
-    total = M * world
+    if saved_out is not None:
+        sys.stdout.flush(); os.dup2(saved_out, 1); os.close(saved_out)
+    D, N, M = w["D"], w["N"], w["M"]
+    model, fit_ms = r["model"], r["fit_ms"]
     if rank == 0:
-        value = total * args.steps / t_dev
-        flops_per_cand = float(N) ** 2 * (2 if w["grad"] else 1) + N * (3 * D + 25) + (4 * N * D if w["grad"] else 0)
-        bytes_per_cand = 8 * D + 8 + (8 * D if w["grad"] else 0) + 4.0 * N * N / 64                                         # L re-read per 64-wide tile
-        peak_fp64 = model.fp64_peak_tflops()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        ach = flops_per_cand * M / t_kern * 1e-12
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}).get("bytes")
-        except Exception:
-            pass
-        roofline = {"kernel": "acq_fused_kernel", "bound": "tensor", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s",
-                    "frac": ach / peak_fp64, "traffic": traffic,
-                    "peak_source": "self-measured DMMA.8x8x4 FP64 rate (b200bo_fp64_peak_tflops; MEASURED_PEAKS.json has no FP64 figure)",
-                    "algorithmic_flops_per_candidate": flops_per_cand, "launch_ms": t_kern * 1e3,
-                    "hbm_view": {"algorithmic_bytes_per_candidate": bytes_per_cand, "achieved_gbs": bytes_per_cand * M / t_kern * 1e-9,
-                                 "peak_gbs": hbm_peak, "frac": bytes_per_cand * M / t_kern * 1e-9 / hbm_peak,
-                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        ln = line_for(w, r, args.steps, world, peaks, args.workload)
+        peak_fp64 = peaks["peak_fp64"]
         nblk, far_flops = (N + 127) // 128, 0.0          # flops of the K=512 trailing updates timed by T_SYRK (csrc/chol.cu schedule)
         for p0 in range(0, nblk, 4):
             p1, p2 = min(p0 + 4, nblk), min(p0 + 8, nblk)
@@ -317,59 +375,104 @@ def main():
                              "syrk_k512_engine": "tcgen05.mma kind::i8, 7-slice error-free product, TMEM accumulators (csrc/syrk_i8.cu); "
                                                  "timed on the second stream while the next outer panel runs"},
                 "alpha_ms": fit_ms["alpha"]}
-        # the north_star's fit targets are quoted at N=4096, D=8 (SEArd): measure that fit beside the workload's own (outside every
-        # timed region; best of three warm refits, library CUDA-event timers around K1 / the factorisation / the K=512 updates)
-        try:
-            rng4 = np.random.default_rng(4)
-            X4 = rng4.random((8, 4096)); y4 = np.sin(3 * X4.sum(0)) + 0.1 * rng4.standard_normal(4096)
-            m4 = b200bo.B200GPE(8, mean=b200bo.MeanConst(0.0), kernel=b200bo.SEArd(np.full(8, np.log(np.sqrt(8) * 0.25)), 0.0), logNoise=-2.0,
-                                capacity=4096, device=local_rank)
-            t4 = []
-            for _ in range(4):
-                m4.fit(X4, y4)
-                t4.append([m4.timing_ms(v) for v in (_lib.T_KMAT, _lib.T_CHOL, _lib.T_SYRK, _lib.T_ALPHA)])
-            k4, c4, s4, a4 = (min(t[i] for t in t4[1:]) for i in range(4))
-            kb4 = 8.0 * 4096 * 4096 + 8.0 * 4096 * 8
-            far4 = 0.0
-            for p0 in range(0, 32, 4):
-                p1, p2 = min(p0 + 4, 32), min(p0 + 8, 32)
-                if p1 >= 32:
-                    break
-                far4 += sum(max(0, (2 * bi + 2) - 2 * p2) for bi in range(p1, 32)) * 128 * 64 * (p1 - p0) * 128 * 2.0
-            side["fit_n4096_d8"] = {"kmat_ms": k4, "kmat_gbs": kb4 / (k4 * 1e-3) * 1e-9, "kmat_frac_of_hbm": kb4 / (k4 * 1e-3) * 1e-9 / hbm_peak,
-                                    "kmat_algorithmic_bytes": kb4, "cholesky_ms": c4, "syrk_k512_ms": s4,
-                                    "syrk_k512_tflops_fp64": far4 / max(s4, 1e-9) * 1e-9, "alpha_ms": a4, "fit_total_ms": k4 + c4 + a4}
-            del m4
-        except Exception as exc:                                       # a side metric must never take the bench line down
-            side["fit_n4096_d8"] = {"error": str(exc)}
-        out = {"metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic",
-               "config": workload_config(w, world),
-               "e2e": {"value": total * args.steps / t_e2e, "unit": "candidates/s", "h2d_bytes_per_step": int(8 * D * M * world),
-                       "d2h_bytes_per_step": int(16 * world), "ms_per_step": t_e2e / args.steps * 1e3},
-               "gpu_launches": int(launches), "roofline": roofline, "side_metrics": side, "clocks": clk.summary(),
-               "best": {"value": best_v, "index": int(best_i), "e2e_value": bv_e2e, "e2e_index": int(bi_e2e)}}
+        if world == 1 and not args.no_side:
+            # the north_star's fit targets are quoted at N=4096, D=8 (SEArd): measure that fit beside the workload's own (outside every
+            # timed region; best of three warm refits, library CUDA-event timers around K1 / the factorisation / the K=512 updates)
+            try:
+                rng4 = np.random.default_rng(4)
+                X4 = rng4.random((8, 4096)); y4 = np.sin(3 * X4.sum(0)) + 0.1 * rng4.standard_normal(4096)
+                m4 = b200bo.B200GPE(8, mean=b200bo.MeanConst(0.0), kernel=b200bo.SEArd(np.full(8, np.log(np.sqrt(8) * 0.25)), 0.0), logNoise=-2.0,
+                                    capacity=4096, device=local_rank)
+                t4 = []
+                for _ in range(4):
+                    m4.fit(X4, y4)
+                    t4.append([m4.timing_ms(v) for v in (_lib.T_KMAT, _lib.T_CHOL, _lib.T_SYRK, _lib.T_ALPHA)])
+                k4, c4, s4, a4 = (min(t[i] for t in t4[1:]) for i in range(4))
+                kb4 = 8.0 * 4096 * 4096 + 8.0 * 4096 * 8
+                far4 = 0.0
+                for p0 in range(0, 32, 4):
+                    p1, p2 = min(p0 + 4, 32), min(p0 + 8, 32)
+                    if p1 >= 32:
+                        break
+                    far4 += sum(max(0, (2 * bi + 2) - 2 * p2) for bi in range(p1, 32)) * 128 * 64 * (p1 - p0) * 128 * 2.0
+                side["fit_n4096_d8"] = {"kmat_ms": k4, "kmat_gbs": kb4 / (k4 * 1e-3) * 1e-9, "kmat_frac_of_hbm": kb4 / (k4 * 1e-3) * 1e-9 / hbm_peak,
+                                        "kmat_algorithmic_bytes": kb4, "cholesky_ms": c4, "syrk_k512_ms": s4,
+                                        "syrk_k512_tflops_fp64": far4 / max(s4, 1e-9) * 1e-9,
+                                        "syrk_k512_int8_tops": far4 * 28.0 / max(s4, 1e-9) * 1e-9, "int8_peak_tops": peaks["peak_i8"],
+                                        "alpha_ms": a4, "fit_total_ms": k4 + c4 + a4}
+                # cfg4 of BASELINE.json: the MAP sweep (64 settings, mll + gradient) on the same N=4096, D=8 model
+                grid = [(lnz, l) for lnz in np.linspace(-3.0, 0.0, 8) for l in np.linspace(-1.5, 0.5, 8)]
+                Theta = np.stack([np.concatenate([[lnz, 0.0], np.full(8, l), [0.0]]) for lnz, l in grid], axis=1)
+                m4.mll_sweep(Theta[:, :8])
+                t0 = time.perf_counter(); m4.mll_sweep(Theta); t_sw = time.perf_counter() - t0
+                t0 = time.perf_counter(); m4.mll_sweep(Theta, want_grad=False); t_sv = time.perf_counter() - t0
+                side["cfg4_map_sweep"] = {"workload": "BASELINE configs[3]: N=4096, D=8, 64 (logNoise, length-scale) settings, mll + dmll",
+                                          "seconds_with_gradient": t_sw, "seconds_values_only": t_sv, "settings": 64}
+                del m4
+            except Exception as exc:                                   # a side metric must never take the bench line down
+                side["fit_n4096_d8"] = {"error": str(exc)}
+            # the other single-GPU configurations of BASELINE.json, each with its own roofline (3 timed steps)
+            for name in ("cfg3", "cfg5", "cfg2"):
+                if name == args.workload:
+                    continue
+                try:
+                    w2 = WORKLOADS[name]
+                    r2 = run_gpu_workload(ctx, w2, 3, 3)
+                    blk = line_for(w2, r2, 3, 1, peaks, name)
+                    blk["config"] = workload_config(w2, 1)
+                    side["workload_" + name] = blk
+                    del r2
+                except Exception as exc:
+                    side["workload_" + name] = {"error": str(exc)}
+        out = {"metric": METRIC, "value": ln["value"], "unit": "candidates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ln["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": workload_config(w, world), "e2e": ln["e2e"], "gpu_launches": ln["gpu_launches"],
+               "roofline": ln["roofline"], "side_metrics": side, "clocks": clk.summary(), "best": ln["best"]}
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(w, X, y, ll, par)
+            out["cpu_baseline"] = cpu_baseline(w, r["X"], r["y"], r["ll"], r["par"])
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
 def cpu_baseline(w, X, y, ll, par):
-    """the CPU restatement (oracle/oracle.c, 'port') timed on this box's host cores on a bounded sample (~10-20 s)."""
+    """the CPU restatement timed on this box's host cores on bounded samples: C1 reference-shaped per-candidate loop
+    (all threads and one thread), C2 best-effort batched dtrsm, C3 fit, C4 one MAP objective + gradient evaluation."""
+    import scipy.linalg as sl
     from oracle import gp_oracle as orc
     from oracle.c_oracle import COracle
+    t0 = time.perf_counter()
     gp = orc.GPOracle(w["D"], w["kernel"], "MeanConst", ll=ll, lsigma=0.0, lognoise=-2.0, beta=0.0).fit(X, y)
+    t_fit = time.perf_counter() - t0
     co = COracle(gp)
     Xs = candidates(w, 0)
-    t0 = time.perf_counter(); r = co.acquire(w["acq"], tuple(par), Xs[:, :256], want_grad=w["grad"]); pilot = (time.perf_counter() - t0) / 256
-    sample = int(max(256, min(w["M"], 12.0 / pilot)))
-    t0 = time.perf_counter(); r = co.acquire(w["acq"], tuple(par), Xs[:, :sample], want_grad=w["grad"]); dt = time.perf_counter() - t0
+    nthr = os.cpu_count() or 1
+    t0 = time.perf_counter(); r = co.acquire(w["acq"], tuple(par), Xs[:, :256], want_grad=w["grad"], nthreads=nthr); pilot = (time.perf_counter() - t0) / 256
+    sample = int(max(256, min(w["M"], 10.0 / pilot)))
+    t0 = time.perf_counter(); r = co.acquire(w["acq"], tuple(par), Xs[:, :sample], want_grad=w["grad"], nthreads=nthr); dt = time.perf_counter() - t0
+    s1 = int(max(64, min(sample, 3.0 / (pilot * nthr))))
+    t0 = time.perf_counter(); co.acquire(w["acq"], tuple(par), Xs[:, :s1], want_grad=w["grad"], nthreads=1); dt1 = time.perf_counter() - t0
+    # C2: the same math batched -- k* block, ONE dtrsm (OpenBLAS, all threads), vectorised epilogue
+    B = 4096
+    L = np.ascontiguousarray(gp.U.T)
+    t0 = time.perf_counter(); nb = 0
+    while time.perf_counter() - t0 < 4.0 and (nb + 1) * B <= w["M"]:
+        Ks = gp.cov(gp.X, Xs[:, nb * B:(nb + 1) * B])
+        v = sl.solve_triangular(L, Ks, lower=True, check_finite=False)
+        mu = gp.beta + Ks.T @ gp.alpha; s2 = np.maximum(gp.sf2 - np.einsum("ij,ij->j", v, v), 0.0)
+        orc.acq_value(w["acq"], tuple(par), mu, s2, eps=np.zeros(B) if w["acq"] == "TS" else None)
+        nb += 1
+    dt2 = time.perf_counter() - t0
+    # C4: one evaluation of the MAP objective and its gradient at the workload's own size
+    t0 = time.perf_counter(); gp.mll_dmll(gp.get_params()); t_map = time.perf_counter() - t0
     return {"value": sample / dt, "unit": "candidates/s", "cores": int(r["threads"]), "kind": "port",
-            "sample": f"first {sample} of {w['M']} LHS candidates, per-candidate predict_f loop (dtrsv-shaped) + functor, oracle/oracle.c, "
-                      f"OpenMP over candidates; host has {os.cpu_count()} logical CPUs; {dt:.1f} s"}
+            "sample": f"C1: first {sample} of {w['M']} LHS candidates, per-candidate predict_f loop (dtrsv-shaped) + functor, oracle/oracle.c, "
+                      f"OpenMP over candidates; host has {os.cpu_count()} logical CPUs; {dt:.1f} s",
+            "c1_one_thread": {"value": s1 / dt1, "cores": 1, "sample": f"{s1} candidates, {dt1:.1f} s"},
+            "c2_batched_dtrsm": {"value": nb * B / dt2, "cores": nthr, "blas": "NumPy/SciPy OpenBLAS", "gradient": False,
+                                 "sample": f"{nb} blocks of {B} candidates: k* block, one dtrsm, vectorised functor; {dt2:.1f} s"},
+            "c3_fit_seconds": {"value": t_fit, "what": f"assembly + dpotrf + alpha + mll at N={w['N']} (oracle/gp_oracle.py, LAPACK)"},
+            "c4_map_eval_seconds": {"value": t_map, "what": f"mll + dmll for one theta at N={w['N']}, D={w['D']} (dpotrf, inverse, D+2 traces)"}}
 
 
 if __name__ == "__main__":

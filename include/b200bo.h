@@ -38,7 +38,8 @@ enum {
   B200BO_ERR_CUDA = -2,      /* CUDA runtime / driver error, or no device */
   B200BO_ERR_NOTPD = -3,     /* not positive definite after 10 jitter retries (EXT make_posdef!) */
   B200BO_ERR_STATE = -4,     /* call needs a fitted model */
-  B200BO_ERR_ALLOC = -5
+  B200BO_ERR_ALLOC = -5,
+  B200BO_ERR_NCCL = -6       /* NCCL could not be loaded or a collective failed */
 };
 
 /* EXT GaussianProcesses.jl kernels reachable from the reference (README.md:22-26, BayesianOptimization.jl:259-264,
@@ -70,7 +71,8 @@ enum {
   B200BO_T_ALPHA = 3,     /* alpha / logdet (K5) of the last fit */
   B200BO_T_ACQ = 4,       /* fused acquisition launch (K6) of the last predict/acquire */
   B200BO_T_MLL = 5,       /* last mll sweep, all settings */
-  B200BO_T_COUNT = 6
+  B200BO_T_ACQ_GEMM = 6,  /* sum over the int8 slice-product launches (acq_i8_gemm_kernel) of the last acquire; needs knob "acq_gemm_timing" */
+  B200BO_T_COUNT = 7
 };
 
 typedef struct { double value; int64_t index; } b200bo_best_t;   /* index = -1: nothing beat -Inf */
@@ -79,6 +81,22 @@ typedef struct { double value; int64_t index; } b200bo_best_t;   /* index = -1: 
 B200BO_API int32_t b200bo_create(b200bo_handle_t* h, int32_t device, int32_t D, int64_t capacity,
                       int32_t kernel_kind, int32_t mean_kind);
 B200BO_API int32_t b200bo_destroy(b200bo_handle_t h);
+
+/* -- multi-GPU (the shard axis is the plain loop over starts of acquire_max, src/acquisition.jl:58-66) ----------------------
+ * b200bo_create_multi: ONE process, n_gpus replicas of the model (devices[i], or devices 0..n_gpus-1 when NULL).  Model updates (fit /
+ *   append / refit / set_params) go to every replica; b200bo_acquire / b200bo_acquire_lhs / b200bo_acquire_ascent / b200bo_predict shard
+ *   their candidate columns and b200bo_mll_sweep its settings over the replicas in contiguous blocks.  b200bo_acquire's exchange step is
+ *   ONE ncclAllGather of a 272-byte record per rank (value, global index, point) + a deterministic merge on the device (largest value,
+ *   lowest index): the result equals the single-GPU result bit for bit.  `_dev` entries of a multi handle address replica 0 only.
+ * b200bo_comm_*: one process per GPU (torchrun / MPI-style hosts): rank 0 calls b200bo_comm_unique_id, the host distributes the 128
+ *   bytes, every rank calls b200bo_comm_init_rank on its own handle; from then on b200bo_acquire and b200bo_acquire_dev return the
+ *   GLOBAL best (and b200bo_acquire's best_x the global winner's point) on every rank -- a collective call: all ranks must make it. */
+B200BO_API int32_t b200bo_create_multi(b200bo_handle_t* h, int32_t n_gpus, const int32_t* devices, int32_t D, int64_t capacity,
+                                       int32_t kernel_kind, int32_t mean_kind);
+B200BO_API int32_t b200bo_num_gpus(b200bo_handle_t h, int32_t* n_gpus);
+B200BO_API int32_t b200bo_comm_unique_id(uint8_t* id128);
+B200BO_API int32_t b200bo_comm_init_rank(b200bo_handle_t h, int32_t world, int32_t rank, const uint8_t* id128);
+B200BO_API int32_t b200bo_comm_destroy(b200bo_handle_t h);
 B200BO_API const char* b200bo_last_error(b200bo_handle_t h);          /* valid until the next call on h; h may be NULL */
 B200BO_API int32_t b200bo_set_stream(b200bo_handle_t h, void* cuda_stream);   /* borrow a caller stream (NULL = own) */
 B200BO_API int32_t b200bo_sync(b200bo_handle_t h);
@@ -160,6 +178,11 @@ B200BO_API int32_t b200bo_set_syrk_engine(b200bo_handle_t h, int32_t engine);
 /* engine of the acquisition step (K6): 1 = error-free int8-slice product against the explicit inverse factor on tcgen05 (default),
    0 = blocked triangular solves on the FP64 tensor pipe (DMMA).  Both are FP64-accurate; the switch exists for in-process A/B tests. */
 B200BO_API int32_t b200bo_set_acq_engine(b200bo_handle_t h, int32_t engine);
+/* self-measured tcgen05.mma kind::i8 rate in TOP/s (2 ops per multiply-add): the int8 tensor-pipe roofline denominator of K4 / K6 */
+B200BO_API int32_t b200bo_i8_peak_tops(b200bo_handle_t h, double* tops);
+/* developer / bench knobs: "acq_lanes" (1 or 2 chunk lanes of the tcgen05 acquisition path), "acq_chunk_mb" (k* slice bytes per chunk,
+   0 = default), "acq_gemm_timing" (1: CUDA-event pairs around every slice-product launch, one lane; read B200BO_T_ACQ_GEMM) */
+B200BO_API int32_t b200bo_set_knob(b200bo_handle_t h, const char* name, int64_t value);
 B200BO_API int32_t b200bo_version(void);
 
 #ifdef __cplusplus

@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(128, 1) probe(const int8_t* __restrict__ A, co
   const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint64_t da = make_desc(smem_u32(sA)), db = make_desc(smem_u32(sB));
   long long t0 = 0;
-  if (tid == 0) {
+  uint32_t elected = 0;
+  if (warp == 0) asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(elected));
+  if (elected) {            // elect.sync, not `tid == 0`: ptxas then emits plain back-to-back UTCIMMA (no per-MMA election loop)
     t0 = clock64();
     if (mode == 0) {
       for (int ks = 0; ks < 4; ++ks) cp_128x256b(tA + 8 * ks, da + 2 * ks);
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(128, 1) probe(const int8_t* __restrict__ A, co
     commit(&bar);
   }
   const bool done = mbar_wait_bounded(&bar, 0, 1 << 24);
-  if (tid == 0 && cycles) cycles[blockIdx.x] = clock64() - t0;
+  if (elected && cycles) cycles[blockIdx.x] = clock64() - t0;
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   if (!done && tid == 0) atomicExch(err, 1);
   if (done && mode == 5 && blockIdx.x == 0) {
