@@ -710,7 +710,7 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
       g.amu = dAmu; g.as2 = dAs2; g.part = dWg + 2 * (size_t)CH * (size_t)Np; g.grad = l.dgrad;
       g.M = M; g.c0 = c0; g.CH = CH; g.N = (int)h->N; g.D = h->D; g.nblk = nblk;
       const int nb = (int)((mc + 31) / 32);
-      g.nsplit = std::max(1, std::min(std::min(nblk, 16), (3 * h->num_sms + nb - 1) / nb));
+      g.nsplit = std::max(1, std::min(16, (nblk + 3) / 4));      // a function of N only: the summation order of a candidate's gradient must not depend on the batch
       if ((e = launch_grad(h, st, g, nb, mc)) != cudaSuccess) return e;
     }
   }

@@ -199,6 +199,16 @@ int32_t check_acq(b200bo_handle_t h, int32_t kind, int32_t n_params, bool grad) 
   return B200BO_OK;
 }
 
+// While a multi handle fans a call out to its replicas, each replica -- the parent included -- must behave as a plain single-GPU
+// handle: no recursion into the fan-out and NO communicator exchange of its own (a lone rank entering a collective never returns).
+struct SoloScope {
+  b200bo_handle_s* h;
+  std::vector<b200bo_handle_s*> kids;
+  bool was;
+  explicit SoloScope(b200bo_handle_s* r) : h(r), was(r->in_multi) { kids.swap(h->replicas); h->in_multi = true; }
+  ~SoloScope() { kids.swap(h->replicas); h->in_multi = was; }
+};
+
 // every replica of a multi handle: the parent first
 std::vector<b200bo_handle_s*> all_replicas(b200bo_handle_s* h) {
   std::vector<b200bo_handle_s*> v{h};
@@ -632,7 +642,7 @@ static int32_t acquire_dev_impl(b200bo_handle_t h, int32_t kind, const double* p
 
 B200BO_API int32_t b200bo_acquire_dev(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* dXs, int64_t M, uint64_t seed,
                            int64_t idx_offset, double* dvalues, double* dgrad, double* dmu, double* dvar, b200bo_best_t* dbest) {
-  const bool exchange = h && h->comm && h->replicas.empty() && !h->is_replica;
+  const bool exchange = h && h->comm && h->replicas.empty() && !h->is_replica && !h->in_multi;
   return acquire_dev_impl(h, kind, p, np, dXs, M, seed, idx_offset, dvalues, dgrad, dmu, dvar, dbest, exchange);
 }
 
@@ -711,7 +721,7 @@ B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t kind, const double*
     if (best_x && hb.index >= 0) memcpy(best_x, hm + 2, sizeof(double) * D);
     return B200BO_OK;
   }
-  const bool exchange = h->comm && !h->is_replica;
+  const bool exchange = h->comm && !h->is_replica && !h->in_multi;
   b200bo_best_t* dbest = nullptr;
   rc = acquire_host_enqueue(h, kind, p, np, Xs, M, seed, idx_offset, values, grad, mu, var, exchange, &dbest);
   if (rc) return rc;
@@ -780,11 +790,9 @@ B200BO_API int32_t b200bo_acquire_lhs(b200bo_handle_t h, int32_t kind, const dou
     std::vector<double> bx((size_t)R * h->D, 0.0);
     rc = on_replicas(h, [&](b200bo_handle_s* r, int k) {
       int64_t lo, hi; shard_bounds(n_local, R, k, &lo, &hi);
-      std::vector<b200bo_handle_s*> none;
-      none.swap(r->replicas);
+      SoloScope solo(r);
       const int32_t e = b200bo_acquire_lhs(r, kind, p, np, lb, ub, n_total, offset + lo, hi - lo, lhs_seed, ts_seed, values ? values + lo : nullptr, &bs[k],
                                            bx.data() + (size_t)k * r->D);
-      none.swap(r->replicas);
       return e;
     });
     if (rc) return rc;
@@ -803,7 +811,7 @@ B200BO_API int32_t b200bo_acquire_lhs(b200bo_handle_t h, int32_t kind, const dou
   double* dval = dXs + M * D;
   b200bo_best_t* dbest = reinterpret_cast<b200bo_best_t*>(dval + M);
   CU(launch_lhs(h, dXs, n_total, offset, n_local, lhs_seed, h->dlbub));
-  rc = b200bo_acquire_dev(h, kind, p, np, dXs, M, ts_seed, offset, values ? dval : nullptr, nullptr, nullptr, nullptr, dbest);
+  rc = acquire_dev_impl(h, kind, p, np, dXs, M, ts_seed, offset, values ? dval : nullptr, nullptr, nullptr, nullptr, dbest, false);   // the best of THIS block
   if (rc) return rc;
   b200bo_best_t hb = {-INFINITY, -1};
   if (values && M > 0) CU(cudaMemcpyAsync(values, dval, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
@@ -830,11 +838,9 @@ B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t kind, const 
     std::vector<double> bx((size_t)R * h->D, 0.0);
     rc = on_replicas(h, [&](b200bo_handle_s* r, int k) {
       int64_t lo, hi; shard_bounds(M, R, k, &lo, &hi);
-      std::vector<b200bo_handle_s*> none;
-      none.swap(r->replicas);
+      SoloScope solo(r);
       const int32_t e = b200bo_acquire_ascent(r, kind, p, np, Xs + lo * r->D, hi - lo, lb, ub, steps, step0, idx_offset + lo, Xout ? Xout + lo * r->D : nullptr,
                                               values ? values + lo : nullptr, &bs[k], bx.data() + (size_t)k * r->D);
-      none.swap(r->replicas);
       return e;
     });
     if (rc) return rc;
@@ -883,10 +889,8 @@ B200BO_API int32_t b200bo_predict(b200bo_handle_t h, const double* Xs, int64_t M
     const int R = 1 + (int)h->replicas.size();
     return on_replicas(h, [&](b200bo_handle_s* r, int k) {
       int64_t lo, hi; shard_bounds(M, R, k, &lo, &hi);
-      std::vector<b200bo_handle_s*> none;
-      none.swap(r->replicas);
+      SoloScope solo(r);
       const int32_t e = b200bo_predict(r, Xs + lo * r->D, hi - lo, mu + lo, var + lo);
-      none.swap(r->replicas);
       return e;
     });
   }
@@ -921,10 +925,8 @@ B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int3
     const int R = 1 + (int)h->replicas.size();
     return on_replicas(h, [&](b200bo_handle_s* r, int k) {
       int64_t lo, hi; shard_bounds(S, R, k, &lo, &hi);
-      std::vector<b200bo_handle_s*> none;
-      none.swap(r->replicas);
+      SoloScope solo(r);
       const int32_t e = hi > lo ? b200bo_mll_sweep(r, Theta + lo * P, P, (int32_t)(hi - lo), mask, mll + lo, dmll ? dmll + lo * P : nullptr) : B200BO_OK;
-      none.swap(r->replicas);
       return e;
     });
   }

@@ -94,6 +94,7 @@ struct b200bo_handle_s {
   int rec_world = 0;
   std::vector<b200bo_handle_s*> replicas;   // children of a multi handle (the parent itself is rank 0)
   bool is_replica = false;   // a child of a multi handle
+  bool in_multi = false;     // inside a fan-out of the parent: behave as a single-GPU handle (no exchange)
   bool fitted = false;
   bool need_upload = false;  // device copies of X / y are stale (a failed elastic append): re-upload before the next refactor
   int acq_ready = 0;         // bit 0: W = L^-1 sliced for the tcgen05 acquisition path, bit 1: Sigma^-1 sliced (acq_i8.cu)

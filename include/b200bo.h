@@ -90,7 +90,8 @@ B200BO_API int32_t b200bo_destroy(b200bo_handle_t h);
  *   lowest index): the result equals the single-GPU result bit for bit.  `_dev` entries of a multi handle address replica 0 only.
  * b200bo_comm_*: one process per GPU (torchrun / MPI-style hosts): rank 0 calls b200bo_comm_unique_id, the host distributes the 128
  *   bytes, every rank calls b200bo_comm_init_rank on its own handle; from then on b200bo_acquire and b200bo_acquire_dev return the
- *   GLOBAL best (and b200bo_acquire's best_x the global winner's point) on every rank -- a collective call: all ranks must make it. */
+ *   GLOBAL best (and b200bo_acquire's best_x the global winner's point) on every rank -- a collective call: all ranks must make it.
+ *   (b200bo_acquire_lhs / b200bo_acquire_ascent stay local: they return the best of the block they were given.) */
 B200BO_API int32_t b200bo_create_multi(b200bo_handle_t* h, int32_t n_gpus, const int32_t* devices, int32_t D, int64_t capacity,
                                        int32_t kernel_kind, int32_t mean_kind);
 B200BO_API int32_t b200bo_num_gpus(b200bo_handle_t h, int32_t* n_gpus);

@@ -592,6 +592,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.timeout(180)
 @pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
 def test_multi_gpu_handle_equals_single_gpu_bit_for_bit(bo, n_gpus):
     """b200bo_create_multi: the candidate columns shard over n_gpus replicas INSIDE the library (contiguous blocks, one 272 B/rank
@@ -614,7 +615,6 @@ def test_multi_gpu_handle_equals_single_gpu_bit_for_bit(bo, n_gpus):
         assert np.array_equal(a["best_x"], b["best_x"]), kind
         if "want_grad" in kw:
             assert np.array_equal(a["grad"], b["grad"]) and np.array_equal(a["mu"], b["mu"]) and np.array_equal(a["var"], b["var"])
-    assert g1.acquire("MaxMean", (), Xs)["best_index"] in (17, 4321) or True
     m1, v1 = g1.predict(Xs[:, :999]); m2, v2 = gm.predict(Xs[:, :999])
     assert np.array_equal(m1, m2) and np.array_equal(v1, v2)
     bo.update(g1, Xs[:, :3], np.zeros(3)); bo.update(gm, Xs[:, :3], np.zeros(3))       # elastic append on every replica
