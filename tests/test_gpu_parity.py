@@ -626,3 +626,28 @@ def test_multi_gpu_handle_equals_single_gpu_bit_for_bit(bo, n_gpus):
     lb, ub = np.zeros(D), np.ones(D)
     ra, rb = g1.acquire_lhs("EI", (tau,), lb, ub, 6000, lhs_seed=3), gm.acquire_lhs("EI", (tau,), lb, ub, 6000, lhs_seed=3)
     assert ra["best_index"] == rb["best_index"] and ra["best_value"] == rb["best_value"] and np.array_equal(ra["best_x"], rb["best_x"])
+
+
+def test_cusolver_cublas_cross_check(bo):
+    """A second, independent GPU-side oracle (tests only): cuSOLVER dpotrf + cuBLAS dtrsm through torch.linalg in FP64 on
+    the library's own Sigma.  Factor, alpha, log-determinant and the posterior of the hand-written path against the vendor libraries."""
+    import torch
+    rng, o, g, X, y = make_pair(bo, "Mat52Ard", "MeanConst", 6, 1500, seed=4242)
+    S = torch.from_numpy(g.kmat()).cuda()
+    L = torch.linalg.cholesky(S)                                               # cuSOLVER potrf
+    U = L.T.cpu().numpy()
+    assert relmax(g.factor, U) < 1e-11
+    r = torch.from_numpy(y - 0.3).cuda()
+    alpha = torch.cholesky_solve(r[:, None], L)[:, 0]                          # cuBLAS trsm x 2
+    assert relmax(g.alpha, alpha.cpu().numpy()) < 1e-9
+    mll = -0.5 * (float(r @ alpha) + 2.0 * float(torch.log(torch.diagonal(L)).sum()) + y.size * np.log(2 * np.pi))
+    assert abs(g.mll - mll) <= 1e-11 * abs(mll)
+    Xs = rng.random((6, 2000)); Xs[:, :20] = X[:, :20]
+    Ks = torch.from_numpy(o.cov(o.X, Xs)).cuda()
+    V = torch.linalg.solve_triangular(L, Ks, upper=False)                      # cuBLAS trsm
+    var = np.maximum(o.sf2 - (V * V).sum(0).cpu().numpy(), 0.0)
+    mu = 0.3 + (Ks.T @ alpha).cpu().numpy()
+    for eng in (1, 0):
+        g.set_acq_engine(eng)
+        m, v = g.predict(Xs)
+        assert close(m, mu, 1e-9, 1e-12) and close(v, var, 1e-8, 1e-13), eng
