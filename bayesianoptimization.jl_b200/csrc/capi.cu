@@ -7,6 +7,7 @@
 #include <string.h>
 #include <algorithm>
 #include <limits>
+#include <chrono>
 #include <new>
 #include <thread>
 #include "common.cuh"
@@ -54,7 +55,7 @@ int32_t alloc_device(b200bo_handle_s* h, int64_t cap) {
   cap = std::max<int64_t>(NB, (cap + NB - 1) / NB * NB);
   free_device(h);
   h->cap = cap; h->ld = cap;
-  h->nslots = std::max<int64_t>(h->num_sms, cap / TILE_N);
+  h->nslots = h->lite ? 1 : std::max<int64_t>(h->num_sms, cap / TILE_N);
   const int64_t nb = cap / NB;
   const int64_t T = cap / 64;
   CU(cudaMalloc(&h->dX, sizeof(double) * cap * h->D));
@@ -287,6 +288,8 @@ B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
   if (!h) return B200BO_OK;
   for (auto* r : h->replicas) b200bo_destroy(r);
   h->replicas.clear();
+  for (auto* wk : h->workers) b200bo_destroy(wk);
+  h->workers.clear();
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   nccl_destroy(h);
@@ -431,6 +434,7 @@ B200BO_API int32_t b200bo_fit(b200bo_handle_t h, const double* X, const double* 
   h->hX.assign(X, X + N * h->D);
   h->hy.assign(y, y + N);
   h->N = N;
+  h->data_version++;
   int32_t rc = upload_data(h);
   if (rc) return rc;
   return refit(h);
@@ -474,6 +478,7 @@ B200BO_API int32_t b200bo_append(b200bo_handle_t h, const double* Xn, const doub
     return B200BO_OK;
   }
   cudaSetDevice(h->device);
+  h->data_version++;
   const int64_t D = h->D, N0 = (int64_t)h->hy.size();
   // Elastic path (EXT ElasticPDMats append!): a valid factor, room in the buffers, a handful of new points.
   const bool elastic = h->fitted && h->N > 0 && m <= 16 && h->N + m <= h->cap;
@@ -931,6 +936,51 @@ B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int3
     });
   }
   cudaSetDevice(h->device);
+  if (!h->lite && h->sweep_workers > 0) {
+    // ---- several settings in flight: K worker models on this device, contiguous blocks of settings, one host thread each ----
+    const int K = std::max(1, std::min<int>(h->sweep_workers, S));
+    while ((int)h->workers.size() < K) {
+      b200bo_handle_s* wk = new (std::nothrow) b200bo_handle_s();
+      if (!wk) return fail(h, B200BO_ERR_ALLOC, "out of host memory");
+      wk->device = h->device; wk->D = h->D; wk->kernel_kind = h->kernel_kind; wk->mean_kind = h->mean_kind; wk->fam = h->fam; wk->iso = h->iso;
+      wk->num_sms = h->num_sms; wk->lite = true; wk->sweep_workers = 0; wk->hp = h->hp;
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&wk->stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+          cudaStreamCreateWithPriority(&wk->stream2, cudaStreamNonBlocking, lo) != cudaSuccess) { delete wk; return fail(h, B200BO_ERR_CUDA, "worker streams"); }
+      for (auto& e : wk->ev) cudaEventCreate(&e);
+      const int32_t rcw = alloc_device(wk, h->cap);
+      if (rcw != B200BO_OK) { h->err = wk->err; b200bo_destroy(wk); return rcw; }
+      wk->fitted = true;
+      h->workers.push_back(wk);
+    }
+    std::vector<int32_t> rcs(K, B200BO_OK);
+    std::vector<std::thread> th;
+    int64_t launches0 = 0;
+    for (int k = 0; k < K; ++k) launches0 += h->workers[k]->launches;
+    auto run = [&](int k) {
+      b200bo_handle_s* wk = h->workers[k];
+      cudaSetDevice(wk->device);
+      if (wk->synced_version != h->data_version) {
+        wk->hX = h->hX; wk->hy = h->hy; wk->N = h->N;
+        const int32_t e = upload_data(wk);
+        if (e) { rcs[k] = e; return; }
+        wk->synced_version = h->data_version;
+      }
+      wk->hp = h->hp; wk->syrk_engine = h->syrk_engine; wk->fitted = false;
+      int64_t lo, hi; shard_bounds(S, K, k, &lo, &hi);
+      if (hi > lo) rcs[k] = b200bo_mll_sweep(wk, Theta + lo * P, P, (int32_t)(hi - lo), mask, mll + lo, dmll ? dmll + lo * P : nullptr);
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int k = 1; k < K; ++k) th.emplace_back(run, k);
+    run(0);
+    for (auto& t : th) t.join();
+    h->timing[B200BO_T_MLL] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (int k = 0; k < K; ++k) h->launches += h->workers[k]->launches;
+    h->launches -= launches0;
+    for (int k = 0; k < K; ++k) if (rcs[k]) return fail(h, rcs[k], "sweep worker " + std::to_string(k) + ": " + h->workers[k]->err);
+    return B200BO_OK;
+  }
   const Hyper saved = h->hp;
   int32_t rc = B200BO_OK;
   cudaEventRecord(h->ev[6], h->stream);
@@ -946,8 +996,9 @@ B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int3
     if (dmll) {
       double raw[35];
       static const bool by_solves = getenv("B200BO_KINV_SOLVE") != nullptr;   // developer cross-check of the two Sigma^-1 paths
-      cudaError_t e = by_solves ? launch_kinv_solve(h) : launch_kinv(h);
-      if (e == cudaSuccess) e = launch_dmll(h, mask, h->dscal + 8, by_solves ? h->dV : h->dKi);
+      const bool solves = by_solves && !h->lite;            // workers carry no solve panels
+      cudaError_t e = solves ? launch_kinv_solve(h) : launch_kinv(h);
+      if (e == cudaSuccess) e = launch_dmll(h, mask, h->dscal + 8, solves ? h->dV : h->dKi);
       if (e == cudaSuccess) e = cudaMemcpyAsync(raw, h->dscal + 8, sizeof(raw), cudaMemcpyDeviceToHost, h->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
       if (e != cudaSuccess) { rc = fail(h, B200BO_ERR_CUDA, std::string("mll gradient: ") + cudaGetErrorString(e)); break; }
@@ -1021,6 +1072,7 @@ B200BO_API int32_t b200bo_set_knob(b200bo_handle_t h, const char* name, int64_t 
   if (k == "acq_lanes") { if (value < 1 || value > 2) return fail(h, B200BO_ERR_ARG, "acq_lanes must be 1 or 2"); h->acq_lanes = (int)value; }
   else if (k == "acq_chunk_mb") { if (value < 0) return fail(h, B200BO_ERR_ARG, "acq_chunk_mb must be >= 0"); h->acq_chunk_mb = value; }
   else if (k == "acq_gemm_timing") h->acq_time_gemm = value != 0;
+  else if (k == "sweep_workers") { if (value < 0 || value > 32) return fail(h, B200BO_ERR_ARG, "sweep_workers must be in 0..32"); h->sweep_workers = (int)value; }
   else return fail(h, B200BO_ERR_ARG, "unknown knob: " + k);
   for (auto* r : h->replicas) b200bo_set_knob(r, name, value);
   return B200BO_OK;

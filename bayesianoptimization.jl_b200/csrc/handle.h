@@ -94,6 +94,12 @@ struct b200bo_handle_s {
   int rec_world = 0;
   std::vector<b200bo_handle_s*> replicas;   // children of a multi handle (the parent itself is rank 0)
   bool is_replica = false;   // a child of a multi handle
+  // MAP sweeps (b200bo_mll_sweep) run on worker models of the same device, several settings in flight at once, each on its own streams
+  // and buffers: one setting's chain of diagonal blocks hides behind another's tile GEMMs, and the parent's own factor stays valid
+  std::vector<b200bo_handle_s*> workers;
+  int64_t data_version = 0, synced_version = -1;
+  bool lite = false;         // a worker: no acquisition solve panels
+  int sweep_workers = 6;
   bool in_multi = false;     // inside a fan-out of the parent: behave as a single-GPU handle (no exchange)
   bool fitted = false;
   bool need_upload = false;  // device copies of X / y are stale (a failed elastic append): re-upload before the next refactor

@@ -136,8 +136,9 @@ B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t acq_kind, const dou
                        b200bo_best_t* best /*or NULL*/, double* best_x /*D or NULL*/);
 
 /* -- MAP objective: the closure of optimizemodel! (gp.jl:59-64): for each column of Theta (P x S) set the
- *    masked params, refactor, return mll[S] and dmll (P x S, may be NULL).  Leaves the model at its
- *    previous parameters. */
+ *    masked params, refactor, return mll[S] and dmll (P x S, may be NULL).  Leaves the model -- parameters AND
+ *    factor -- untouched: the settings are factored on worker buffers, several in flight at once (knob
+ *    "sweep_workers"), and on a multi handle they shard over the GPUs. */
 B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int32_t P, int32_t S, int32_t mask,
                          double* mll, double* dmll);
 
@@ -182,7 +183,8 @@ B200BO_API int32_t b200bo_set_acq_engine(b200bo_handle_t h, int32_t engine);
 /* self-measured tcgen05.mma kind::i8 rate in TOP/s (2 ops per multiply-add): the int8 tensor-pipe roofline denominator of K4 / K6 */
 B200BO_API int32_t b200bo_i8_peak_tops(b200bo_handle_t h, double* tops);
 /* developer / bench knobs: "acq_lanes" (1 or 2 chunk lanes of the tcgen05 acquisition path), "acq_chunk_mb" (k* slice bytes per chunk,
-   0 = default), "acq_gemm_timing" (1: CUDA-event pairs around every slice-product launch, one lane; read B200BO_T_ACQ_GEMM) */
+   0 = default), "acq_gemm_timing" (1: CUDA-event pairs around every slice-product launch, one lane; read B200BO_T_ACQ_GEMM),
+   "sweep_workers" (settings of a MAP sweep in flight at once on one GPU, default 6; 0 = one after the other on the model's own buffers) */
 B200BO_API int32_t b200bo_set_knob(b200bo_handle_t h, const char* name, int64_t value);
 B200BO_API int32_t b200bo_version(void);
 
