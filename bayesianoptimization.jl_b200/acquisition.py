@@ -2,13 +2,11 @@
 
 The reference runs `restarts` serial NLopt optimisations, each calling the closure up to `maxeval` times
 (acquisition.jl:54-68).  Here `restarts` becomes the number M of Latin-hypercube candidates scored -- value,
-optional gradient and arg-max -- by a single fused kernel launch (b200bo_acquire).  `polish` optionally runs a
-box-bounded L-BFGS from the winning candidate on value+gradient evaluated by the same kernel, mirroring what
-one NLopt LD_LBFGS run adds on top of a start point (honours maxeval / ftol / xtol style options).
+optional gradient and arg-max -- by a single fused kernel launch (b200bo_acquire).  `polish` then refines the `polish_top`
+best candidates by box-bounded L-BFGS ascents in lock-step INSIDE the library (b200bo_acquire_lbfgs) -- what the reference's
+NLopt LD_LBFGS run does per start -- with the options it forwards (maxeval, maxtime, ftol_rel/abs, xtol_rel/abs).
 """
 from __future__ import annotations
-
-import warnings
 
 import numpy as np
 
@@ -37,6 +35,7 @@ class AcquisitionSearch:
         self.maxeval, self.maxtime = 0, 0.0
         self.ftol_abs = self.ftol_rel = self.xtol_abs = self.xtol_rel = 0.0
         self.polish = True
+        self.polish_top = 16             # L-BFGS restarts refined in lock-step after the sweep (the reference refines every start)
         self.device_lhs = False          # candidates generated in HBM (b200bo_acquire_lhs) instead of on the host
         self.ascent_steps = 0            # > 0: refine the `ascent_top` best candidates by batched ascent on the device
         self.ascent_top = 256
@@ -57,23 +56,15 @@ def nlopt_setup(a: AbstractAcquisition, model: B200GPE, lowerbounds, upperbounds
     return opt
 
 
-def _polish(opt: AcquisitionSearch, x0: np.ndarray, f0: float):
-    from scipy.optimize import minimize
+def _refine(opt: AcquisitionSearch, data: np.ndarray, values: np.ndarray):
+    """the NLopt :LD_LBFGS runs of the reference (acquisition.jl:59), for the `polish_top` best candidates of the sweep at once: box-bounded
+    L-BFGS ascents in lock-step inside the library (b200bo_acquire_lbfgs) with the forwarded options (acquisition.jl:24-27)."""
     a, model = opt.acquisition, opt.model
-    lb, ub = opt.lower_bounds, opt.upper_bounds
-
-    def negf(x):
-        r = model.acquire(a.kind, a.params(), x, want_grad=True)
-        return -float(r["values"][0]), -r["grad"][:, 0]
-
-    # stopping rules in the spirit of the NLopt options the reference forwards (acquisition.jl:24-27): maxeval, ftol_rel
-    kw = dict(maxfun=int(opt.maxeval) if opt.maxeval else 15000, gtol=1e-11, ftol=float(opt.ftol_rel) if opt.ftol_rel else 1e-15)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        res = minimize(negf, np.clip(x0, lb, ub), jac=True, method="L-BFGS-B", bounds=list(zip(lb, ub)), options=kw)
-    if np.isfinite(res.fun) and -res.fun > f0:
-        return -float(res.fun), np.asarray(res.x, float)
-    return f0, x0
+    v = np.where(np.isnan(values), -np.inf, values)
+    top = np.argsort(-v, kind="stable")[:max(1, min(int(opt.polish_top), v.size))]
+    return model.acquire_lbfgs(a.kind, a.params(), data[:, top], opt.lower_bounds, opt.upper_bounds, maxeval=int(opt.maxeval) if opt.maxeval else 2000,
+                               ftol_rel=float(opt.ftol_rel), ftol_abs=float(opt.ftol_abs), xtol_rel=float(opt.xtol_rel), xtol_abs=float(opt.xtol_abs),
+                               maxtime=float(opt.maxtime))
 
 
 def acquire_max(opt, lowerbounds=None, upperbounds=None, restarts=None, options=None):
@@ -88,26 +79,26 @@ def acquire_max(opt, lowerbounds=None, upperbounds=None, restarts=None, options=
     lb = np.asarray(lowerbounds, float); ub = np.asarray(upperbounds, float)
     a, model = opt.acquisition, opt.model
     derivative_free = isinstance(a, ThompsonSamplingSimple) or not opt.gradient
-    refine = opt.ascent_steps > 0 and not derivative_free
+    refine = (opt.polish or opt.ascent_steps > 0) and not derivative_free
     if opt.device_lhs and not refine:
         r = model.acquire_lhs(a.kind, a.params(), lb, ub, int(restarts), lhs_seed=opt.seed, ts_seed=opt.seed)
     else:
         data = model.lhs(lb, ub, int(restarts), seed=opt.seed) if opt.device_lhs else ScaledLHSIterator(lb, ub, int(restarts), opt.rng).data  # :57
         r = model.acquire(a.kind, a.params(), data, seed=opt.seed, want_values=refine)
         if refine and r["best_index"] >= 0:
-            v = np.where(np.isnan(r["values"]), -np.inf, r["values"])
-            top = np.argsort(-v, kind="stable")[:max(1, min(int(opt.ascent_top), v.size))]
-            r2 = model.acquire_ascent(a.kind, a.params(), data[:, top], lb, ub, steps=int(opt.ascent_steps))
+            if opt.ascent_steps > 0:                 # projected-gradient variant (fixed number of steps)
+                v = np.where(np.isnan(r["values"]), -np.inf, r["values"])
+                top = np.argsort(-v, kind="stable")[:max(1, min(int(opt.ascent_top), v.size))]
+                r2 = model.acquire_ascent(a.kind, a.params(), data[:, top], lb, ub, steps=int(opt.ascent_steps))
+            else:
+                r2 = _refine(opt, data, r["values"])
             if r2["best_index"] >= 0 and r2["best_value"] > r["best_value"]:
                 r = dict(r, best_value=r2["best_value"], best_x=r2["best_x"])
     opt.seed += 1
     opt.last = r
     if r["best_index"] < 0:
         return -np.inf, lb                           # :55-56
-    maxf, maxx = r["best_value"], r["best_x"].copy()
-    if opt.polish and not derivative_free:
-        maxf, maxx = _polish(opt, maxx, maxf)
-    return maxf, maxx
+    return r["best_value"], r["best_x"].copy()
 
 
 def acquire_model_max(o, options=None):

@@ -11,6 +11,7 @@
 #include <new>
 #include <thread>
 #include "common.cuh"
+#include "lbfgs.cuh"
 #include "handle.h"
 
 using namespace b200bo;
@@ -886,6 +887,138 @@ B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t kind, const 
   }
   if (best) *best = hb;
   return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_sobol(b200bo_handle_t h, const double* lb, const double* ub, uint64_t index0, int64_t n, double* Xs) {
+  if (!h || n < 0 || (n > 0 && !Xs) || index0 + (uint64_t)n > (1ull << 32)) return fail(h, B200BO_ERR_ARG, "bad arguments to sobol (indices must stay below 2^32)");
+  cudaSetDevice(h->device);
+  int32_t rc = upload_bounds(h, lb, ub);
+  if (rc) return rc;
+  rc = ensure_io(h, sizeof(double) * (n * h->D + 2));
+  if (rc) return rc;
+  CU(launch_sobol(h, h->dio, index0, n, h->dlbub));
+  if (n > 0) CU(cudaMemcpyAsync(Xs, h->dio, sizeof(double) * n * h->D, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return B200BO_OK;
+}
+
+B200BO_API int32_t b200bo_acquire_lbfgs(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* Xs, int64_t M, const double* lb,
+                                        const double* ub, int32_t maxeval, double ftol_rel, double ftol_abs, double xtol_rel, double xtol_abs,
+                                        double maxtime, double step0, int64_t idx_offset, double* Xout, double* values, double* evals,
+                                        b200bo_best_t* best, double* best_x) {
+  if (!h || M < 0 || (M > 0 && !Xs) || !(step0 > 0.0) || ftol_rel < 0 || ftol_abs < 0 || xtol_rel < 0 || xtol_abs < 0)
+    return fail(h, B200BO_ERR_ARG, "bad arguments to acquire_lbfgs");
+  int32_t rc = check_acq(h, kind, np, true);
+  if (rc) return rc;
+  if (!h->replicas.empty()) {
+    const int R = 1 + (int)h->replicas.size();
+    std::vector<b200bo_best_t> bs(R, b200bo_best_t{-INFINITY, -1});
+    std::vector<double> bx((size_t)R * h->D, 0.0);
+    rc = on_replicas(h, [&](b200bo_handle_s* r, int k) {
+      int64_t lo, hi; shard_bounds(M, R, k, &lo, &hi);
+      SoloScope solo(r);
+      return b200bo_acquire_lbfgs(r, kind, p, np, Xs + lo * r->D, hi - lo, lb, ub, maxeval, ftol_rel, ftol_abs, xtol_rel, xtol_abs, maxtime, step0,
+                                  idx_offset + lo, Xout ? Xout + lo * r->D : nullptr, values ? values + lo : nullptr, evals ? evals + lo : nullptr, &bs[k],
+                                  bx.data() + (size_t)k * r->D);
+    });
+    if (rc) return rc;
+    b200bo_best_t acc = {-INFINITY, -1};
+    for (int k = 0; k < R; ++k) merge_host(acc, best_x, bs[k], bx.data() + (size_t)k * h->D, h->D);
+    if (best) *best = acc;
+    return B200BO_OK;
+  }
+  cudaSetDevice(h->device);
+  rc = upload_bounds(h, lb, ub);
+  if (rc) return rc;
+  rc = ensure_fitted(h);
+  if (rc) return rc;
+  const int64_t D = h->D, B = lbfgs_state_doubles((int)D);
+  rc = ensure_io(h, sizeof(double) * (M * D + M * B + M + M * D + M + 4));
+  if (rc) return rc;
+  double* dXe = h->dio;
+  double* dwork = dXe + M * D;                                       // state | val | grad | evals
+  double* dval = dwork + M * B;
+  double* devals = dval + M + M * D;
+  b200bo_best_t* dbest = reinterpret_cast<b200bo_best_t*>(devals + M);
+  b200bo_best_t hb = {-INFINITY, -1};
+  if (M > 0) {
+    CU(cudaMemcpyAsync(dXe, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, h->stream));
+    AcqLaunch l;
+    l.acq_kind = kind; l.p0 = np > 0 ? p[0] : 0.0; l.p1 = np > 1 ? p[1] : 0.0; l.idx_offset = idx_offset; l.M = M; l.dbest = dbest;
+    LbfgsOpts o;
+    o.maxeval = maxeval; o.ftol_rel = ftol_rel; o.ftol_abs = ftol_abs; o.xtol_rel = xtol_rel; o.xtol_abs = xtol_abs; o.step0 = step0;
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    int rounds = 0;
+    CU(launch_lbfgs(h, l, dXe, dwork, h->dlbub, o, maxtime, &rounds));
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    if (Xout) CU(cudaMemcpyAsync(Xout, dXe, sizeof(double) * M * D, cudaMemcpyDeviceToHost, h->stream));
+    if (values) CU(cudaMemcpyAsync(values, dval, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+    if (evals) CU(cudaMemcpyAsync(evals, devals, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&hb, dbest, sizeof(hb), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->timing[B200BO_T_ACQ], h->ev[4], h->ev[5]);
+    if (best_x && hb.index >= 0) {
+      CU(cudaMemcpyAsync(best_x, dXe + (hb.index - idx_offset) * D, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+  }
+  if (best) *best = hb;
+  return B200BO_OK;
+}
+
+// optimizemodel!(::MAPGPOptimizer, model) (src/models/gp.jl:54-77): box-bounded L-BFGS ascent of the marginal log-likelihood over the
+// masked parameters, every evaluation = mll + dmll on the device (K1-K5 + K7).  R starts run in lock-step: one b200bo_mll_sweep of R
+// settings per round (on a multi handle the settings shard over the GPUs).  The model is left at the best parameters found.
+B200BO_API int32_t b200bo_map_fit(b200bo_handle_t h, const double* Theta0, int32_t P, int32_t R, int32_t mask, const double* lb, const double* ub,
+                                  int32_t maxeval, double ftol_rel, double ftol_abs, double xtol_rel, double xtol_abs, double maxtime,
+                                  double* theta_best, double* mll_best, int32_t* evals_out, int32_t* status_out) {
+  if (!h || !Theta0 || !lb || !ub || R < 1 || P < 1 || !theta_best) return fail(h, B200BO_ERR_ARG, "bad arguments to map_fit");
+  for (int k = 0; k < P; ++k) if (!(lb[k] <= ub[k])) return fail(h, B200BO_ERR_ARG, "lower bound above upper bound");
+  const int64_t B = lbfgs_state_doubles(P);
+  std::vector<double> state((size_t)R * B, 0.0), xe((size_t)R * P), f(R), g((size_t)R * P);
+  for (int r = 0; r < R; ++r)
+    for (int k = 0; k < P; ++k) xe[(size_t)r * P + k] = lb_clamp(Theta0[(size_t)r * P + k], lb[k], ub[k]);
+  LbfgsOpts o;
+  o.maxeval = maxeval; o.ftol_rel = ftol_rel; o.ftol_abs = ftol_abs; o.xtol_rel = xtol_rel; o.xtol_abs = xtol_abs; o.step0 = 0.02;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int cap = maxeval > 0 ? maxeval : 100000;
+  int rounds = 0;
+  for (; rounds < cap; ++rounds) {
+    int32_t rc = b200bo_mll_sweep(h, xe.data(), P, R, mask, f.data(), g.data());
+    if (rc == B200BO_ERR_NOTPD) {      // the reference's closure throws inside NLopt (FORCED_STOP): treat the point as infeasible
+      for (int r = 0; r < R; ++r) f[r] = -INFINITY;
+      std::fill(g.begin(), g.end(), 0.0);
+    } else if (rc) return rc;
+    int running = 0;
+    for (int r = 0; r < R; ++r) {
+      double* st = state.data() + (size_t)r * B;
+      lbfgs_step(st, xe.data() + (size_t)r * P, f[r], g.data() + (size_t)r * P, lb, ub, P, o);
+      if (LbfgsState(st, P).status() == 0.0) ++running;
+    }
+    if (running == 0) { ++rounds; break; }
+    if (maxtime > 0.0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= maxtime) { ++rounds; break; }
+  }
+  int bestr = 0;
+  for (int r = 1; r < R; ++r)
+    if (LbfgsState(state.data() + (size_t)r * B, P).f() > LbfgsState(state.data() + (size_t)bestr * B, P).f()) bestr = r;
+  LbfgsState sb(state.data() + (size_t)bestr * B, P);
+  memcpy(theta_best, sb.x, sizeof(double) * P);
+  if (mll_best) *mll_best = sb.f();
+  if (evals_out) *evals_out = (int32_t)sb.evals();
+  if (status_out) *status_out = (int32_t)sb.status();
+  // leave the model at the optimum (masked parameters only)
+  const bool m_noise = mask & B200BO_MASK_NOISE, m_mean = (mask & B200BO_MASK_MEAN) && h->mean_kind == B200BO_MEAN_CONST, m_kern = mask & B200BO_MASK_KERN;
+  const int np_full = num_params(h);
+  std::vector<double> th(np_full);
+  int32_t rc = b200bo_get_params(h, th.data(), np_full);
+  if (rc) return rc;
+  int i = 0, j = 0;
+  if (m_noise) th[i] = sb.x[j++];
+  ++i;
+  if (h->mean_kind == B200BO_MEAN_CONST) { if (m_mean) th[i] = sb.x[j++]; ++i; }
+  if (m_kern) for (; i < np_full; ++i) th[i] = sb.x[j++];
+  if (j != P) return fail(h, B200BO_ERR_ARG, "Theta0 has the wrong number of rows for this mask");
+  return b200bo_set_params(h, th.data(), np_full);
 }
 
 B200BO_API int32_t b200bo_predict(b200bo_handle_t h, const double* Xs, int64_t M, double* mu, double* var) {

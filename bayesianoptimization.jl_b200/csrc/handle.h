@@ -164,6 +164,10 @@ int nccl_init_rank(b200bo_handle_s* h, int world, int rank, const uint8_t* id128
 int nccl_init_all(const std::vector<b200bo_handle_s*>& reps, std::string* err);
 void nccl_destroy(b200bo_handle_s* h);
 void shard_bounds(int64_t total, int R, int r, int64_t* lo, int64_t* hi);
+struct LbfgsOpts;
+cudaError_t launch_sobol(b200bo_handle_s* h, double* dXs, unsigned long long index0, int64_t n, const double* d_lbub);
+cudaError_t launch_lbfgs(b200bo_handle_s* h, const AcqLaunch& base, double* dXe, double* dwork, const double* d_lbub, const LbfgsOpts& o,
+                         double maxtime_s, int* rounds_out);
 // peak.cu
 cudaError_t launch_dmma_peak(b200bo_handle_s* h, double* tflops);
 cudaError_t launch_i8_peak(b200bo_handle_s* h, double* tops);

@@ -6,7 +6,10 @@
 //    once per dimension (the LHS property), columns can be generated in any order / on any rank (sharding-invariant).
 //  * ascent_step_kernel: M projected-gradient ascents in lock-step on the fused value+gradient kernel -- what one NLopt run per
 //    restart does in the reference (src/acquisition.jl:59; box bounds :28-29), with a per-candidate adaptive step.
+#include <chrono>
 #include "common.cuh"
+#include "lbfgs.cuh"
+#include "sobol_dirs.cuh"
 #include "handle.h"
 
 namespace b200bo {
@@ -140,6 +143,89 @@ cudaError_t launch_ascent(b200bo_handle_s* h, const AcqLaunch& base, double* dX,
     argmax_values_kernel<<<1, 256, 0, h->stream>>>(Fb, M, base.idx_offset, base.dbest);
     h->launches++;
   }
+  return cudaGetLastError();
+}
+
+// ---- Sobol points on device (reference ScaledSobolIterator, src/utils.jl:64-87; EXT Sobol.jl, Joe-Kuo direction numbers) ---------------
+// point `index` of the unscrambled sequence in Gray-code order (index 0 = the origin, which Sobol.jl never emits: its k-th point is
+// index k), scaled to the box as next!(seq, lb, ub) does.  Stateless: any block of indices on any rank.
+__global__ void sobol_kernel(double* __restrict__ Xs, int D, unsigned long long index0, int64_t n, const double* __restrict__ lbub) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * D) return;
+  const int64_t j = e / D;
+  const int d = (int)(e - j * D);
+  const unsigned long long idx = index0 + (unsigned long long)j;
+  uint32_t gray = (uint32_t)(idx ^ (idx >> 1)), x = 0u;
+  for (int b = 0; gray; ++b, gray >>= 1)
+    if (gray & 1u) x ^= SOBOL_V[d][b];
+  const double u = (double)x * 2.3283064365386963e-10;         // / 2^32
+  const double lo = lbub[d], hi = lbub[D + d];
+  Xs[e] = __dadd_rn(lo, __dmul_rn(hi - lo, u));
+}
+
+cudaError_t launch_sobol(b200bo_handle_s* h, double* dXs, unsigned long long index0, int64_t n, const double* d_lbub) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t total = n * h->D;
+  sobol_kernel<<<(int)((total + 255) / 256), 256, 0, h->stream>>>(dXs, h->D, index0, n, d_lbub);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+// ---- M box-bounded L-BFGS ascents in lock-step (lbfgs.cuh): one thread per restart consumes the fused launch's value + gradient ----
+__global__ void lbfgs_step_kernel(double* __restrict__ state, double* __restrict__ Xe, const double* __restrict__ val, const double* __restrict__ grad,
+                                  const double* __restrict__ lbub, int D, int64_t M, LbfgsOpts o, int* __restrict__ running) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double* st = state + i * lbfgs_state_doubles(D);
+  lbfgs_step(st, Xe + i * D, val[i], grad + i * D, lbub, lbub + D, D, o);
+  if (LbfgsState(st, D).status() == 0.0) atomicAdd(running, 1);
+}
+
+__global__ void lbfgs_finish_kernel(double* __restrict__ state, double* __restrict__ Xe, double* __restrict__ val, double* __restrict__ evals, int D,
+                                    int64_t M) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  LbfgsState s(state + i * lbfgs_state_doubles(D), D);
+  for (int k = 0; k < D; ++k) Xe[i * D + k] = s.x[k];
+  val[i] = s.f();
+  if (evals) evals[i] = s.evals();
+}
+
+// dXe [M][D]: starts in, maximisers out; dwork: state [M][B] | val [M] | grad [M][D] | evals [M]; returns the number of rounds
+cudaError_t launch_lbfgs(b200bo_handle_s* h, const AcqLaunch& base, double* dXe, double* dwork, const double* d_lbub, const LbfgsOpts& o,
+                         double maxtime_s, int* rounds_out) {
+  const int64_t M = base.M, D = h->D, B = lbfgs_state_doubles((int)D);
+  double* state = dwork;
+  double* val = state + M * B;
+  double* grad = val + M;
+  double* evals = grad + M * D;
+  cudaError_t e = cudaMemsetAsync(state, 0, sizeof(double) * M * B, h->stream);
+  if (e != cudaSuccess) return e;
+  int* drun = h->dinfo + 3;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int cap = o.maxeval > 0 ? o.maxeval : 100000;
+  int rounds = 0;
+  for (; rounds < cap; ++rounds) {
+    AcqLaunch l = base;
+    l.dXs = dXe; l.dvalues = val; l.dgrad = grad; l.dmu = nullptr; l.dvar = nullptr; l.dbest = nullptr;
+    if ((e = launch_acquire(h, l)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(drun, 0, sizeof(int), h->stream)) != cudaSuccess) return e;
+    lbfgs_step_kernel<<<(int)((M + 127) / 128), 128, 0, h->stream>>>(state, dXe, val, grad, d_lbub, (int)D, M, o, drun);
+    h->launches++;
+    int running = 0;
+    if ((e = cudaMemcpyAsync(&running, drun, sizeof(int), cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return e;
+    if (running == 0) { ++rounds; break; }
+    if (maxtime_s > 0.0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= maxtime_s) { ++rounds; break; }   // NLopt maxtime
+  }
+  lbfgs_finish_kernel<<<(int)((M + 127) / 128), 128, 0, h->stream>>>(state, dXe, val, evals, (int)D, M);
+  h->launches++;
+  if (base.dvalues) cudaMemcpyAsync(base.dvalues, val, sizeof(double) * M, cudaMemcpyDeviceToDevice, h->stream);
+  if (base.dbest) {
+    argmax_values_kernel<<<1, 256, 0, h->stream>>>(val, M, base.idx_offset, base.dbest);
+    h->launches++;
+  }
+  if (rounds_out) *rounds_out = rounds;
   return cudaGetLastError();
 }
 

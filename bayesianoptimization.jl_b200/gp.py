@@ -272,6 +272,43 @@ class B200GPE:
                                      C.byref(best), dptr(bx)), self._h)
         return dict(best_value=best.value, best_index=best.index, best_x=bx, values=vals)
 
+    def sobol(self, lb, ub, index0: int, n: int) -> np.ndarray:
+        """points index0 .. index0+n-1 of the unscrambled Joe-Kuo Sobol sequence, generated on the device and scaled to [lb, ub]
+        (ScaledSobolIterator, src/utils.jl:64-87).  D x n."""
+        lb = np.ascontiguousarray(lb, float); ub = np.ascontiguousarray(ub, float)
+        out = np.empty((self.D, int(n)), order="F")
+        check(lib.b200bo_sobol(self._h, dptr(lb), dptr(ub), int(index0), int(n), dptr(out)), self._h)
+        return out
+
+    def acquire_lbfgs(self, kind: str, params, X, lb, ub, maxeval: int = 2000, ftol_rel: float = 0.0, ftol_abs: float = 0.0,
+                      xtol_rel: float = 0.0, xtol_abs: float = 0.0, maxtime: float = 0.0, step0: float = 0.02, idx_offset: int = 0):
+        """box-bounded L-BFGS ascents from ALL columns of X in lock-step on the fused value+gradient launch -- what the reference's
+        per-restart NLopt :LD_LBFGS run does (src/acquisition.jl:59), with its stopping options (:24-27)."""
+        Xs = self._cands(X)
+        M = Xs.shape[1]
+        lb = np.ascontiguousarray(lb, float); ub = np.ascontiguousarray(ub, float)
+        p = np.ascontiguousarray(params, float).ravel()
+        Xout = np.empty((self.D, M), order="F"); vals = np.empty(M); evals = np.empty(M)
+        best = _lib.Best(); bx = np.full(self.D, np.nan)
+        check(lib.b200bo_acquire_lbfgs(self._h, _lib.ACQ_KINDS[kind], dptr(p) if p.size else None, p.size, dptr(Xs), M, dptr(lb), dptr(ub),
+                                       int(maxeval), float(ftol_rel), float(ftol_abs), float(xtol_rel), float(xtol_abs), float(maxtime),
+                                       float(step0), idx_offset, dptr(Xout), dptr(vals), dptr(evals), C.byref(best), dptr(bx)), self._h)
+        return dict(X=Xout, values=vals, evals=evals.astype(int), best_value=best.value, best_index=best.index, best_x=bx)
+
+    def map_fit(self, theta0, lb, ub, noise=True, domean=True, kern=True, maxeval: int = 500, ftol_rel: float = 0.0, ftol_abs: float = 0.0,
+                xtol_rel: float = 0.0, xtol_abs: float = 0.0, maxtime: float = 0.0):
+        """optimizemodel!(::MAPGPOptimizer, model) (src/models/gp.jl:54-77) inside the library: L-BFGS ascent of mll over the selected
+        parameters within [lb, ub] from the columns of theta0 (P x R starts in lock-step).  Leaves the model at the optimum."""
+        T0 = np.asfortranarray(np.asarray(theta0, float))
+        T0 = T0.reshape(-1, 1) if T0.ndim == 1 else T0
+        P, R = T0.shape
+        lb = np.ascontiguousarray(lb, float); ub = np.ascontiguousarray(ub, float)
+        mask = (_lib.MASK_NOISE if noise else 0) | (_lib.MASK_MEAN if domean else 0) | (_lib.MASK_KERN if kern else 0)
+        th = np.empty(P); mll = C.c_double(); ev = C.c_int32(); st = C.c_int32()
+        check(lib.b200bo_map_fit(self._h, dptr(T0), P, R, mask, dptr(lb), dptr(ub), int(maxeval), float(ftol_rel), float(ftol_abs), float(xtol_rel),
+                                 float(xtol_abs), float(maxtime), dptr(th), C.byref(mll), C.byref(ev), C.byref(st)), self._h)
+        return dict(theta=th, mll=mll.value, evals=ev.value, status=st.value)
+
     def acquire_ascent(self, kind: str, params, X, lb, ub, steps: int = 20, step0: float = 0.05, idx_offset: int = 0):
         """M box-constrained gradient ascents in lock-step on the fused value+gradient kernel (acquisition.jl:59)."""
         Xs = self._cands(X)
@@ -402,8 +439,12 @@ def optimizemodel(o, model: B200GPE):
     return ret
 
 
+_NLOPT_STATUS = {3: "FTOL_REACHED", 4: "XTOL_REACHED", 5: "MAXEVAL_REACHED", 6: "STALLED", 0: "MAXTIME_REACHED"}
+
+
 def _map_fit(model: B200GPE, opts: dict):
-    from scipy.optimize import minimize
+    """the optimisation of optimizemodel! (gp.jl:54-77) runs inside the library (b200bo_map_fit): objective, gradient and the box-bounded
+    L-BFGS iteration; maxeval / ftol / xtol / maxtime are the NLopt options the reference forwards (gp.jl:72)."""
     if model.nobs == 0:
         return None
     sel = _mask_select(model, opts)
@@ -412,17 +453,7 @@ def _map_fit(model: B200GPE, opts: dict):
         raise ValueError("bounds do not match the number of optimised parameters")
     theta_full = model.get_params()
     x0 = np.clip(theta_full[sel], lb, ub)
-
-    def negf(x):
-        try:
-            mll, dmll = model.mll_sweep(x.reshape(-1, 1), noise=opts["noise"], domean=opts["domean"], kern=opts["kern"])
-        except _lib.B200BOError as e:       # not positive definite: the reference's closure throws -> FORCED_STOP
-            if e.code == _lib.ERR_NOTPD:
-                return np.inf, np.zeros_like(x)
-            raise
-        return -float(mll[0]), -dmll[:, 0]
-
-    res = minimize(negf, x0, jac=True, method="L-BFGS-B", bounds=list(zip(lb, ub)), options=dict(maxfun=int(opts["maxeval"])))
-    theta_full[sel] = res.x
-    model.set_params(theta_full)
-    return -float(res.fun), res.x, res.message
+    r = model.map_fit(x0, lb, ub, noise=opts["noise"], domean=opts["domean"], kern=opts["kern"], maxeval=int(opts["maxeval"]),
+                      ftol_rel=float(opts.get("ftol_rel", 0.0)), ftol_abs=float(opts.get("ftol_abs", 0.0)), xtol_rel=float(opts.get("xtol_rel", 0.0)),
+                      xtol_abs=float(opts.get("xtol_abs", 0.0)), maxtime=float(opts.get("maxtime", 0.0)))
+    return float(r["mll"]), r["theta"], _NLOPT_STATUS.get(r["status"], str(r["status"]))

@@ -167,6 +167,26 @@ B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t acq_kind, co
                                          int64_t idx_offset, double* Xout /*D x M or NULL*/, double* values /*M or NULL*/,
                                          b200bo_best_t* best, double* best_x /*D or NULL*/);
 
+/* b200bo_sobol: ScaledSobolIterator (src/utils.jl:64-87) on device: points index0 .. index0+n-1 of the unscrambled Joe-Kuo Sobol sequence
+ *   (index 0 = the origin, which EXT Sobol.jl never emits: its k-th point is index k; the reference's iterator starts at index
+ *   1 + 2^floor(log2(N+1)), utils.jl:80), scaled to [lb, ub].  D <= 32, indices below 2^32.
+ * b200bo_acquire_lbfgs: what NLopt :LD_LBFGS adds per restart (src/acquisition.jl:59) for ALL M starts at once: box-bounded L-BFGS ascents
+ *   in lock-step on the fused value + gradient launch, with the options the reference forwards (src/acquisition.jl:24-27): maxeval
+ *   (evaluations per start, <= 0 unlimited), ftol_rel / ftol_abs, xtol_rel / xtol_abs (0 disables), maxtime (seconds, <= 0 unlimited).
+ *   evals[M] (optional) = evaluations each start used.
+ * b200bo_map_fit: optimizemodel!(::MAPGPOptimizer, model) (src/models/gp.jl:54-77): L-BFGS ascent of mll over the masked parameters within
+ *   [lb, ub] (gp.jl:65-68) from R starts in lock-step (Theta0 P x R; R = 1 and Theta0 = current parameters is the reference's run);
+ *   every evaluation is a device refactorisation + gradient.  Leaves the model at the best parameters; status = NLopt's numbering
+ *   (3 FTOL_REACHED, 4 XTOL_REACHED, 5 MAXEVAL_REACHED, 6 = stalled). */
+B200BO_API int32_t b200bo_sobol(b200bo_handle_t h, const double* lb, const double* ub, uint64_t index0, int64_t n, double* Xs /* host, D x n */);
+B200BO_API int32_t b200bo_acquire_lbfgs(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params, const double* Xs, int64_t M,
+                                        const double* lb, const double* ub, int32_t maxeval, double ftol_rel, double ftol_abs, double xtol_rel,
+                                        double xtol_abs, double maxtime, double step0, int64_t idx_offset, double* Xout /*D x M or NULL*/,
+                                        double* values /*M or NULL*/, double* evals /*M or NULL*/, b200bo_best_t* best, double* best_x /*D or NULL*/);
+B200BO_API int32_t b200bo_map_fit(b200bo_handle_t h, const double* Theta0, int32_t P, int32_t R, int32_t mask, const double* lb, const double* ub,
+                                  int32_t maxeval, double ftol_rel, double ftol_abs, double xtol_rel, double xtol_abs, double maxtime,
+                                  double* theta_best /*P*/, double* mll_best, int32_t* evals, int32_t* status);
+
 /* -- introspection for benches / tests ----------------------------------------------------------------------- */
 B200BO_API int32_t b200bo_kmat(b200bo_handle_t h, double* K);         /* N x N Sigma = K + (e^{2 logNoise}+eps) I to host */
 B200BO_API int32_t b200bo_last_timing_ms(b200bo_handle_t h, int32_t which, float* ms);

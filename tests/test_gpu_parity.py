@@ -651,3 +651,78 @@ def test_cusolver_cublas_cross_check(bo):
         g.set_acq_engine(eng)
         m, v = g.predict(Xs)
         assert close(m, mu, 1e-9, 1e-12) and close(v, var, 1e-8, 1e-13), eng
+
+
+def test_device_sobol_matches_joe_kuo_and_the_reference_iterator(bo):
+    """b200bo_sobol (reference ScaledSobolIterator, src/utils.jl:64-87): bit-equal to the unscrambled Joe-Kuo sequence SciPy
+    and Sobol.jl ship, any block of indices; the reference iterator's points are the block starting at 1 + 2^floor(log2(N+1))."""
+    from scipy.stats import qmc
+    for D in (2, 8, 32):
+        g = bo.B200GPE(D, capacity=128)
+        lb = -np.arange(1.0, D + 1.0); ub = 2.0 + np.arange(D)
+        pts = g.sobol(lb, ub, 9, 700)
+        s = qmc.Sobol(D, scramble=False, bits=32); s.fast_forward(9)
+        u = s.random(700)
+        assert np.array_equal(pts, (lb + (ub - lb) * u).T), D
+    g = bo.B200GPE(2, capacity=128)
+    host = np.array(list(bo.ScaledSobolIterator([-5.0, 0.0], [10.0, 15.0], 10))).T
+    assert np.array_equal(g.sobol([-5.0, 0.0], [10.0, 15.0], 1 + 8, 10), host)
+    assert np.array_equal(g.sobol([0.0, 0.0], [1.0, 1.0], 1, 3), np.array([[0.5, 0.75, 0.25], [0.5, 0.25, 0.75]]))   # Sobol.jl's first points
+
+
+def test_batched_lbfgs_against_restatement_and_options(bo):
+    """b200bo_acquire_lbfgs: M box-bounded L-BFGS ascents in lock-step on the fused value+gradient launch, against the
+    plain-Python restatement of the same iteration driven by the oracle's value and gradient; NLopt-style options (reference
+    src/acquisition.jl:24-27): maxeval per start, ftol_rel stops early, iterates stay in the box, values never fall below the start."""
+    from oracle import lbfgs_oracle as lo
+    rng, o, g, X, y = make_pair(bo, "Mat52Ard", "MeanConst", 3, 220, seed=991)
+    lb, ub = np.zeros(3), np.ones(3)
+    M = 40
+    X0 = rng.random((3, M)); X0[:, 0] = [0.0, 1.0, 0.5]                       # one start on the boundary
+    tau = float(np.quantile(y, 0.8))
+    for kind, par in (("EI", (tau,)), ("UCB", (2.0,))):
+        f0 = g.acquire(kind, par, X0)["values"]
+        r = g.acquire_lbfgs(kind, par, X0, lb, ub, maxeval=60, ftol_rel=1e-10)
+        assert np.all(r["X"] >= 0.0) and np.all(r["X"] <= 1.0) and np.all(r["evals"] <= 60) and np.all(r["evals"] >= 1)
+        assert np.all(r["values"] >= f0 - 1e-15 * np.abs(f0))
+        assert np.mean(r["values"] > f0 + 1e-9 * np.abs(f0)) > 0.7                       # the ascent actually climbs
+        chk = g.acquire(kind, par, r["X"])["values"]
+        assert close(chk, r["values"], 1e-9)                                             # reported value = value at the reported point
+        assert r["best_index"] == orc.first_strict_argmax_np(r["values"]) and np.array_equal(r["best_x"], r["X"][:, r["best_index"]])
+        agree = 0
+        for j in range(M):
+            fg = lambda x: tuple(v[0] if np.ndim(v) == 1 else v[:, 0] for v in orc.acq_grad(o, kind, par, x.reshape(3, 1)))
+            ro = lo.maximize(fg, X0[:, j], lb, ub, maxeval=60, ftol_rel=1e-10)
+            agree += abs(ro.f - r["values"][j]) <= 1e-6 * abs(ro.f) + 1e-10
+        assert agree >= 0.8 * M                                                          # same trajectories up to accept/reject ties
+        few = g.acquire_lbfgs(kind, par, X0, lb, ub, maxeval=3)
+        assert np.all(few["evals"] <= 3) and np.all(few["values"] <= r["values"] + 1e-9 * np.abs(r["values"]) + 1e-12)
+    with pytest.raises(bo._lib.B200BOError):
+        g.acquire_lbfgs("TS", (), X0, lb, ub)                                            # derivative-free in the reference (acquisition.jl:7-9)
+
+
+def test_map_fit_in_library_matches_scipy_on_the_oracle(bo):
+    """b200bo_map_fit (reference optimizemodel!, src/models/gp.jl:54-77): box-bounded L-BFGS over the device mll + gradient,
+    bounds as `noisebounds` / `kernbounds` (gp.jl:65-68), against SciPy's L-BFGS-B on the oracle's objective from the same start."""
+    from scipy.optimize import minimize
+    rng, o, g, X, y = make_pair(bo, "SEArd", "MeanConst", 2, 160, seed=515)
+    th0 = g.get_params()
+    sel = np.array([0, 2, 3, 4])                                                         # noise + kernel; the mean stays (domean = false)
+    lbp, ubp = np.array([-4.0, -3.0, -3.0, -2.0]), np.array([1.0, 2.0, 2.0, 2.0])
+    r = g.map_fit(th0[sel], lbp, ubp, noise=True, domean=False, kern=True, maxeval=200, ftol_rel=1e-12)
+
+    def negf(x):
+        th = th0.copy(); th[sel] = x
+        f, gr = o.mll_dmll(th)
+        return -f, -gr[sel]
+    ref = minimize(negf, th0[sel], jac=True, method="L-BFGS-B", bounds=list(zip(lbp, ubp)), options=dict(ftol=1e-14, gtol=1e-9, maxfun=400))
+    assert r["status"] in (3, 4) and r["evals"] <= 200
+    assert r["mll"] >= -ref.fun - 1e-6 * abs(ref.fun)                                    # at least as good an optimum
+    assert np.all(r["theta"] >= lbp) and np.all(r["theta"] <= ubp)
+    if abs(r["mll"] + ref.fun) <= 1e-7 * abs(ref.fun):
+        assert np.allclose(r["theta"], ref.x, atol=2e-3)
+    th = g.get_params()
+    assert np.array_equal(th[sel], r["theta"]) and th[1] == th0[1]                       # the model sits at the optimum, mean untouched
+    assert abs(g.mll - r["mll"]) <= 1e-10 * abs(r["mll"])
+    three = g.map_fit(np.stack([th0[sel], th0[sel] + 0.3, th0[sel] - 0.3], axis=1), lbp, ubp, noise=True, domean=False, kern=True, maxeval=60)
+    assert three["mll"] >= r["mll"] - 1e-6 * abs(r["mll"])                               # restarts in lock-step never do worse

@@ -339,3 +339,26 @@ def test_explicit_inverse_sliced_product_keeps_posterior_accuracy():
         got = ozaki.posterior_var_i8(o.U.T.copy(), Ks, o.sf2)
         assert np.all(np.abs(got - vo) <= 1e-9 * np.abs(vo) + 1e-13), kern
         assert np.max(np.abs(got - vo)) < 2e-13 * o.sf2, kern
+
+
+def test_lbfgs_restatement_on_a_bounded_quadratic_and_options():
+    """oracle/lbfgs_oracle.py (the restatement of csrc/lbfgs.cuh): converges to the constrained maximiser, honours maxeval / ftol / xtol
+    the way NLopt counts them (reference src/acquisition.jl:24-27), never leaves the box, accepted values never decrease."""
+    from oracle import lbfgs_oracle as lo
+    rng = np.random.default_rng(3)
+    D = 6
+    A = rng.standard_normal((D, D)); A = A @ A.T + 0.5 * np.eye(D)
+    c = rng.standard_normal(D) * 0.7                      # some coordinates end on a bound, the others inside the box
+    fg = lambda x: (float(-0.5 * (x - c) @ A @ (x - c) - 0.05 * np.sum((x - c) ** 4)), -A @ (x - c) - 0.2 * (x - c) ** 3)
+    lb, ub = -np.ones(D), np.ones(D)
+    r = lo.maximize(fg, np.zeros(D), lb, ub, maxeval=500, ftol_rel=1e-14)
+    from scipy.optimize import minimize
+    ref = minimize(lambda x: (-fg(x)[0], -fg(x)[1]), np.zeros(D), jac=True, method="L-BFGS-B", bounds=list(zip(lb, ub)), options=dict(ftol=1e-15, gtol=1e-12))
+    assert np.all(r.x >= lb) and np.all(r.x <= ub) and r.status in (lo.FTOL, lo.XTOL)
+    assert abs(r.f + ref.fun) <= 1e-8 * abs(ref.fun) and np.allclose(r.x, ref.x, atol=1e-5)
+    r2 = lo.maximize(fg, np.zeros(D), lb, ub, maxeval=7)
+    assert r2.status == lo.MAXEVAL and r2.evals == 7 and r2.f <= r.f + 1e-12
+    r3 = lo.maximize(fg, np.zeros(D), lb, ub, maxeval=500, ftol_abs=1e-2)
+    assert r3.status == lo.FTOL and r3.evals <= r.evals and r3.f <= r.f + 1e-12
+    r4 = lo.maximize(fg, np.zeros(D), lb, ub, maxeval=500, xtol_abs=1e-3)
+    assert r4.status in (lo.XTOL, lo.FTOL) and r4.evals <= r.evals
