@@ -55,16 +55,18 @@ __device__ __forceinline__ uint4 gather_byte(const unsigned long long (&dg)[16],
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// ---- FP64 rows -> 7 int8 slices + per-row scale 2^(e-6).  One warp per row; tri != 0: only columns [0, 128 (row / 128 + 1)) exist. ----
+// ---- FP64 rows -> 7 int8 slices + per-row scale 2^(e-6).  One warp per row; tri = 1: only columns [0, 128 (row / 128 + 1)) exist (W = L^-1),
+//      tri = 2: only columns [128 (row / 128), ncols_full) exist (W^T); the other columns are never read by the products. ----
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ A, int64_t lda, int nrows, int ncols_full, int tri,
                                                          uint8_t* __restrict__ Sl, int64_t pitch, int64_t slice_stride,
                                                          double* __restrict__ Se) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= nrows) return;
-  const int ncols = tri ? (((row >> 7) + 1) << 7) : ncols_full;            // a multiple of 128
+  const int ncols = tri == 1 ? (((row >> 7) + 1) << 7) : ncols_full;       // a multiple of 128
+  const int clo = tri == 2 ? ((row >> 7) << 7) : 0;
   const double* src = A + (int64_t)row * lda;
   double m = 0.0;
-  for (int c = 2 * lane; c < ncols; c += 64) {
+  for (int c = clo + 2 * lane; c < ncols; c += 64) {
     const double2 v = *reinterpret_cast<const double2*>(src + c);
     m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
   }
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   const int e = (m > 0.0 && m < INFINITY) ? ilogb(m) + 1 : 0;             // |x| < 2^e
   const double sc = ldexp(1.0, 54 - e);                                   // |x sc| <= 2^54, an integer wherever x has the row's top exponent
-  for (int c0 = 16 * lane; c0 < ncols; c0 += 512) {
+  for (int c0 = clo + 16 * lane; c0 < ncols; c0 += 512) {
     unsigned long long dg[16];
 #pragma unroll
     for (int u = 0; u < 16; u += 2) {
@@ -166,23 +168,26 @@ __global__ void __launch_bounds__(256) kstar_slice_kernel(const KsArgs a) {
 struct A8Maps { CUtensorMap A, B; };   // A: k* slices [7][CH][Kp] in 128-row boxes, B: W or Sigma^-1 slices [7][cap][cap] in 64-row boxes
 
 // work items sorted by decreasing length (it descending), dealt to the CTAs in snake order so that every CTA gets the same mix
+template <int MODE>
 __device__ __forceinline__ bool a8_item(int r, int G, int b, int total, int nct, int nit, int& it, int& ct) {
   const int pos = r * G + ((r & 1) ? G - 1 - b : b);
   if (pos >= total) return false;
-  it = nit - 1 - pos / nct;
+  it = MODE == 2 ? pos / nct : nit - 1 - pos / nct;          // MODE 2 items get longer towards it = 0
   ct = pos - (pos / nct) * nct;
   return true;
 }
 
-// MODE 0: out = SsP[2 nit][CH], partial sums over 32 rows of (W k*)^2; k-blocks 0 .. it/2 (W is lower triangular)
-// MODE 1: out = WgT[Np][CH], w = Sigma^-1 k*; all k-blocks
+// MODE 0: out = SsP[2 nit][CH], partial sums over 32 rows of v^2, v = W k*; k-blocks 0 .. it/2 (W is lower triangular).  With `vs` the
+//         epilogue also slices v (fixed scale 2^ev >= 2 sigma_f) into vs[7][CH][Kp]: the A operand of the gradient's second product
+// MODE 1: out = WgT[Np][CH], w = Sigma^-1 k* from the slices of Sigma^-1; all k-blocks (kept for reference; MODE 2 does half the work)
+// MODE 2: out = WgT[Np][CH], w = W^T v from the slices of v and of W^T; k-blocks it/2 .. nkb_full-1 (W^T is upper triangular)
 // TS: the k* slices reach the MMAs through tensor memory (tcgen05.cp into two 32-column buffers behind the accumulators) instead of
 // being re-read from shared memory by each of the up to 7 MMAs per k-step that use them: the shared-memory port (128 B/clk), which
 // bounds the SS form at 840 KB per k-block, carries 504 KB.
 template <int MODE, bool TS>
 __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double* __restrict__ Be, double sBk, int nct, int nit, int nkb_full,
-                                                                     int64_t CH, double* __restrict__ out,
-                                                                     const __grid_constant__ A8Maps maps) {
+                                                                     int64_t CH, double* __restrict__ out, uint8_t* __restrict__ vs, int64_t Kp,
+                                                                     double vq, const __grid_constant__ A8Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sB = smem_raw;                                     // [2][7 slices][64 rows x 128 B]: W / Sigma^-1, double buffered per k-block
   uint8_t* sA = smem_raw + 2 * A8_S * A8_B_BYTES;             // [7 slices][128 rows x 128 B]: k*, stage p = slice p of the current k-block
@@ -214,10 +219,10 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
       tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B);
       uint32_t kcnt = 0;                                      // k-blocks so far: B buffer kcnt & 1, phase of every A stage kcnt & 1
       int it, ct;
-      for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
+      for (int r = 0; a8_item<MODE>(r, G, b, total, nct, nit, it, ct); ++r) {
         const int arow = ct * A8_BM, brow = it * A8_BN;
-        const int nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
-        for (int kb = 0; kb < nkb; ++kb, ++kcnt) {
+        const int kb0 = MODE == 2 ? it / 2 : 0, nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
+        for (int kb = kb0; kb < nkb; ++kb, ++kcnt) {
           const int bs = kcnt & 1;
           mbar_wait_or_trap(&bempty[bs], ((kcnt >> 1) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&bfull[bs], A8_S * A8_B_BYTES);
@@ -246,15 +251,15 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
 #define A8_TIMED(acc_, stmt) do { stmt; } while (0)
 #define A8_EXTRA(P)
 #endif
-      for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
-        const int nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
+      for (int r = 0; a8_item<MODE>(r, G, b, total, nct, nit, it, ct); ++r) {
+        const int kb0 = MODE == 2 ? it / 2 : 0, nkb = MODE == 0 ? it / 2 + 1 : nkb_full;
 #ifdef A8_PROF
         ++nitems;
 #endif
         A8_TIMED(w_t, mbar_wait_or_trap(tempty, ((uint32_t)r & 1u) ^ 1u));   // the epilogue has read the previous item's accumulators
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        for (int kb = 0; kb < nkb; ++kb, ++kcnt) {
-          const uint32_t bs = kcnt & 1u, aph = kcnt & 1u, acc = kb > 0;
+        for (int kb = kb0; kb < nkb; ++kb, ++kcnt) {
+          const uint32_t bs = kcnt & 1u, aph = kcnt & 1u, acc = kb > kb0;
           const uint64_t db = dB0 + (uint64_t)(bs * ((A8_S * A8_B_BYTES) >> 4));
           A8_TIMED(w_b, mbar_wait_or_trap(&bfull[bs], (kcnt >> 1) & 1u));
           // slice p of k*: one asm block issues its 4 (7 - p) MMAs (umma_issue.cuh); tcgen05.commit frees the stage behind them
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
     const int g4 = warp & 3, half = (warp - 2) >> 2;
     const int m = 32 * g4 + lane;
     int it, ct;
-    for (int r = 0; a8_item(r, G, b, total, nct, nit, it, ct); ++r) {
+    for (int r = 0; a8_item<MODE>(r, G, b, total, nct, nit, it, ct); ++r) {
       const int brow = it * A8_BN + 32 * half;
       mbar_wait_or_trap(tfull, (uint32_t)r & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -317,10 +322,21 @@ __global__ void __launch_bounds__(A8_THREADS, 1) acq_i8_gemm_kernel(const double
         double ss = 0.0;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const double v = acc[c] * (sBk * __ldg(Be + brow + c));
-          ss = fma(v, v, ss);
+          acc[c] *= sBk * __ldg(Be + brow + c);
+          ss = fma(acc[c], acc[c], ss);
         }
         out[(int64_t)(2 * it + half) * CH + (int64_t)ct * A8_BM + m] = ss;
+        if (vs) {                                             // v -> 7 int8 slices, 32 consecutive rows of W = 32 bytes per slice
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            unsigned long long dg[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) dg[u] = i8_digits(__double2ll_rn(acc[16 * hh + u] * vq));
+#pragma unroll
+            for (int s = 0; s < A8_S; ++s)
+              *reinterpret_cast<uint4*>(vs + ((int64_t)s * CH + (int64_t)ct * A8_BM + m) * Kp + brow + 16 * hh) = gather_byte(dg, 6 - s);
+          }
+        }
       } else {
 #pragma unroll
         for (int c = 0; c < 32; ++c) __stcs(out + (int64_t)(brow + c) * CH + (int64_t)ct * A8_BM + m, acc[c] * (sBk * __ldg(Be + brow + c)));   // read once, by the gradient pass
@@ -506,21 +522,24 @@ static cudaError_t ensure_slices(b200bo_handle_s* h, bool want_grad) {
     }
     e = launch_linv(h);                                       // W row-major in h->dKi, W^T in h->dWT
     if (e != cudaSuccess) return e;
+    h->wt_valid = true;
     slice_rows_kernel<<<(Np + 7) / 8, 256, 0, h->stream>>>(h->dKi, h->ld, Np, Np, 1, reinterpret_cast<uint8_t*>(h->dWs), cap, cap * cap, h->dWe);
     h->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     h->acq_ready = 1;
   }
-  if (want_grad && !(h->acq_ready & 2)) {
+  if (want_grad && !(h->acq_ready & 2)) {                      // the gradient's second product w = W^T v needs the rows of W^T
     if (!h->dKs) {
       e = cudaMalloc(&h->dKs, (size_t)A8_S * cap * cap);
       if (e == cudaSuccess) e = cudaMalloc(&h->dKe, sizeof(double) * cap);
       if (e == cudaSuccess) e = make_map3d_u8(&h->tmKsB, h->dKs, (uint64_t)cap, (uint64_t)cap, A8_S, 128, A8_BN);
       if (e != cudaSuccess) { cudaFree(h->dKs); cudaFree(h->dKe); h->dKs = nullptr; h->dKe = nullptr; return e; }
     }
-    e = launch_kinv_syrk(h);                                  // Sigma^-1 = W^T W into h->dKi (W itself is no longer needed: it is sliced)
-    if (e != cudaSuccess) return e;
-    slice_rows_kernel<<<(Np + 7) / 8, 256, 0, h->stream>>>(h->dKi, h->ld, Np, Np, 0, reinterpret_cast<uint8_t*>(h->dKs), cap, cap * cap, h->dKe);
+    if (!h->wt_valid) {                                       // W^T was overwritten (a MAP sweep ran on these buffers): rebuild it
+      if ((e = launch_linv(h)) != cudaSuccess) return e;
+      h->wt_valid = true;
+    }
+    slice_rows_kernel<<<(Np + 7) / 8, 256, 0, h->stream>>>(h->dWT, h->ld, Np, Np, 2, reinterpret_cast<uint8_t*>(h->dKs), cap, cap * cap, h->dKe);
     h->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     h->acq_ready |= 2;
@@ -533,16 +552,18 @@ static cudaError_t ensure_slices(b200bo_handle_s* h, bool want_grad) {
 static cudaError_t ensure_chunk_buffers(b200bo_handle_s* h, int64_t CH, bool want_grad, int64_t nblocks) {
   const int64_t Np = std::max<int64_t>(h->Np, NB);
   cudaError_t e = cudaSuccess;
-  const size_t lane_bs = (size_t)A8_S * CH * Np;
-  if (2 * lane_bs > h->bs_bytes) {
+  const size_t lane_bs = (size_t)A8_S * CH * Np;              // per lane: k* slices, and behind them (gradient) the slices of v
+  const size_t need_bs = (want_grad ? 4 : 2) * lane_bs;
+  if (need_bs > h->bs_bytes) {
     cudaFree(h->dBs); h->dBs = nullptr; h->bs_bytes = 0; h->bs_np = 0;
-    if ((e = cudaMalloc(&h->dBs, 2 * lane_bs)) != cudaSuccess) return e;
-    h->bs_bytes = 2 * lane_bs;
+    if ((e = cudaMalloc(&h->dBs, need_bs)) != cudaSuccess) return e;
+    h->bs_bytes = need_bs;
   }
-  if (h->bs_np != Np || h->bs_ch != CH) {
-    for (int ln = 0; ln < 2; ++ln)
+  if (h->bs_np != Np || h->bs_ch != CH || (want_grad && !h->bs_grad)) {
+    const int nmaps = h->bs_bytes >= 4 * lane_bs ? 4 : 2;
+    for (int ln = 0; ln < nmaps; ++ln)
       if ((e = make_map3d_u8(&h->tmBsA[ln], static_cast<uint8_t*>(h->dBs) + ln * lane_bs, (uint64_t)Np, (uint64_t)CH, A8_S, 128, A8_BM)) != cudaSuccess) return e;
-    h->bs_np = Np; h->bs_ch = CH;
+    h->bs_np = Np; h->bs_ch = CH; h->bs_grad = nmaps == 4;
   }
   const size_t need_p = 2 * sizeof(double) * (size_t)CH * (size_t)(Np / NB + Np / 32 + 2);
   if (need_p > h->part_bytes) {
@@ -631,13 +652,16 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
   int e2 = 0;
   frexp(sf2, &e2);                                            // sf2 = f 2^e2, f in [0.5, 1): the fixed scale of k* is S = 2^e2 > sf2
   const double qscale = ldexp(1.0, 54 - e2), sBk = ldexp(1.0, e2 - 6);
+  int ev = 0;
+  frexp(sqrt(sf2), &ev);                                      // |v_i| <= sigma_f < 2^ev: the slices of v use the fixed scale 2^(ev+1)
+  const double vq = ldexp(1.0, 54 - (ev + 1)), sVk = ldexp(1.0, ev + 1 - 6);
   static const bool ts = getenv("B200BO_ACQ_TS") && atoi(getenv("B200BO_ACQ_TS")) == 1;   // developer knob: 1 = A through tensor memory (measured slower: the tcgen05.cp copies cost more than the A-collector reuse saves)
   const bool one_lane = h->acq_lanes == 1 || h->acq_time_gemm;
   h->gemm_ev_used = 0;
   cudaFuncSetAttribute(acq_i8_gemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
-  cudaFuncSetAttribute(acq_i8_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  cudaFuncSetAttribute(acq_i8_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
   cudaFuncSetAttribute(acq_i8_gemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
-  cudaFuncSetAttribute(acq_i8_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
+  cudaFuncSetAttribute(acq_i8_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A8_SMEM);
   const bool two = nchunks > 1 && !one_lane && h->stream2 != nullptr;
   cudaStream_t lanes[2] = {h->stream, two ? h->stream2 : h->stream};
   if (two) {                                                  // lane 1 starts behind everything already queued on the handle's stream
@@ -650,6 +674,7 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
     const int ln = two ? (int)(ci & 1) : 0;
     cudaStream_t st = lanes[ln];
     uint8_t* dBs = static_cast<uint8_t*>(h->dBs) + ln * lane_bs;
+    uint8_t* dVs = want_grad ? static_cast<uint8_t*>(h->dBs) + (2 + ln) * lane_bs : nullptr;
     double* dMuP = h->dMuP + ln * lane_p;
     double* dSsP = dMuP + (size_t)CH * (size_t)(Npb / NB);
     double* dAmu = dSsP + (size_t)CH * (size_t)(Npb / 32);
@@ -657,7 +682,7 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
     double* dWg = want_grad ? h->dWg + ln * lane_w : nullptr;
     A8Maps mapsW, mapsK;
     mapsW.A = h->tmBsA[ln]; mapsW.B = h->tmWsB;
-    mapsK.A = h->tmBsA[ln]; mapsK.B = h->tmKsB;
+    mapsK.A = h->tmBsA[want_grad ? 2 + ln : ln]; mapsK.B = h->tmKsB;        // A = slices of v, B = slices of W^T
     const int64_t mc = std::min<int64_t>(CH, M - c0);
     const int64_t mcp = (mc + 127) / 128 * 128;
     const int nct = (int)(mcp / A8_BM);
@@ -676,8 +701,8 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
       const int total = nct * nit;
       const int grid = std::min(total, h->num_sms);
       gemm_event(h, st);
-      if (ts) acq_i8_gemm_kernel<0, true><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
-      else acq_i8_gemm_kernel<0, false><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, mapsW);
+      if (ts) acq_i8_gemm_kernel<0, true><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, dVs, Np, vq, mapsW);
+      else acq_i8_gemm_kernel<0, false><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dWe, sBk, nct, nit, nblk, CH, dSsP, dVs, Np, vq, mapsW);
       gemm_event(h, st);
       h->launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -700,8 +725,8 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
       const int total = nct * nit;
       const int grid = std::min(total, h->num_sms);
       gemm_event(h, st);
-      if (ts) acq_i8_gemm_kernel<1, true><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dKe, sBk, nct, nit, nblk, CH, dWg, mapsK);
-      else acq_i8_gemm_kernel<1, false><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dKe, sBk, nct, nit, nblk, CH, dWg, mapsK);
+      if (ts) acq_i8_gemm_kernel<2, true><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dKe, sVk, nct, nit, nblk, CH, dWg, nullptr, Np, 0.0, mapsK);
+      else acq_i8_gemm_kernel<2, false><<<grid, A8_THREADS, A8_SMEM, st>>>(h->dKe, sVk, nct, nit, nblk, CH, dWg, nullptr, Np, 0.0, mapsK);
       gemm_event(h, st);
       h->launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;

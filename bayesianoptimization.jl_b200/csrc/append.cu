@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) append_finish_kernel(double* __restrict__
   }
 }
 
-cudaError_t launch_append_one(b200bo_handle_s* h, double noise) {
+cudaError_t launch_append_one(b200bo_handle_s* h, double noise, bool last) {
   // preconditions (capi.cu): x_new / y_new already at row N of dX / dZ / dy; h->N is still the OLD count, factor valid
   const int N = (int)h->N, D = h->D;
   const double sf2 = exp(2.0 * h->hp.lsigma);
@@ -115,6 +115,7 @@ cudaError_t launch_append_one(b200bo_handle_s* h, double noise) {
   h->launches++;
   h->N = N + 1;
   h->Np = Np;
+  if (!last) return cudaGetLastError();            // alpha and the log-determinant are refreshed once, behind the last point of a batch
   e = launch_backward_solve(h, h->dz, h->dw, h->dalpha, Np / NB);
   if (e != cudaSuccess) return e;
   return launch_logdet_dot(h);

@@ -44,7 +44,7 @@ void free_device(b200bo_handle_s* h) {
   cudaFree(h->dcta_best); cudaFree(h->dbest); cudaFree(h->dpart);
   cudaFree(h->dWs); cudaFree(h->dKs); cudaFree(h->dBs); cudaFree(h->dWe); cudaFree(h->dKe); cudaFree(h->dMuP); cudaFree(h->dWg); cudaFree(h->dcta_best2);
   h->dWs = h->dKs = h->dBs = nullptr; h->dWe = h->dKe = h->dMuP = h->dWg = nullptr; h->dcta_best2 = nullptr;
-  h->bs_bytes = h->part_bytes = h->wg_bytes = 0; h->bs_np = h->bs_ch = h->nbest2 = 0; h->acq_ready = 0;
+  h->bs_bytes = h->part_bytes = h->wg_bytes = 0; h->bs_np = h->bs_ch = h->nbest2 = 0; h->acq_ready = 0; h->bs_grad = false; h->wt_valid = false;
   h->dz = nullptr; h->dflags = nullptr; h->dKi = h->dWT = h->dTT = nullptr; h->dSl = nullptr; h->dSe = nullptr;
   h->dX = h->dZ = h->dZk = h->dy = h->dw = h->dalpha = h->dinv_ell = h->dL = h->dLinv = h->dLinvT = h->dV = h->dscal = h->dpart = nullptr;
   h->dinfo = nullptr; h->dcta_best = nullptr; h->dbest = nullptr;
@@ -131,6 +131,7 @@ int32_t upload_data(b200bo_handle_s* h);
 int32_t refit(b200bo_handle_s* h) {
   h->jitter = 0;
   h->acq_ready = 0;                     // W = L^-1 and its int8 slices (acq_i8.cu) belong to the previous factor
+  h->wt_valid = false;
   if (h->need_upload) { const int32_t rc = upload_data(h); if (rc) return rc; }
   if (h->N == 0) { h->fitted = true; h->mll = 0.0; h->Np = 0; return B200BO_OK; }
   std::vector<double> ie;
@@ -441,25 +442,25 @@ B200BO_API int32_t b200bo_fit(b200bo_handle_t h, const double* X, const double* 
   return refit(h);
 }
 
-// one elastic step per new point; *ok = false when positive definiteness is lost (the caller refactors with the jitter rule)
+// elastic append of m points (EXT ElasticPDMats append!, reached from src/models/gp.jl:11; `repetitions` columns at
+// src/BayesianOptimization.jl:194-196): ONE enqueue -- per point the new factor row (forward solve), pivot and block-inverse row; alpha
+// and the log-determinant once behind the last point -- and ONE synchronisation.  *ok = false when positive definiteness was lost on
+// the way (the caller refactors with the jitter rule).
 static int32_t append_elastic(b200bo_handle_t h, const double* Xn, const double* yn, int64_t m, bool* ok) {
-  const int64_t D = h->D;
+  const int64_t D = h->D, N0 = h->N;
   *ok = true;
-  for (int64_t j = 0; j < m && *ok; ++j) {
-    const int64_t N = h->N;
-    CU(cudaMemcpyAsync(h->dX + N * D, Xn + j * D, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->dy + N, yn + j, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CU(launch_scale_inputs(h, N, N + 1));
-    CU(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
-    CU(launch_append_one(h, h->noise_total));          // advances h->N / h->Np
-    int info = 0;
-    double sc[2];
-    CU(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(sc, h->dscal, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    if (info != 0) *ok = false;
-    else h->mll = -0.5 * (sc[1] + sc[0] + (double)h->N * 1.8378770664093453);
-  }
+  CU(cudaMemcpyAsync(h->dX + N0 * D, Xn, sizeof(double) * m * D, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->dy + N0, yn, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+  CU(launch_scale_inputs(h, N0, N0 + m));
+  CU(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
+  for (int64_t j = 0; j < m; ++j) CU(launch_append_one(h, h->noise_total, j == m - 1));          // advances h->N / h->Np
+  int info = 0;
+  double sc[2];
+  CU(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(sc, h->dscal, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (info != 0) *ok = false;
+  else h->mll = -0.5 * (sc[1] + sc[0] + (double)h->N * 1.8378770664093453);
   return B200BO_OK;
 }
 
@@ -492,13 +493,13 @@ B200BO_API int32_t b200bo_append(b200bo_handle_t h, const double* Xn, const doub
       h->N = N0;
       h->need_upload = true;
       h->fitted = false;
-      h->acq_ready = 0;
+      h->acq_ready = 0; h->wt_valid = false;
       return rc;
     }
     if (ok) {
       h->hX.insert(h->hX.end(), Xn, Xn + m * D);
       h->hy.insert(h->hy.end(), yn, yn + m);
-      h->acq_ready = 0;
+      h->acq_ready = 0; h->wt_valid = false;     // the factor grew: W = L^-1 and its slices are rebuilt by the next acquisition
       return B200BO_OK;
     }
   }

@@ -58,7 +58,8 @@ struct b200bo_handle_s {
   b200bo_best_t* dcta_best2 = nullptr;
   size_t bs_bytes = 0, part_bytes = 0, wg_bytes = 0;
   int64_t bs_np = 0, bs_ch = 0, nbest2 = 0;
-  CUtensorMap tmWsB, tmKsB, tmBsA[2];
+  CUtensorMap tmWsB, tmKsB, tmBsA[4];   // tmBsA: k* slices of the two lanes, then the v slices of the two lanes
+  bool bs_grad = false, wt_valid = false;   // v-slice buffers / maps exist; h->dWT holds W^T of the CURRENT factor
   cudaEvent_t acq_ev[2] = {nullptr, nullptr};   // fork / join of the two chunk lanes
   int acq_lanes = 2;         // chunk lanes of the tcgen05 acquisition path (1: everything on the handle's stream)
   int64_t acq_chunk_mb = 0;  // 0: default L2 budget per chunk
@@ -132,7 +133,7 @@ cudaError_t launch_forward_solve(b200bo_handle_s* h, double* w, double* z, int n
 cudaError_t launch_backward_solve(b200bo_handle_s* h, const double* z, double* w, double* alpha, int nblk);
 cudaError_t launch_logdet_dot(b200bo_handle_s* h);
 // append.cu
-cudaError_t launch_append_one(b200bo_handle_s* h, double noise);
+cudaError_t launch_append_one(b200bo_handle_s* h, double noise, bool last);
 // acq.cu
 struct AcqLaunch {
   int acq_kind = -1;         // -1: predict only

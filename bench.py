@@ -156,11 +156,11 @@ def run_reference(args, w):
 
 def roofline_i8(w, M, gemm_ms, step_ms, peak_i8, peak_fp64, peaks, traffic):
     """dominant kernel = acq_i8_gemm_kernel (tcgen05.mma kind::i8).  Algorithmic work per candidate (DESIGN.md 4, K6): the value path is
-    W k* over the lower triangle = N^2/2 multiply-adds per slice product x 28 products (p + q <= 6) = 28 N^2 int8 ops (2 per MAC); a
-    gradient launch adds the full product Sigma^-1 k* = 56 N^2."""
+    v = W k* over the lower triangle = N^2/2 multiply-adds per slice product x 28 products (p + q <= 6) = 28 N^2 int8 ops (2 per MAC); a
+    gradient launch adds the second triangular product w = W^T v, another 28 N^2."""
     N = float(w["N"])
-    ops = 28.0 * N * N + (56.0 * N * N if w["grad"] else 0.0)
-    fp64_flops = N * N + (2.0 * N * N if w["grad"] else 0.0)
+    ops = 28.0 * N * N * (2.0 if w["grad"] else 1.0)
+    fp64_flops = N * N * (2.0 if w["grad"] else 1.0)
     ach = ops * M / (gemm_ms * 1e-3) * 1e-12
     bf16 = peaks.get("bf16_tflops")
     return {"kernel": "acq_i8_gemm_kernel (tcgen05.mma.cta_group::1.kind::i8, 128x64x32, TMEM accumulators)", "bound": "tensor",
