@@ -99,7 +99,7 @@ struct KsArgs {
   double sf2, qscale;           // qscale = 2^54 / S, S = the fixed power-of-two scale of k*
 };
 
-template <int FAM, int DP>
+template <int FAM, int DP, bool WG>      // WG: also write sf2 psi (gradient launches); a template flag keeps the value path at 70 registers
 __global__ void __launch_bounds__(256) kstar_slice_kernel(const KsArgs a) {
   extern __shared__ __align__(16) uint8_t ks_smem[];
   double* zx = reinterpret_cast<double*>(ks_smem);            // [128][DP]
@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(256) kstar_slice_kernel(const KsArgs a) {
       }
       const bool live = jb * 128 + j0 + j < a.N;
       double phi, psi = 0.0;
-      if (a.G) kern_phi_psi<FAM>(r2, phi, psi); else phi = kern_phi<FAM>(r2);      // the same phi either way, bit for bit
+      if (WG) kern_phi_psi<FAM>(r2, phi, psi); else phi = kern_phi<FAM>(r2);       // the same phi either way, bit for bit
       const double ks = live ? a.sf2 * phi : 0.0;
-      if (a.G) __stcs(a.G + ((int64_t)jb * 128 + j0 + j) * a.CH + t0 + n, live ? a.sf2 * psi : 0.0);
+      if (WG) __stcs(a.G + ((int64_t)jb * 128 + j0 + j) * a.CH + t0 + n, live ? a.sf2 * psi : 0.0);
       mu = fma(alb[j0 + j], ks, mu);
       dg[j] = i8_digits(__double2ll_rn(ks * a.qscale));
     }
@@ -595,10 +595,15 @@ static cudaError_t launch_kstar(b200bo_handle_s* h, cudaStream_t st, const KsArg
   const int DP = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
   const size_t smem = sizeof(double) * (128 * DP + 128 + 8 * 64) + A8_S * 64 * 128;
   const dim3 grid(nblk, ntile64);
-#define B200BO_KS(DPV)                                                                                              \
-  do {                                                                                                              \
-    cudaFuncSetAttribute(kstar_slice_kernel<FAM, DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-    kstar_slice_kernel<FAM, DPV><<<grid, 256, smem, st>>>(a);                                                \
+#define B200BO_KS(DPV)                                                                                                     \
+  do {                                                                                                                     \
+    if (a.G) {                                                                                                             \
+      cudaFuncSetAttribute(kstar_slice_kernel<FAM, DPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+      kstar_slice_kernel<FAM, DPV, true><<<grid, 256, smem, st>>>(a);                                                      \
+    } else {                                                                                                               \
+      cudaFuncSetAttribute(kstar_slice_kernel<FAM, DPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+      kstar_slice_kernel<FAM, DPV, false><<<grid, 256, smem, st>>>(a);                                                     \
+    }                                                                                                                      \
   } while (0)
   if (DP == 4) B200BO_KS(4); else if (DP == 8) B200BO_KS(8); else if (DP == 16) B200BO_KS(16); else B200BO_KS(32);
 #undef B200BO_KS

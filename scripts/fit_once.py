@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import b200bo
 from b200bo import _lib
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-D = 8
+D = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 rng = np.random.default_rng(0)
 X = rng.random((D, N)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N)
 g = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.0), kernel=b200bo.SEArd(np.full(D, np.log(np.sqrt(D) * 0.25)), 0.0), logNoise=-2.0, capacity=N)
