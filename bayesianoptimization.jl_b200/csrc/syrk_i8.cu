@@ -26,9 +26,9 @@ namespace b200bo {
 constexpr int I8_S = 7;                 // slices per FP64 value
 constexpr int I8_K = 512;               // bytes of K per slice row = columns of one outer panel
 constexpr int I8_BM = 128, I8_BN = 64;
-constexpr int I8_ASTAGES = 4;            // A ring of the 128-wide two-pass variant
+constexpr int I8_ASTAGES = 4;
 constexpr uint32_t I8_A_BYTES = I8_BM * 128, I8_B_BYTES = I8_BN * 128;
-constexpr size_t I8_SMEM = 2 * I8_S * I8_B_BYTES + I8_S * I8_A_BYTES + 1024;     // B double buffered per k-block, A one stage per slice
+constexpr size_t I8_SMEM = 2 * I8_S * I8_B_BYTES + I8_ASTAGES * I8_A_BYTES + 1024;
 constexpr int I8_THREADS = 320;          // producer warp, MMA warp, 8 epilogue warps
 
 // ---- FP64 panel rows -> 8 int8 slices + scale.  One warp per row, 16 consecutive columns per lane. ----
@@ -89,16 +89,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
                                                                 int col2_lo, int col2_hi, int nblk, int ntiles, int nkb,
                                                                 const __grid_constant__ I8Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* sB = smem_raw;                                     // [2][7 slices][64 rows x 128 B], double buffered per k-block
-  uint8_t* sA = smem_raw + 2 * I8_S * I8_B_BYTES;             // [7 slices][128 rows x 128 B]: stage p = slice p of the current k-block
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + I8_S * I8_A_BYTES);
-  uint64_t *afull = bars, *aempty = bars + 3, *bfull = bars + 6, *bempty = bars + 8, *tfull = bars + 10, *tempty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint8_t* sB = smem_raw;                                     // [2][8 slices][64 rows x 128 B]
+  uint8_t* sA = smem_raw + 2 * I8_S * I8_B_BYTES;             // [4][128 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + I8_ASTAGES * I8_A_BYTES);
+  uint64_t *afull = bars, *aempty = bars + 4, *bfull = bars + 8, *bempty = bars + 10, *tfull = bars + 12, *tempty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    for (int s = 0; s < 3; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }     // slices {0,1}, {2,3}, {4,5,6}
+    for (int s = 0; s < 4; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 8);                                     // one arrival per epilogue warp
@@ -116,20 +116,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
   if (warp == 0) {
     if (elect_one()) {                                        // ===== TMA producer =====
       tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B);
-      uint32_t kcnt = 0;                                      // k-blocks so far: B buffer kcnt & 1, phase of every A group kcnt & 1
+      int as = 0; uint32_t aph = 0, bcnt = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int bi, c2; i8_tile(tile, bi_lo, col2_lo, col2_hi, nblk, bi, c2);
         const int arow = bi * I8_BM, brow = c2 * I8_BN;
-        for (int kb = 0; kb < nkb; ++kb, ++kcnt) {
-          const int bs = kcnt & 1;
-          mbar_wait_or_trap(&bempty[bs], ((kcnt >> 1) & 1u) ^ 1u);
+        for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
+          const int bs = bcnt & 1;
+          mbar_wait_or_trap(&bempty[bs], ((bcnt >> 1) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&bfull[bs], I8_S * I8_B_BYTES);
           for (int q = 0; q < I8_S; ++q) tma_load_3d(sB + (bs * I8_S + q) * I8_B_BYTES, &maps.B, &bfull[bs], kb * 128, brow, q);
-          for (int g = 0; g < 3; ++g) {
-            const int p0 = 2 * g, p1 = g == 2 ? I8_S : 2 * g + 2;
-            mbar_wait_or_trap(&aempty[g], (kcnt & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&afull[g], (uint32_t)(p1 - p0) * I8_A_BYTES);
-            for (int p = p0; p < p1; ++p) tma_load_3d(sA + p * I8_A_BYTES, &maps.A, &afull[g], kb * 128, arow, p);
+          for (int p = 0; p < I8_S; ++p) {
+            mbar_wait_or_trap(&aempty[as], aph ^ 1u);
+            mbar_arrive_expect_tx(&afull[as], I8_A_BYTES);
+            tma_load_3d(sA + as * I8_A_BYTES, &maps.A, &afull[as], kb * 128, arow, p);
+            if (++as == I8_ASTAGES) { as = 0; aph ^= 1u; }
           }
         }
       }
@@ -138,26 +138,35 @@ __global__ void __launch_bounds__(I8_THREADS, 1) syrk_i8_kernel(double* __restri
     if (elect_one()) {                                        // ===== MMA issuer =====
       // D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
-      const uint64_t dA0 = umma_desc_sw128(smem_u32(sA)), dB0 = umma_desc_sw128(smem_u32(sB));
-      uint32_t kcnt = 0, it = 0;
+      int as = 0; uint32_t aph = 0, bcnt = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         mbar_wait_or_trap(tempty, (it & 1u) ^ 1u);            // the epilogue has read the previous tile's accumulators
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        for (int kb = 0; kb < nkb; ++kb, ++kcnt) {
-          const uint32_t bs = kcnt & 1u, aph = kcnt & 1u, acc = kb > 0;
-          const uint64_t db = dB0 + (uint64_t)(bs * ((I8_S * I8_B_BYTES) >> 4));
-          mbar_wait_or_trap(&bfull[bs], (kcnt >> 1) & 1u);
-          // one asm block per slice issues its 4 (7 - p) MMAs with immediate descriptor offsets and A-collector reuse (umma_issue.cuh)
-#define I8_WAIT(G) mbar_wait_or_trap(&afull[G], aph); asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#define I8_ISSUE(P) umma_i8_issue<P, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, dA0 + (uint64_t)((P) * (I8_A_BYTES >> 4)), db, idesc, (P) ? 1u : acc);
-          I8_WAIT(0) I8_ISSUE(0) I8_ISSUE(1) umma_commit(&aempty[0]);
-          I8_WAIT(1) I8_ISSUE(2) I8_ISSUE(3) umma_commit(&aempty[1]);
-          I8_WAIT(2) I8_ISSUE(4) I8_ISSUE(5) I8_ISSUE(6) umma_commit(&aempty[2]);
-#undef I8_ISSUE
-#undef I8_WAIT
+        for (int kb = 0; kb < nkb; ++kb, ++bcnt) {
+          const int bs = bcnt & 1;
+          mbar_wait_or_trap(&bfull[bs], (bcnt >> 1) & 1u);
+          for (int p = 0; p < I8_S; ++p) {
+            mbar_wait_or_trap(&afull[as], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint64_t da = umma_desc_sw128(smem_u32(sA + as * I8_A_BYTES));
+            const uint64_t db = umma_desc_sw128(smem_u32(sB + bs * I8_S * I8_B_BYTES));
+            const uint32_t acc = (kb > 0) || (p > 0);         // slice p > 0 always finds its accumulators started by slice p - 1
+            // one asm block per slice issues its 4 (7 - p) MMAs with immediate descriptor offsets (umma_issue.cuh)
+            switch (p) {
+              case 0: umma_i8_issue<0, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 1: umma_i8_issue<1, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 2: umma_i8_issue<2, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 3: umma_i8_issue<3, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 4: umma_i8_issue<4, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              case 5: umma_i8_issue<5, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+              default: umma_i8_issue<6, I8_BN, (I8_B_BYTES >> 4), 1>(tmem, da, db, idesc, acc); break;
+            }
+            umma_commit(&aempty[as]);                         // the A stage is free once these MMAs have read it
+            if (++as == I8_ASTAGES) { as = 0; aph ^= 1u; }
+          }
           umma_commit(&bempty[bs]);
         }
-        umma_commit(tfull);                                   // every MMA of the tile retired: accumulators complete
+        umma_commit(tfull);                                   // all 448 MMAs of the tile retired: accumulators complete
       }
     }
   } else {
