@@ -1,7 +1,8 @@
 # B200BayesOpt.jl -- the reference-side binding of libb200bo.so (include/b200bo.h).
 #
-# NOT EXECUTED in this repository's environment (no julia binary in the image; SURVEY.md 0.3).  Every ccall below is
-# mirrored one-to-one by the ctypes calls in ../_lib.py / ../gp.py, which ARE exercised by tests/ on a B200.
+# NOT EXECUTED in this repository's environment (no julia binary in the image; SURVEY.md 0.3): treat it as the binding a maintainer
+# starts from, not as tested code.  Every ccall below is mirrored one-to-one by the ctypes calls in ../_lib.py / ../gp.py, which ARE
+# exercised by tests/ on a B200 (the argument lists are checked against include/b200bo.h by tests/test_host.py).
 #
 # Drop-in: a `B200GPE` stands where a reference script uses `ElasticGPE(D; mean, kernel, logNoise, capacity)`
 # (README.md:22-26).  It implements the generic functions BayesianOptimization.jl dispatches on
@@ -40,10 +41,15 @@ mutable struct B200GPE
     dim::Int
     function B200GPE(D::Integer; kernel::Symbol = :SEArd, meanconst::Union{Nothing, Real} = nothing,
                      ll = zeros(kernel in (:SEIso, :Mat12Iso, :Mat32Iso, :Mat52Iso) ? 1 : D), lσ = 0.0,
-                     logNoise = -2.0, capacity = 3000, device = 0)
+                     logNoise = -2.0, capacity = 3000, device = 0, n_gpus = 1)
         ref = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:b200bo_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Int32, Int64, Int32, Int32),
-                    ref, device, D, capacity, KERNELS[kernel], meanconst === nothing ? 0 : 1))
+        if n_gpus == 1
+            check(ccall((:b200bo_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Int32, Int64, Int32, Int32),
+                        ref, device, D, capacity, KERNELS[kernel], meanconst === nothing ? 0 : 1))
+        else    # ONE Julia process, n_gpus replicas behind one handle: every call below shards inside the library (include/b200bo.h)
+            check(ccall((:b200bo_create_multi, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Ptr{Int32}, Int32, Int64, Int32, Int32),
+                        ref, n_gpus, C_NULL, D, capacity, KERNELS[kernel], meanconst === nothing ? 0 : 1))
+        end
         m = new(ref[], D)
         finalizer(x -> ccall((:b200bo_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), m)
         θ = Float64[logNoise; (meanconst === nothing ? Float64[] : [Float64(meanconst)]); ll; lσ]
@@ -127,10 +133,25 @@ function nlopt_setup(a::AbstractAcquisition, m::B200GPE, lb, ub, options)       
     setparams!(a, m)
     B200Search(a, m, options)
 end
+optget(o, k, d) = hasproperty(o, k) ? getproperty(o, k) : d
 function acquire_max(s::B200Search, lb, ub, restarts)                                        # acquisition.jl:54-68
     seq = ScaledLHSIterator(lb, ub, restarts)
-    r = acquire(s.model, s.acquisition, seq.data; seed = rand(UInt64))
-    r.best.index < 0 ? (-Inf, lb) : (r.best.value, r.best_x)
+    a, m, o = s.acquisition, s.model, s.options
+    r = acquire(m, a, seq.data; seed = rand(UInt64))
+    r.best.index < 0 && return (-Inf, lb)
+    (a isa ThompsonSamplingSimple || string(o.method)[2] != 'D') && return (r.best.value, r.best_x)     # derivative-free (acquisition.jl:31)
+    # what NLopt :LD_LBFGS does per start (acquisition.jl:59), for the best starts of the sweep at once, inside the library, with the
+    # options the reference forwards (acquisition.jl:24-27)
+    top = partialsortperm(r.values, 1:min(16, length(r.values)); rev = true)
+    X0 = Matrix{Float64}(seq.data[:, top]); p = acqparams(a); lbv = Vector{Float64}(lb); ubv = Vector{Float64}(ub)
+    best = Ref(Best(-Inf, -1)); bx = fill(NaN, m.dim)
+    GC.@preserve X0 p lbv ubv bx check(ccall((:b200bo_acquire_lbfgs, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Float64, Float64, Float64,
+         Float64, Float64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Best}, Ptr{Float64}),
+        m.h, acqkind(a), isempty(p) ? C_NULL : pointer(p), length(p), X0, size(X0, 2), lbv, ubv, Int32(optget(o, :maxeval, 2000)),
+        Float64(optget(o, :ftol_rel, 0.0)), Float64(optget(o, :ftol_abs, 0.0)), Float64(optget(o, :xtol_rel, 0.0)), Float64(optget(o, :xtol_abs, 0.0)),
+        Float64(optget(o, :maxtime, 0.0)), 0.02, 0, C_NULL, C_NULL, C_NULL, best, bx), m.h)
+    best[].value > r.best.value ? (best[].value, bx) : (r.best.value, r.best_x)
 end
 
 # ---- MAP objective (gp.jl:54-77): the closure f(θ, g) of optimizemodel! is one b200bo_mll_sweep call ----------------
@@ -138,18 +159,38 @@ function mll_and_grad!(g::Vector{Float64}, m::B200GPE, θ::Vector{Float64}; nois
     mll = Ref{Float64}(0.0)
     mask = Int32((noise ? 1 : 0) | (domean ? 2 : 0) | (kern ? 4 : 0))
     GC.@preserve θ g check(ccall((:b200bo_mll_sweep, LIB), Int32,
-        (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Int32, Ref{Float64}, Ptr{Float64}), m.h, θ, length(θ), 1, mask, mll, g), m.h)
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Int32, Ref{Float64}, Ptr{Float64}), m.h, θ, length(θ), 1, mask, mll,
+        isempty(g) ? C_NULL : pointer(g)), m.h)              # NLopt passes an empty g when it wants no gradient
     mll[]
 end
-function optimizemodel!(o::MAPGPOptimizer, m::B200GPE)                                       # gp.jl:42-47
-    if o.i % o.every == 0
+
+# bounds in the parameter order [logNoise, (mean), kernel...] restricted to the optimised blocks (gp.jl:65-68; `nothing` = unbounded)
+function map_bounds(o, m::B200GPE, nmean::Int, nkern::Int)
+    lb = Float64[]; ub = Float64[]
+    blk(b, n) = b === nothing ? (fill(-Inf, n), fill(Inf, n)) : (Float64.(b[1] isa AbstractVector ? b[1] : fill(b[1], n)), Float64.(b[2] isa AbstractVector ? b[2] : fill(b[2], n)))
+    if o.noise; l, u = blk(o.noisebounds, 1); append!(lb, l); append!(ub, u); end
+    if o.domean && nmean > 0; l, u = blk(o.meanbounds, nmean); append!(lb, l); append!(ub, u); end
+    if o.kern; l, u = blk(o.kernbounds, nkern); append!(lb, l); append!(ub, u); end
+    lb, ub
+end
+function optimizemodel!(o::MAPGPOptimizer, m::B200GPE)                                       # gp.jl:42-77
+    if o.i % o.every == 0 && dims(m)[2] > 0
+        op = o.options
         P = Ref{Int32}(0); ccall((:b200bo_num_params, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), m.h, P)
-        θ0 = Vector{Float64}(undef, P[]); ccall((:b200bo_get_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), m.h, θ0, P[])
-        opt = BO.NLopt.Opt(o.options.method, length(θ0))                                     # same NLopt driver as gp.jl:69-74
-        BO.NLopt.maxeval!(opt, o.options.maxeval)
-        BO.NLopt.max_objective!(opt, (θ, g) -> mll_and_grad!(g, m, θ))
-        _, θ, _ = BO.NLopt.optimize(opt, θ0)
-        check(ccall((:b200bo_set_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), m.h, θ, length(θ)), m.h)
+        θfull = Vector{Float64}(undef, P[]); ccall((:b200bo_get_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), m.h, θfull, P[])
+        nkern = (length(θfull) - 1 > m.dim + 1) ? length(θfull) - 2 : length(θfull) - 1 - (length(θfull) - 1 == m.dim + 2 ? 1 : 0)
+        nmean = length(θfull) - 1 - nkern
+        sel = vcat(op.noise ? [1] : Int[], (op.domean && nmean > 0) ? collect(2:1 + nmean) : Int[], op.kern ? collect(2 + nmean:length(θfull)) : Int[])
+        lb, ub = map_bounds(op, m, nmean, nkern)
+        θ0 = clamp.(θfull[sel], lb, ub)
+        mask = Int32((op.noise ? 1 : 0) | (op.domean ? 2 : 0) | (op.kern ? 4 : 0))
+        θ = similar(θ0); mll = Ref{Float64}(0.0); ev = Ref{Int32}(0); st = Ref{Int32}(0)
+        # the whole optimisation of gp.jl:69-74 -- objective, gradient and the box-bounded L-BFGS iteration -- runs inside the library
+        GC.@preserve θ0 lb ub θ check(ccall((:b200bo_map_fit, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Float64, Float64, Float64, Float64,
+             Ptr{Float64}, Ref{Float64}, Ref{Int32}, Ref{Int32}),
+            m.h, θ0, length(θ0), 1, mask, lb, ub, Int32(op.maxeval), Float64(optget(op, :ftol_rel, 0.0)), Float64(optget(op, :ftol_abs, 0.0)),
+            Float64(optget(op, :xtol_rel, 0.0)), Float64(optget(op, :xtol_abs, 0.0)), Float64(optget(op, :maxtime, 0.0)), θ, mll, ev, st), m.h)
     end
     o.i += 1
 end
