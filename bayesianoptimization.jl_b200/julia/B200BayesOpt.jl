@@ -39,6 +39,7 @@ check(rc, h = C_NULL) = rc == 0 ? nothing : error("libb200bo error $rc: $(laster
 mutable struct B200GPE
     h::Ptr{Cvoid}
     dim::Int
+    nmean::Int                     # 1 with MeanConst, 0 with MeanZero: theta = [logNoise, (beta), kernel...]
     function B200GPE(D::Integer; kernel::Symbol = :SEArd, meanconst::Union{Nothing, Real} = nothing,
                      ll = zeros(kernel in (:SEIso, :Mat12Iso, :Mat32Iso, :Mat52Iso) ? 1 : D), lσ = 0.0,
                      logNoise = -2.0, capacity = 3000, device = 0, n_gpus = 1)
@@ -50,7 +51,7 @@ mutable struct B200GPE
             check(ccall((:b200bo_create_multi, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Ptr{Int32}, Int32, Int64, Int32, Int32),
                         ref, n_gpus, C_NULL, D, capacity, KERNELS[kernel], meanconst === nothing ? 0 : 1))
         end
-        m = new(ref[], D)
+        m = new(ref[], D, meanconst === nothing ? 0 : 1)
         finalizer(x -> ccall((:b200bo_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), m)
         θ = Float64[logNoise; (meanconst === nothing ? Float64[] : [Float64(meanconst)]); ll; lσ]
         check(ccall((:b200bo_set_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), m.h, θ, length(θ)), m.h)
@@ -178,8 +179,8 @@ function optimizemodel!(o::MAPGPOptimizer, m::B200GPE)                          
         op = o.options
         P = Ref{Int32}(0); ccall((:b200bo_num_params, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), m.h, P)
         θfull = Vector{Float64}(undef, P[]); ccall((:b200bo_get_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), m.h, θfull, P[])
-        nkern = (length(θfull) - 1 > m.dim + 1) ? length(θfull) - 2 : length(θfull) - 1 - (length(θfull) - 1 == m.dim + 2 ? 1 : 0)
-        nmean = length(θfull) - 1 - nkern
+        nmean = m.nmean
+        nkern = length(θfull) - 1 - nmean
         sel = vcat(op.noise ? [1] : Int[], (op.domean && nmean > 0) ? collect(2:1 + nmean) : Int[], op.kern ? collect(2 + nmean:length(θfull)) : Int[])
         lb, ub = map_bounds(op, m, nmean, nkern)
         θ0 = clamp.(θfull[sel], lb, ub)
