@@ -51,6 +51,7 @@ PROTOTYPES = {
     "b200bo_num_params": [_H, C.POINTER(C.c_int32)],
     "b200bo_set_params": [_H, _dp, C.c_int32],
     "b200bo_get_params": [_H, _dp, C.c_int32],
+    "b200bo_set_priors": [_H, C.c_int32, C.POINTER(C.c_int32), _dp, _dp],
     "b200bo_fit": [_H, _dp, _dp, C.c_int64],
     "b200bo_append": [_H, _dp, _dp, C.c_int64],
     "b200bo_refit": [_H],

@@ -407,6 +407,24 @@ B200BO_API int32_t b200bo_set_params(b200bo_handle_t h, const double* th, int32_
   return sync_inv_ell(h);
 }
 
+// EXT GaussianProcesses.jl: "non-flat priors can be specified directly on the GP parameters" (reference src/models/gp.jl:30-35,
+// set_priors!(obj, [Normal(mu, sigma), ...])); the MAP target is then mll + sum of the log prior densities and dtarget gains their
+// derivatives.  kind[i] = 0 flat (default), 1 Normal(a[i], b[i]), in the full parameter order [logNoise, (beta), kernel...].
+B200BO_API int32_t b200bo_set_priors(b200bo_handle_t h, int32_t P, const int32_t* kind, const double* a, const double* b) {
+  if (!h) return fail(h, B200BO_ERR_ARG, "null handle");
+  if (P == 0) { h->prior_kind.clear(); h->prior_a.clear(); h->prior_b.clear(); }
+  else {
+    if (P != num_params(h) || !kind || !a || !b) return fail(h, B200BO_ERR_ARG, "priors need one entry per parameter");
+    for (int i = 0; i < P; ++i) {
+      if (kind[i] != 0 && kind[i] != 1) return fail(h, B200BO_ERR_ARG, "unknown prior kind (0 = flat, 1 = Normal)");
+      if (kind[i] == 1 && !(b[i] > 0.0)) return fail(h, B200BO_ERR_ARG, "Normal prior needs sigma > 0");
+    }
+    h->prior_kind.assign(kind, kind + P); h->prior_a.assign(a, a + P); h->prior_b.assign(b, b + P);
+  }
+  for (auto* r : h->replicas) b200bo_set_priors(r, P, kind, a, b);
+  return B200BO_OK;
+}
+
 B200BO_API int32_t b200bo_get_params(b200bo_handle_t h, double* th, int32_t P) {
   if (!h || !th) return fail(h, B200BO_ERR_ARG, "null argument");
   if (P != num_params(h)) return fail(h, B200BO_ERR_ARG, "parameter vector has the wrong length");
@@ -1052,7 +1070,31 @@ B200BO_API int32_t b200bo_predict(b200bo_handle_t h, const double* Xs, int64_t M
   return B200BO_OK;
 }
 
+static int32_t mll_sweep_impl(b200bo_handle_t h, const double* Theta, int32_t P, int32_t S, int32_t mask, double* mll, double* dmll);
+
 B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int32_t P, int32_t S, int32_t mask, double* mll, double* dmll) {
+  const int32_t rc = mll_sweep_impl(h, Theta, P, S, mask, mll, dmll);
+  if (rc != B200BO_OK || h->prior_kind.empty() || h->lite || h->is_replica || h->in_multi) return rc;
+  // target = mll + log prior of the swept parameters (the priors of the parameters held fixed are constants of the sweep)
+  const bool m_noise = mask & B200BO_MASK_NOISE, m_mean = (mask & B200BO_MASK_MEAN) && h->mean_kind == B200BO_MEAN_CONST, m_kern = mask & B200BO_MASK_KERN;
+  std::vector<int> full;                                      // swept row -> index in the full parameter vector
+  int i = 0;
+  if (m_noise) full.push_back(i);
+  ++i;
+  if (h->mean_kind == B200BO_MEAN_CONST) { if (m_mean) full.push_back(i); ++i; }
+  if (m_kern) for (; i < num_params(h); ++i) full.push_back(i);
+  for (int s = 0; s < S; ++s)
+    for (int r = 0; r < P; ++r) {
+      const int k = full[r];
+      if (h->prior_kind[k] != 1) continue;
+      const double z = (Theta[(int64_t)s * P + r] - h->prior_a[k]) / h->prior_b[k];
+      mll[s] += -0.5 * z * z - log(h->prior_b[k]) - 0.9189385332046727;
+      if (dmll) dmll[(int64_t)s * P + r] += -z / h->prior_b[k];
+    }
+  return B200BO_OK;
+}
+
+static int32_t mll_sweep_impl(b200bo_handle_t h, const double* Theta, int32_t P, int32_t S, int32_t mask, double* mll, double* dmll) {
   if (!h || !Theta || !mll || S < 0) return fail(h, B200BO_ERR_ARG, "bad arguments to mll_sweep");
   const bool m_noise = mask & B200BO_MASK_NOISE, m_mean = (mask & B200BO_MASK_MEAN) && h->mean_kind == B200BO_MEAN_CONST,
              m_kern = mask & B200BO_MASK_KERN;

@@ -102,6 +102,8 @@ struct b200bo_handle_s {
   bool lite = false;         // a worker: no acquisition solve panels
   int sweep_workers = 6;
   bool in_multi = false;     // inside a fan-out of the parent: behave as a single-GPU handle (no exchange)
+  std::vector<int32_t> prior_kind;      // per parameter (full order): 0 flat, 1 Normal(prior_a, prior_b); empty = all flat
+  std::vector<double> prior_a, prior_b;
   bool fitted = false;
   bool need_upload = false;  // device copies of X / y are stale (a failed elastic append): re-upload before the next refactor
   int acq_ready = 0;         // bit 0: W = L^-1 sliced for the tcgen05 acquisition path, bit 1: Sigma^-1 sliced (acq_i8.cu)

@@ -103,6 +103,20 @@ class B200GPE:
         th = np.ascontiguousarray(theta, float)
         check(lib.b200bo_set_params(self._h, dptr(th), th.size), self._h)
 
+    def set_priors(self, priors):
+        """EXT set_priors! (reference src/models/gp.jl:30-35): one entry per parameter in the order of get_params(): None = flat,
+        (mu, sigma) = Normal.  The MAP objective (mll_sweep / map_fit) becomes mll + log prior.  set_priors(None) clears."""
+        if priors is None:
+            check(lib.b200bo_set_priors(self._h, 0, None, None, None), self._h)
+            return
+        P = self.num_params
+        if len(priors) != P:
+            raise ValueError("one prior per parameter")
+        kind = (C.c_int32 * P)(*[0 if p is None else 1 for p in priors])
+        a = np.array([0.0 if p is None else p[0] for p in priors], float)
+        b = np.array([1.0 if p is None else p[1] for p in priors], float)
+        check(lib.b200bo_set_priors(self._h, P, kind, dptr(a), dptr(b)), self._h)
+
     # -- data ------------------------------------------------------------------------------------------------
     def fit(self, X, y):
         X = np.asfortranarray(np.asarray(X, float).reshape(self.D, -1))

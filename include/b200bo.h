@@ -106,6 +106,9 @@ B200BO_API int32_t b200bo_sync(b200bo_handle_t h);
 B200BO_API int32_t b200bo_num_params(b200bo_handle_t h, int32_t* P);
 B200BO_API int32_t b200bo_set_params(b200bo_handle_t h, const double* theta, int32_t P);   /* invalidates the factor */
 B200BO_API int32_t b200bo_get_params(b200bo_handle_t h, double* theta, int32_t P);
+/* EXT set_priors! (reference src/models/gp.jl:30-35: "non-flat priors can be specified directly on the GP parameters"): kind[i] = 0 flat,
+   1 Normal(a[i], b[i]) per parameter in the order of theta; b200bo_mll_sweep / b200bo_map_fit then work on mll + log prior.  P = 0 clears. */
+B200BO_API int32_t b200bo_set_priors(b200bo_handle_t h, int32_t P, const int32_t* kind, const double* a, const double* b);
 
 /* -- model update: update!(model, X, y) (gp.jl:11-18).  fit = full refactor (GP.fit!), append = elastic append! */
 B200BO_API int32_t b200bo_fit(b200bo_handle_t h, const double* X, const double* y, int64_t N);

@@ -252,7 +252,26 @@ class GPOracle:
             else:
                 g.extend(per_d.tolist())
             g.append(float(np.sum(A * (self.sf2 * phi))))       # d/dlsigma: dK = 2K -> 1/2 tr(A 2K)
-        return self.mll, np.array(g, float)
+        g = np.array(g, float)
+        f = self.mll
+        pri = getattr(self, "priors", None)          # EXT set_priors!: target = mll + sum of Normal log densities of the swept parameters
+        if pri is not None:
+            th = self.get_params(noise=noise, domean=domean, kern=kern)
+            full = self.get_params()
+            keep = []
+            i = 0
+            if noise: keep.append(i)
+            i += 1
+            if self.mean == "MeanConst":
+                if domean: keep.append(i)
+                i += 1
+            if kern: keep.extend(range(i, full.size))
+            for r, k in enumerate(keep):
+                if pri[k] is not None:
+                    z = (th[r] - pri[k][0]) / pri[k][1]
+                    f += -0.5 * z * z - math.log(pri[k][1]) - 0.5 * math.log(2 * math.pi)
+                    g[r] += -z / pri[k][1]
+        return f, g
 
 
 # --------------------------------------------------------------------------------------------------

@@ -726,3 +726,26 @@ def test_map_fit_in_library_matches_scipy_on_the_oracle(bo):
     assert abs(g.mll - r["mll"]) <= 1e-10 * abs(r["mll"])
     three = g.map_fit(np.stack([th0[sel], th0[sel] + 0.3, th0[sel] - 0.3], axis=1), lbp, ubp, noise=True, domean=False, kern=True, maxeval=60)
     assert three["mll"] >= r["mll"] - 1e-6 * abs(r["mll"])                               # restarts in lock-step never do worse
+
+
+def test_normal_priors_in_the_map_target(bo):
+    """EXT set_priors! (reference src/models/gp.jl:30-35): Normal priors on chosen parameters enter the MAP target and its gradient; the
+    fixed parameters' priors are constants of the sweep; clearing restores the flat target."""
+    rng, o, g, X, y = make_pair(bo, "Mat32Ard", "MeanConst", 3, 140, seed=707)
+    th = g.get_params()
+    pri = [(-2.0, 0.5), None, (0.0, 1.0), None, (-0.3, 0.2), (0.1, 2.0)]
+    m0, d0 = g.mll_sweep(np.stack([th, th + 0.1], axis=1))
+    g.set_priors(pri); o.priors = pri
+    m1, d1 = g.mll_sweep(np.stack([th, th + 0.1], axis=1))
+    for k, t in enumerate((th, th + 0.1)):
+        fo, go = o.mll_dmll(t)
+        assert abs(m1[k] - fo) <= 1e-10 * abs(fo) and relmax(d1[:, k], go) < 1e-8
+    assert np.all(m1 != m0)
+    mk, dk = g.mll_sweep(np.stack([th[[0, 2, 3, 4, 5]]], axis=1), domean=False)          # beta fixed: its (flat) prior drops out
+    fo, go = o.mll_dmll(th[[0, 2, 3, 4, 5]], domean=False)
+    assert abs(mk[0] - fo) <= 1e-10 * abs(fo) and relmax(dk[:, 0], go) < 1e-8
+    r = g.map_fit(th[[0, 2, 3, 4, 5]], np.full(5, -4.0), np.full(5, 3.0), domean=False, maxeval=80)
+    assert r["mll"] >= mk[0] - 1e-9 * abs(mk[0])
+    g.set_priors(None)
+    m2, _ = g.mll_sweep(np.stack([th, th + 0.1], axis=1))
+    assert np.array_equal(m2, m0)
