@@ -39,6 +39,8 @@ WORKLOADS = {
                  desc="BASELINE configs[4] per-GPU shard: synthetic D=16, N=8192, SEArd, ThompsonSamplingSimple, M=1048576/8"),
     "metric": dict(kernel="SEArd", D=8, N=2048, M=65536, acq="EI", grad=False,
                    desc="metric text: GP posterior + EI at N=2048, D=8, M=65536 candidates"),
+    "target": dict(kernel="SEArd", D=8, N=4096, M=262144, acq="EI", grad=False,
+                   desc="north_star target: GP posterior + EI at N=4096, D=8, M=262144 candidates"),
 }
 METRIC = "acquisition-step candidates/sec (GP posterior + acquisition score + arg-max over an M-candidate sweep)"
 
@@ -179,8 +181,11 @@ def roofline_i8(w, M, gemm_ms, step_ms, peak_i8, peak_fp64, peaks, traffic):
                                         "ran at 0.85 of the self-measured DMMA peak"}}
 
 
-def run_gpu_workload(ctx, w, steps, warmup, want_fit_side=True):
-    """one workload on this rank's GPU: device-resident arm, end-to-end arm, slice-product timing pass."""
+def run_gpu_workload(ctx, w, steps, warmup, want_fit_side=True, m_local=None):
+    """one workload on this rank's GPU: device-resident arm, end-to-end arm, slice-product timing pass.  m_local overrides the
+    candidates per rank (strong scaling: a fixed total split over the ranks)."""
+    if m_local is not None:
+        w = dict(w, M=int(m_local))
     import torch
     import b200bo
     from b200bo import _lib
@@ -350,6 +355,18 @@ def main():
         sys.stdout.flush(); os.dup2(saved_out, 1); os.close(saved_out)
     D, N, M = w["D"], w["N"], w["M"]
     model, fit_ms = r["model"], r["fit_ms"]
+    # the north_star's target shape (N=4096, D=8, M=262144) at this GPU count: every rank takes part (library-side exchange).  Weak: 262144
+    # candidates per GPU, like the headline; strong: 262144 candidates in total, split over the ranks.
+    tgt = {}
+    if not args.no_side and args.workload != "target":
+        try:
+            wt = WORKLOADS["target"]
+            tgt["weak"] = (wt, run_gpu_workload(ctx, wt, 3, 3))
+            if world > 1:
+                ws = dict(wt, M=wt["M"] // world)
+                tgt["strong"] = (ws, run_gpu_workload(ctx, ws, 3, 3))
+        except Exception as exc:
+            tgt = {"error": str(exc)}
     if rank == 0:
         peaks = {}
         try:
@@ -375,6 +392,17 @@ def main():
                              "syrk_k512_engine": "tcgen05.mma kind::i8, 7-slice error-free product, TMEM accumulators (csrc/syrk_i8.cu); "
                                                  "timed on the second stream while the next outer panel runs"},
                 "alpha_ms": fit_ms["alpha"]}
+        if "error" in tgt:
+            side["target_n4096_d8_m262144"] = tgt
+        elif tgt:
+            blk = {}
+            for kind, (wk, rk) in tgt.items():
+                b = line_for(wk, rk, 3, world, peaks, "target")
+                b["config"] = workload_config(wk, world)
+                b["scaling"] = kind
+                b["total_candidates"] = wk["M"] * world
+                blk[kind] = b
+            side["target_n4096_d8_m262144"] = blk
         if world == 1 and not args.no_side:
             # the north_star's fit targets are quoted at N=4096, D=8 (SEArd): measure that fit beside the workload's own (outside every
             # timed region; best of three warm refits, library CUDA-event timers around K1 / the factorisation / the K=512 updates)
