@@ -471,7 +471,21 @@ static int32_t append_elastic(b200bo_handle_t h, const double* Xn, const double*
   CU(cudaMemcpyAsync(h->dy + N0, yn, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
   CU(launch_scale_inputs(h, N0, N0 + m));
   CU(cudaMemsetAsync(h->dinfo, 0, sizeof(int), h->stream));
-  for (int64_t j = 0; j < m; ++j) CU(launch_append_one(h, h->noise_total, j == m - 1));          // advances h->N / h->Np
+  int64_t j = 0;
+  if (h->wt_valid && !h->lite) {
+    // the acquisition path left W = L^-1 behind: the rows of all new points that fit the current 128-block come from ONE dense product
+    // (append.cu: launch_append_block) instead of one chained forward solve per point
+    const int64_t room = NB - (N0 % NB);                       // N0 % NB == 0: a fresh block
+    const int mb = (int)std::min<int64_t>(m, room);
+    CU(launch_append_block(h, h->noise_total, mb));            // advances h->N / h->Np
+    j = mb;
+    h->wt_valid = false;                                       // the factor grew
+    if (j == m) {
+      CU(launch_backward_solve(h, h->dz, h->dw, h->dalpha, (int)(h->Np / NB)));
+      CU(launch_logdet_dot(h));
+    }
+  }
+  for (; j < m; ++j) CU(launch_append_one(h, h->noise_total, j == m - 1));          // advances h->N / h->Np
   int info = 0;
   double sc[2];
   CU(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

@@ -136,6 +136,7 @@ cudaError_t launch_backward_solve(b200bo_handle_s* h, const double* z, double* w
 cudaError_t launch_logdet_dot(b200bo_handle_s* h);
 // append.cu
 cudaError_t launch_append_one(b200bo_handle_s* h, double noise, bool last);
+cudaError_t launch_append_block(b200bo_handle_s* h, double noise, int m);   // m <= 16 points inside one 128-block, from W = L^-1 (h->wt_valid)
 // acq.cu
 struct AcqLaunch {
   int acq_kind = -1;         // -1: predict only

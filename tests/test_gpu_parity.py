@@ -750,3 +750,31 @@ def test_normal_priors_in_the_map_target(bo):
     g.set_priors(None)
     m2, _ = g.mll_sweep(np.stack([th, th + 0.1], axis=1))
     assert np.array_equal(m2, m0)
+
+
+@pytest.mark.parametrize("kern,N0,m", [("SEArd", 1000, 16), ("Mat52Ard", 250, 9), ("SEArd", 120, 16), ("Mat32Iso", 128, 5)])
+def test_blocked_append_from_the_inverse_factor(bo, kern, N0, m):
+    """A batch of m points appended right after an acquisition (the BO loop's order: acquire_max, then update!, reference
+    src/BayesianOptimization.jl:185-196): the new factor rows come from ONE dense product with W = L^-1 (U12 = U11^-T A12 of EXT
+    ElasticPDMats append!), the m x m block from a small Cholesky; batches that cross a 128-block boundary finish point by point.
+    Against a full refactor and the oracle, then again after a second acquisition + append."""
+    import time
+    D = 4
+    rng = np.random.default_rng(N0 + m)
+    X = rng.random((D, N0 + 2 * m)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N0 + 2 * m)
+    ll = np.full(1 if kern.endswith("Iso") else D, np.log(0.5))
+    mk = lambda: bo.B200GPE(D, mean=bo.MeanConst(0.2), kernel=bo.gp._Kernel(kern, ll, 0.1), logNoise=-2.0, capacity=N0 + 300)
+    g = mk(); g.fit(X[:, :N0], y[:N0])
+    Xs = rng.random((D, 500))
+    for rnd in range(2):
+        n1 = N0 + (rnd + 1) * m
+        g.acquire("EI", (0.3,), Xs)                                   # leaves W = L^-1 of the current factor behind
+        t0 = time.perf_counter(); bo.update(g, X[:, n1 - m:n1], y[n1 - m:n1]); dt = time.perf_counter() - t0
+        ref = mk(); ref.fit(X[:, :n1], y[:n1])
+        o = orc.GPOracle(D, kern, "MeanConst", ll=ll, lsigma=0.1, lognoise=-2.0, beta=0.2).fit(X[:, :n1], y[:n1])
+        assert bo.dims(g) == (D, n1)
+        assert relmax(g.factor, o.U) < 1e-11 and relmax(g.alpha, o.alpha) < 1e-9 and abs(g.mll - o.mll) < 1e-10 * abs(o.mll)
+        assert relmax(g.factor, ref.factor) < 1e-12
+        r, r0 = g.acquire("EI", (0.3,), Xs, want_grad=True, want_mu_var=True), ref.acquire("EI", (0.3,), Xs, want_grad=True, want_mu_var=True)
+        assert close(r["mu"], r0["mu"], 1e-9) and close(r["var"], r0["var"], 1e-8, 1e-13) and r["best_index"] == r0["best_index"]
+    print(f"append of {m} points at N={N0 + m}: {dt * 1e3:.3f} ms")
