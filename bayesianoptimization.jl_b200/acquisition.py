@@ -5,6 +5,8 @@ The reference runs `restarts` serial NLopt optimisations, each calling the closu
 optional gradient and arg-max -- by a single fused kernel launch (b200bo_acquire).  `polish` then refines the `polish_top`
 best candidates by box-bounded L-BFGS ascents in lock-step INSIDE the library (b200bo_acquire_lbfgs) -- what the reference's
 NLopt LD_LBFGS run does per start -- with the options it forwards (maxeval, maxtime, ftol_rel/abs, xtol_rel/abs).
+With method = :GN_DIRECT_L (the reference's default for ThompsonSamplingSimple) the library's batched DIRECT-L search
+(b200bo_acquire_direct, `maxeval` evaluations) runs besides the sweep and the better of the two is returned.
 """
 from __future__ import annotations
 
@@ -39,6 +41,8 @@ class AcquisitionSearch:
         self.device_lhs = False          # candidates generated in HBM (b200bo_acquire_lhs) instead of on the host
         self.ascent_steps = 0            # > 0: refine the `ascent_top` best candidates by batched ascent on the device
         self.ascent_top = 256
+        self.direct = True               # method :GN_DIRECT*: run the batched DIRECT-L search (b200bo_acquire_direct) besides the sweep
+        self.direct_width = 1            # rectangles divided per size class and iteration (1 = DIRECT-L)
         self.seed = 0
         self.rng = None
         for k, v in options.items():                 # acquisition.jl:24-27: every key but method/restarts is set
@@ -94,6 +98,12 @@ def acquire_max(opt, lowerbounds=None, upperbounds=None, restarts=None, options=
                 r2 = _refine(opt, data, r["values"])
             if r2["best_index"] >= 0 and r2["best_value"] > r["best_value"]:
                 r = dict(r, best_value=r2["best_value"], best_x=r2["best_x"])
+    if opt.direct and str(opt.method).startswith("GN_DIRECT"):
+        # the reference's derivative-free global search (:GN_DIRECT_L, maxeval evaluations; acquisition.jl:7-9,31-36) inside the library
+        rd = model.acquire_direct(a.kind, a.params(), lb, ub, maxeval=int(opt.maxeval) if opt.maxeval else 2000, maxtime=float(opt.maxtime),
+                                  width=int(opt.direct_width), seed=opt.seed + (1 << 32))
+        if rd["best_index"] >= 0 and (r["best_index"] < 0 or rd["best_value"] > r["best_value"]):
+            r = dict(r, best_value=rd["best_value"], best_x=rd["best_x"], best_index=rd["best_index"])
     opt.seed += 1
     opt.last = r
     if r["best_index"] < 0:

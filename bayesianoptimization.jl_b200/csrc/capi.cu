@@ -12,6 +12,7 @@
 #include <thread>
 #include "common.cuh"
 #include "lbfgs.cuh"
+#include "direct.h"
 #include "handle.h"
 
 using namespace b200bo;
@@ -996,6 +997,52 @@ B200BO_API int32_t b200bo_acquire_lbfgs(b200bo_handle_t h, int32_t kind, const d
     }
   }
   if (best) *best = hb;
+  return B200BO_OK;
+}
+
+// The derivative-free global search of the reference (NLopt :GN_DIRECT_L, the default for ThompsonSamplingSimple -- src/acquisition.jl:7-9;
+// reached through the derivative-free wrapper, :31-36).  The rectangle bookkeeping is host logic (direct.h); every iteration's new centres
+// -- all potentially optimal rectangles, all their longest sides -- are scored by ONE fused acquisition launch.  Evaluation e draws its
+// Thompson sample from the Philox stream at global index e (a fresh epsilon per closure call, as in the reference).  Runs on the handle's
+// first GPU only (the batches are tens of points); with a communicator attached every rank runs the same deterministic search.
+B200BO_API int32_t b200bo_acquire_direct(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* lb, const double* ub,
+                                         int32_t maxeval, double maxtime, int32_t width, uint64_t seed, double* Xtrace, double* ftrace,
+                                         int32_t* evals_out, int32_t* batches_out, b200bo_best_t* best, double* best_x) {
+  if (!h || !lb || !ub || (maxeval <= 0 && !(maxtime > 0.0)) || ((Xtrace || ftrace) && maxeval <= 0))
+    return fail(h, B200BO_ERR_ARG, "bad arguments to acquire_direct (a search needs maxeval > 0 or maxtime > 0; a trace needs maxeval)");
+  int32_t rc = check_acq(h, kind, np, false);
+  if (rc) return rc;
+  const int D = h->D;
+  if (D > 64) return fail(h, B200BO_ERR_ARG, "acquire_direct supports D <= 64");
+  for (int d = 0; d < D; ++d)
+    if (!(lb[d] <= ub[d]) || !std::isfinite(lb[d]) || !std::isfinite(ub[d])) return fail(h, B200BO_ERR_ARG, "DIRECT needs finite bounds with lb <= ub");
+  SoloScope solo(h);
+  DirectL s;
+  s.init(D, maxeval, width);
+  std::vector<double> pts, xs, vals;
+  const auto t0 = std::chrono::steady_clock::now();
+  int batches = 0;
+  for (;;) {
+    const int64_t n = s.ask(pts);
+    if (n == 0) break;
+    xs.resize((size_t)n * D); vals.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i)
+      for (int d = 0; d < D; ++d) xs[(size_t)i * D + d] = lb[d] + pts[(size_t)i * D + d] * (ub[d] - lb[d]);
+    b200bo_best_t* dbest = nullptr;
+    rc = acquire_host_enqueue(h, kind, p, np, xs.data(), n, seed, s.evals, vals.data(), nullptr, nullptr, nullptr, false, &dbest);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    if (Xtrace) memcpy(Xtrace + (size_t)s.evals * D, xs.data(), sizeof(double) * n * D);
+    if (ftrace) memcpy(ftrace + s.evals, vals.data(), sizeof(double) * n);
+    s.tell(pts, vals.data());
+    ++batches;
+    if (maxtime > 0.0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= maxtime) break;
+  }
+  if (evals_out) *evals_out = (int32_t)s.evals;
+  if (batches_out) *batches_out = batches;
+  if (best) { best->value = s.best_f; best->index = s.best_f > -INFINITY ? 0 : -1; }
+  if (best_x && s.best_f > -INFINITY)
+    for (int d = 0; d < D; ++d) best_x[d] = lb[d] + s.best_c[d] * (ub[d] - lb[d]);
   return B200BO_OK;
 }
 

@@ -309,6 +309,25 @@ class B200GPE:
                                        float(step0), idx_offset, dptr(Xout), dptr(vals), dptr(evals), C.byref(best), dptr(bx)), self._h)
         return dict(X=Xout, values=vals, evals=evals.astype(int), best_value=best.value, best_index=best.index, best_x=bx)
 
+    def acquire_direct(self, kind: str, params, lb, ub, maxeval: int = 2000, maxtime: float = 0.0, width: int = 1, seed: int = 0,
+                       want_trace: bool = False):
+        """NLopt :GN_DIRECT_L (the reference's default search for ThompsonSamplingSimple, src/acquisition.jl:7-9) as a batched
+        locally-biased DIRECT inside the library: one fused launch per iteration over all new rectangle centres."""
+        lb = np.ascontiguousarray(lb, float); ub = np.ascontiguousarray(ub, float)
+        if lb.size != self.D or ub.size != self.D:
+            raise ValueError("bounds must have length D")
+        p = np.ascontiguousarray(params, float).ravel()
+        Xt = np.full((self.D, int(maxeval)), np.nan, order="F") if want_trace else None
+        ft = np.full(int(maxeval), np.nan) if want_trace else None
+        ev = C.c_int32(); nb = C.c_int32(); best = _lib.Best(); bx = np.full(self.D, np.nan)
+        check(lib.b200bo_acquire_direct(self._h, _lib.ACQ_KINDS[kind], dptr(p) if p.size else None, p.size, dptr(lb), dptr(ub), int(maxeval),
+                                        float(maxtime), int(width), seed & 0xFFFFFFFFFFFFFFFF, dptr(Xt), dptr(ft), C.byref(ev), C.byref(nb),
+                                        C.byref(best), dptr(bx)), self._h)
+        r = dict(best_value=best.value, best_index=best.index, best_x=bx, evals=ev.value, batches=nb.value)
+        if want_trace:
+            r.update(X=Xt[:, :ev.value], values=ft[:ev.value])
+        return r
+
     def map_fit(self, theta0, lb, ub, noise=True, domean=True, kern=True, maxeval: int = 500, ftol_rel: float = 0.0, ftol_abs: float = 0.0,
                 xtol_rel: float = 0.0, xtol_abs: float = 0.0, maxtime: float = 0.0):
         """optimizemodel!(::MAPGPOptimizer, model) (src/models/gp.jl:54-77) inside the library: L-BFGS ascent of mll over the selected

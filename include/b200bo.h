@@ -181,6 +181,17 @@ B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t acq_kind, co
  *   [lb, ub] (gp.jl:65-68) from R starts in lock-step (Theta0 P x R; R = 1 and Theta0 = current parameters is the reference's run);
  *   every evaluation is a device refactorisation + gradient.  Leaves the model at the best parameters; status = NLopt's numbering
  *   (3 FTOL_REACHED, 4 XTOL_REACHED, 5 MAXEVAL_REACHED, 6 = stalled). */
+/* b200bo_acquire_direct: the derivative-free global search the reference selects with method = :GN_DIRECT_L (the default for
+ *   ThompsonSamplingSimple, src/acquisition.jl:7-9; wrapper :31-36): locally-biased DIRECT on [lb, ub] (csrc/direct.h), every iteration's
+ *   new centres -- all potentially optimal rectangles, all their longest sides -- scored by ONE fused acquisition launch.  maxeval = total
+ *   evaluations (exactly, as NLopt counts them), maxtime in seconds (<= 0 unlimited), width = rectangles divided per hull size class
+ *   (1 = DIRECT-L).  Evaluation e uses the Thompson stream (seed, global index e).  Xtrace (D x maxeval) / ftrace (maxeval) optionally
+ *   receive every evaluated point and value in evaluation order; evals = evaluations used, batches = device launches.  best->index = 0
+ *   when a point was found, -1 if nothing beat -Inf. */
+B200BO_API int32_t b200bo_acquire_direct(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params, const double* lb,
+                                         const double* ub, int32_t maxeval, double maxtime, int32_t width, uint64_t seed,
+                                         double* Xtrace /*D x maxeval or NULL*/, double* ftrace /*maxeval or NULL*/, int32_t* evals /*or NULL*/,
+                                         int32_t* batches /*or NULL*/, b200bo_best_t* best, double* best_x /*D or NULL*/);
 B200BO_API int32_t b200bo_sobol(b200bo_handle_t h, const double* lb, const double* ub, uint64_t index0, int64_t n, double* Xs /* host, D x n */);
 B200BO_API int32_t b200bo_acquire_lbfgs(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params, const double* Xs, int64_t M,
                                         const double* lb, const double* ub, int32_t maxeval, double ftol_rel, double ftol_abs, double xtol_rel,
