@@ -63,6 +63,7 @@ PROTOTYPES = {
     "b200bo_get_factor": [_H, _dp],
     "b200bo_jitter_tries": [_H, C.POINTER(C.c_int32)],
     "b200bo_predict": [_H, _dp, C.c_int64, _dp, _dp],
+    "b200bo_rand_joint": [_H, _dp, C.c_int64, C.c_uint64, C.c_int64, _dp, _dp, C.POINTER(C.c_int32)],
     "b200bo_acquire": [_H, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, C.c_uint64, C.c_int64, _dp, _dp, _dp, _dp,
                        C.POINTER(Best), _dp],
     "b200bo_mll_sweep": [_H, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp],

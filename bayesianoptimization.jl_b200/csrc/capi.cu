@@ -234,6 +234,23 @@ int32_t on_replicas(b200bo_handle_s* h, F f) {
   return B200BO_OK;
 }
 
+// a "lite" model on the parent's device (no acquisition solve panels, own streams and buffers): MAP sweeps and the joint posterior sample
+int32_t new_worker(b200bo_handle_s* h, int64_t cap, b200bo_handle_s** out) {
+  b200bo_handle_s* wk = new (std::nothrow) b200bo_handle_s();
+  if (!wk) return fail(h, B200BO_ERR_ALLOC, "out of host memory");
+  wk->device = h->device; wk->D = h->D; wk->kernel_kind = h->kernel_kind; wk->mean_kind = h->mean_kind; wk->fam = h->fam; wk->iso = h->iso;
+  wk->num_sms = h->num_sms; wk->lite = true; wk->sweep_workers = 0; wk->hp = h->hp;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&wk->stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&wk->stream2, cudaStreamNonBlocking, lo) != cudaSuccess) { delete wk; return fail(h, B200BO_ERR_CUDA, "worker streams"); }
+  for (auto& e : wk->ev) cudaEventCreate(&e);
+  const int32_t rcw = alloc_device(wk, cap);
+  if (rcw != B200BO_OK) { h->err = wk->err; b200bo_destroy(wk); return rcw; }
+  *out = wk;
+  return B200BO_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -293,6 +310,7 @@ B200BO_API int32_t b200bo_destroy(b200bo_handle_t h) {
   h->replicas.clear();
   for (auto* wk : h->workers) b200bo_destroy(wk);
   h->workers.clear();
+  if (h->joint) { b200bo_destroy(h->joint); h->joint = nullptr; }
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   nccl_destroy(h);
@@ -1131,6 +1149,75 @@ B200BO_API int32_t b200bo_predict(b200bo_handle_t h, const double* Xs, int64_t M
   return B200BO_OK;
 }
 
+// myrand(model, X::Matrix) (src/models/gp.jl:7): ONE joint draw from the posterior at the M columns of Xs -- EXT rand(gp, X) =
+// mu + chol(make_posdef!(Sigma_post)) eps.  See joint.cu: the augmented covariance is factorised on a worker model by the fit kernels and
+// its trailing block applied to the Philox normals eps_j = stream(seed, idx_offset + j).  tries = make_posdef! retries that were needed.
+B200BO_API int32_t b200bo_rand_joint(b200bo_handle_t h, const double* Xs, int64_t M, uint64_t seed, int64_t idx_offset, double* sample,
+                                     double* mu_out, int32_t* tries_out) {
+  if (!h || M < 0 || (M > 0 && (!Xs || !sample))) return fail(h, B200BO_ERR_ARG, "bad arguments to rand_joint");
+  if (tries_out) *tries_out = 0;
+  if (M == 0) return B200BO_OK;
+  const int64_t D = h->D, N = h->N;
+  if (N + M > 32768) return fail(h, B200BO_ERR_ARG, "rand_joint: observations + sample points must not exceed 32768 (the joint covariance is dense)");
+  std::vector<double> mu(M), var(M);
+  int32_t rc;
+  {
+    SoloScope solo(h);                   // a dense M x M factor does not shard: the primary GPU draws the sample
+    rc = b200bo_predict(h, Xs, M, mu.data(), var.data());
+  }
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  if (!h->joint) { rc = new_worker(h, std::max<int64_t>(N + M, NB), &h->joint); if (rc) return rc; }
+  b200bo_handle_s* wk = h->joint;
+  wk->hp = h->hp; wk->syrk_engine = h->syrk_engine;
+  wk->hX.assign(h->hX.begin(), h->hX.begin() + N * D);
+  wk->hX.insert(wk->hX.end(), Xs, Xs + M * D);
+  wk->hy.assign(h->hy.begin(), h->hy.begin() + N);
+  wk->hy.resize(N + M, h->mean_kind == B200BO_MEAN_CONST ? h->hp.beta : 0.0);
+  wk->N = N + M;
+  rc = upload_data(wk);
+  if (rc) { h->err = wk->err; return rc; }
+  {
+    b200bo_handle_s* h = wk;             // CU() reports on the worker
+    std::vector<double> ie;
+    upload_inv_ell(h, ie);
+    CU(cudaMemcpyAsync(h->dinv_ell, ie.data(), sizeof(double) * 2 * D, cudaMemcpyHostToDevice, h->stream));
+    CU(launch_scale_inputs(h, 0, h->Np));
+  }
+  const double sf2 = exp(2.0 * h->hp.lsigma);
+  const double noise = N > 0 && h->fitted ? h->noise_total : exp(2.0 * h->hp.lognoise) + std::numeric_limits<double>::epsilon();
+  double mean_var = 0.0;
+  for (int64_t i = 0; i < M; ++i) mean_var += var[i];
+  mean_var /= (double)M;
+  double jit = 0.0;
+  int tries = 0;
+  for (;;) {
+    b200bo_handle_s* h = wk;
+    CU(launch_kmat(h, h->dL, h->ld, h->N, h->Np, noise, true));
+    CU(launch_joint_diag(h, N, M, sf2 + jit));
+    CU(launch_cholesky(h));
+    int info = 0;
+    CU(cudaMemcpyAsync(&info, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (info == 0) break;
+    if (tries >= 10) return fail(h, B200BO_ERR_NOTPD, "posterior covariance not positive definite after 10 jitter retries");
+    jit += 1e-6 * (mean_var + jit);     // make_posdef!: 1e-6 tr(Sigma_post)/M, the trace including the jitter added so far
+    ++tries;
+  }
+  {
+    b200bo_handle_s* h = wk;
+    // dw: mu | dz: eps | dalpha: sample   (the worker's single-RHS vectors; capacity >= N + M)
+    CU(cudaMemcpyAsync(h->dw, mu.data(), sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
+    CU(launch_joint_sample(h, N, M, h->dw, h->dz, h->dalpha, seed, idx_offset));
+    CU(cudaMemcpyAsync(sample, h->dalpha, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  h->launches += wk->launches; wk->launches = 0;
+  if (mu_out) memcpy(mu_out, mu.data(), sizeof(double) * M);
+  if (tries_out) *tries_out = tries;
+  return B200BO_OK;
+}
+
 static int32_t mll_sweep_impl(b200bo_handle_t h, const double* Theta, int32_t P, int32_t S, int32_t mask, double* mll, double* dmll);
 
 B200BO_API int32_t b200bo_mll_sweep(b200bo_handle_t h, const double* Theta, int32_t P, int32_t S, int32_t mask, double* mll, double* dmll) {
@@ -1177,17 +1264,9 @@ static int32_t mll_sweep_impl(b200bo_handle_t h, const double* Theta, int32_t P,
     // ---- several settings in flight: K worker models on this device, contiguous blocks of settings, one host thread each ----
     const int K = std::max(1, std::min<int>(h->sweep_workers, S));
     while ((int)h->workers.size() < K) {
-      b200bo_handle_s* wk = new (std::nothrow) b200bo_handle_s();
-      if (!wk) return fail(h, B200BO_ERR_ALLOC, "out of host memory");
-      wk->device = h->device; wk->D = h->D; wk->kernel_kind = h->kernel_kind; wk->mean_kind = h->mean_kind; wk->fam = h->fam; wk->iso = h->iso;
-      wk->num_sms = h->num_sms; wk->lite = true; wk->sweep_workers = 0; wk->hp = h->hp;
-      int lo = 0, hi = 0;
-      cudaDeviceGetStreamPriorityRange(&lo, &hi);
-      if (cudaStreamCreateWithPriority(&wk->stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
-          cudaStreamCreateWithPriority(&wk->stream2, cudaStreamNonBlocking, lo) != cudaSuccess) { delete wk; return fail(h, B200BO_ERR_CUDA, "worker streams"); }
-      for (auto& e : wk->ev) cudaEventCreate(&e);
-      const int32_t rcw = alloc_device(wk, h->cap);
-      if (rcw != B200BO_OK) { h->err = wk->err; b200bo_destroy(wk); return rcw; }
+      b200bo_handle_s* wk = nullptr;
+      const int32_t rcw = new_worker(h, h->cap, &wk);
+      if (rcw != B200BO_OK) return rcw;
       wk->fitted = true;
       h->workers.push_back(wk);
     }

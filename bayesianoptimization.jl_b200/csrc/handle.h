@@ -98,6 +98,7 @@ struct b200bo_handle_s {
   // MAP sweeps (b200bo_mll_sweep) run on worker models of the same device, several settings in flight at once, each on its own streams
   // and buffers: one setting's chain of diagonal blocks hides behind another's tile GEMMs, and the parent's own factor stays valid
   std::vector<b200bo_handle_s*> workers;
+  b200bo_handle_s* joint = nullptr;      // worker model of the joint posterior sample (b200bo_rand_joint): observations + sample points
   int64_t data_version = 0, synced_version = -1;
   bool lite = false;         // a worker: no acquisition solve panels
   int sweep_workers = 6;
@@ -172,6 +173,10 @@ struct LbfgsOpts;
 cudaError_t launch_sobol(b200bo_handle_s* h, double* dXs, unsigned long long index0, int64_t n, const double* d_lbub);
 cudaError_t launch_lbfgs(b200bo_handle_s* h, const AcqLaunch& base, double* dXe, double* dwork, const double* d_lbub, const LbfgsOpts& o,
                          double maxtime_s, int* rounds_out);
+// joint.cu
+cudaError_t launch_joint_diag(b200bo_handle_s* h, int64_t n0, int64_t m, double value);
+cudaError_t launch_joint_sample(b200bo_handle_s* h, int64_t n0, int64_t m, const double* dmu, double* deps, double* dout,
+                                unsigned long long seed, int64_t idx_offset);
 // peak.cu
 cudaError_t launch_dmma_peak(b200bo_handle_s* h, double* tflops);
 cudaError_t launch_i8_peak(b200bo_handle_s* h, double* tops);

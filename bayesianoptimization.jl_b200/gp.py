@@ -244,6 +244,16 @@ class B200GPE:
         check(lib.b200bo_predict(self._h, dptr(Xs), M, dptr(mu), dptr(var)), self._h)
         return mu, var
 
+    def rand_joint(self, X, seed: int = 0, idx_offset: int = 0):
+        """ONE joint posterior draw over the columns of X (EXT rand(gp, X), reached from myrand(model, X::Matrix), gp.jl:7).
+        Returns dict(sample, mu, tries)."""
+        Xs = self._cands(X)
+        M = Xs.shape[1]
+        out, mu = np.empty(M), np.empty(M)
+        tries = C.c_int32()
+        check(lib.b200bo_rand_joint(self._h, dptr(Xs), M, seed & 0xFFFFFFFFFFFFFFFF, idx_offset, dptr(out), dptr(mu), C.byref(tries)), self._h)
+        return dict(sample=out, mu=mu, tries=tries.value)
+
     def acquire(self, kind: str, params, X, seed: int = 0, idx_offset: int = 0, want_values=True, want_grad=False,
                 want_mu_var=False):
         """One fused acquisition step over the columns of X.  Returns a dict with best_value, best_index, best_x and
@@ -375,10 +385,13 @@ def mean_var(model: B200GPE, x):
     return (float(mu[0]), float(var[0])) if x.ndim == 1 else (mu, var)
 
 
-def myrand(model: B200GPE, x, seed: int = 0, idx_offset: int = 0):
-    """gp.jl:6-7.  Independent per-candidate posterior samples mu + sigma eps (quirk 9), eps from the Philox stream
-    keyed by (seed, global candidate index)."""
+def myrand(model: B200GPE, x, seed: int = 0, idx_offset: int = 0, joint: bool = True):
+    """gp.jl:6-7.  Vector x: an independent posterior sample mu + sigma eps (:6).  Matrix X: ONE joint draw with the full posterior
+    covariance (:7 -> EXT rand(gp, X), quirk 9) -- `joint=False` gives independent per-column draws instead (what the batched acquisition
+    sweep uses).  eps from the Philox stream keyed by (seed, global index)."""
     x = np.asarray(x, float)
+    if x.ndim == 2 and joint:
+        return model.rand_joint(x, seed=seed, idx_offset=idx_offset)["sample"]
     r = model.acquire("TS", (), x, seed=seed, idx_offset=idx_offset)
     return float(r["values"][0]) if x.ndim == 1 else r["values"]
 

@@ -127,6 +127,15 @@ B200BO_API int32_t b200bo_jitter_tries(b200bo_handle_t h, int32_t* tries);
 /* -- posterior: mean_var(model, X) = GP.predict_f (gp.jl:2-5,8) ---------------------------------------------- */
 B200BO_API int32_t b200bo_predict(b200bo_handle_t h, const double* Xs, int64_t M, double* mu, double* var);
 
+/* -- joint posterior sample: myrand(model, X::Matrix) = EXT rand(gp, X) (gp.jl:7): ONE draw
+ *    mu + chol(make_posdef!(Sigma_post)) eps over the M columns of Xs with the full M x M posterior covariance (latent, no noise term);
+ *    eps_j = the Thompson Philox stream at (seed, idx_offset + j).  The covariance is never formed: the points are appended noise-free to
+ *    a worker copy of the model and the augmented matrix is factorised by the fit kernels (csrc/joint.cu).  N + M <= 32768.
+ *    mu_out (optional) = the posterior mean; tries (optional) = make_posdef! jitter retries (1e-6 tr/M each, at most 10).
+ *    The vector form myrand(model, x) -- an independent draw per column -- is b200bo_acquire with B200BO_ACQ_TS. */
+B200BO_API int32_t b200bo_rand_joint(b200bo_handle_t h, const double* Xs, int64_t M, uint64_t seed, int64_t idx_offset, double* sample /*M*/,
+                                     double* mu_out /*M or NULL*/, int32_t* tries /*or NULL*/);
+
 /* -- acquisition step: acquisitionfunction(a, model)(X) + the selection rule of acquire_max
  *    (acquisitionfunctions.jl:4-9, acquisition.jl:54-68).  One fused launch over the M candidate columns:
  *    k(x*,X), both triangular solves, mu, sigma^2, a(mu, sigma^2), optional gradient D x M, arg-max with

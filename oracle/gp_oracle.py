@@ -197,6 +197,32 @@ class GPOracle:
         var = np.maximum(self.sf2 - np.einsum("ij,ij->j", V, V), 0.0)
         return (mu, var, Ks, V) if return_aux else (mu, var)
 
+    # -- rand(gp, X)  (reached from myrand(model, X::Matrix), gp.jl:7; App. A "Sample", quirk 9): EXT GaussianProcesses.jl rand!:
+    #    mu, Sigma = predict_f(gp, X; full_cov = true); Sigma, chol = make_posdef!(Sigma); mu + unwhiten(PDMat(Sigma, chol), randn)
+    #    i.e. mu + L eps with L the LOWER factor; make_posdef! retries add 1e-6 tr(Sigma)/M to the diagonal (<= 10 times).
+    def posterior_cov(self, Xs: np.ndarray):
+        Xs = np.asarray(Xs, float).reshape(self.D, -1)
+        Kss = self.cov(Xs, Xs)
+        if self.y.size == 0:
+            return self.mean_at(Xs.shape[1]), Kss
+        mu, _, _, V = self.predict(Xs, return_aux=True)
+        return mu, Kss - V.T @ V
+
+    def rand_joint(self, Xs: np.ndarray, eps: np.ndarray):
+        mu, S = self.posterior_cov(Xs)
+        M = mu.size
+        tries = 0
+        while True:
+            try:
+                Lc = cholesky(S, lower=True)
+                break
+            except np.linalg.LinAlgError:
+                if tries >= 10:
+                    raise
+                S[np.diag_indices(M)] += 1e-6 * np.trace(S) / M
+                tries += 1
+        return mu + Lc @ np.asarray(eps, float), tries
+
     def predict_column_loop(self, Xs: np.ndarray):
         """Reference-shaped: one predict_full per column (GaussianProcesses.jl predict_f loop)."""
         Xs = np.asarray(Xs, float).reshape(self.D, -1)

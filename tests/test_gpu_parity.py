@@ -778,3 +778,64 @@ def test_blocked_append_from_the_inverse_factor(bo, kern, N0, m):
         r, r0 = g.acquire("EI", (0.3,), Xs, want_grad=True, want_mu_var=True), ref.acquire("EI", (0.3,), Xs, want_grad=True, want_mu_var=True)
         assert close(r["mu"], r0["mu"], 1e-9) and close(r["var"], r0["var"], 1e-8, 1e-13) and r["best_index"] == r0["best_index"]
     print(f"append of {m} points at N={N0 + m}: {dt * 1e3:.3f} ms")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# joint posterior sample: myrand(model, X::Matrix) -> EXT rand(gp, X) (src/models/gp.jl:7)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel,N,M", [("SEArd", 200, 40), ("Mat52Ard", 700, 300), ("SEArd", 0, 50)])
+def test_joint_posterior_sample_matches_restatement(kernel, N, M):
+    import b200bo
+    rng = np.random.default_rng(N + M)
+    D = 3
+    X = rng.random((D, N)); y = np.sin(4 * X.sum(axis=0)) + 0.05 * rng.normal(size=N)
+    ll = np.full(D, -1.6)                      # short length-scale: the posterior covariance of M scattered points is well conditioned
+    g = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.3), kernel=getattr(b200bo, kernel)(ll, 0.2), logNoise=-1.5, capacity=max(N, 128))
+    o = orc.GPOracle(D, kernel, "MeanConst", ll=ll, lsigma=0.2, lognoise=-1.5, beta=0.3)
+    if N:
+        g.fit(X, y)
+    o.fit(X, y)
+    Xs = rng.random((D, M))
+    seed, off = 77, 1000
+    r = g.rand_joint(Xs, seed=seed, idx_offset=off)
+    eps = orc.philox_normal(seed, off + np.arange(M))
+    want, tries = o.rand_joint(Xs, eps)
+    mu, S = o.posterior_cov(Xs)
+    assert r["tries"] == tries == 0
+    assert np.all(np.abs(r["mu"] - mu) <= 1e-6 * np.abs(mu) + 1e-12)
+    scale = np.sqrt(np.diag(S).max())
+    assert np.abs(r["sample"] - want).max() <= 1e-7 * scale       # the Schur complement inside the augmented factor == chol(K** - V'V)
+    # matrix form of the generic function (gp.jl:7) is the joint draw; the vector form (gp.jl:6) stays an independent draw
+    assert np.array_equal(b200bo.myrand(g, Xs, seed=seed, idx_offset=off), r["sample"])
+    one = b200bo.myrand(g, Xs[:, 0], seed=seed, idx_offset=off)
+    m1, v1 = o.predict(Xs[:, :1])
+    assert abs(one - (m1[0] + np.sqrt(v1[0]) * eps[0])) <= 1e-9 * scale
+
+
+def test_joint_posterior_sample_statistics_and_make_posdef():
+    """duplicate columns make Sigma_post exactly singular: make_posdef!'s jitter rule must kick in and the draws at the duplicates agree to
+    sqrt(jitter); over many seeds the empirical covariance approaches Sigma_post"""
+    import b200bo
+    rng = np.random.default_rng(9)
+    D, N, M = 2, 60, 12
+    X = rng.random((D, N)); y = np.cos(3 * X[0]) * X[1]
+    g = b200bo.B200GPE(D, mean=b200bo.MeanZero(), kernel=b200bo.SEArd(np.full(D, -1.0), 0.0), logNoise=-2.0, capacity=128)
+    g.fit(X, y)
+    o = orc.GPOracle(D, "SEArd", "MeanZero", ll=np.full(D, -1.0), lsigma=0.0, lognoise=-2.0).fit(X, y)
+    Xs = rng.random((D, M)) * 1.5
+    mu, S = o.posterior_cov(Xs)
+    draws = np.stack([g.rand_joint(Xs, seed=s)["sample"] for s in range(1500)])
+    emp = np.cov(draws.T)
+    assert np.abs(draws.mean(axis=0) - mu).max() < 5 * np.sqrt(np.diag(S).max() / 1500)
+    assert np.abs(emp - S).max() < 0.15 * np.diag(S).max()
+    dup = np.concatenate([Xs, Xs[:, :3]], axis=1)
+    r = g.rand_joint(dup, seed=3)
+    sd = np.sqrt(np.diag(S)[:3])
+    assert r["tries"] <= 10 and np.all(np.abs(r["sample"][M:] - r["sample"][:3]) <= 0.05 * sd + 1e-3)
+    # 150 numerically coincident points: 149 pivots of rounding noise cannot all come out positive -> the jitter rule must act
+    cl = np.array([[0.4], [0.6]]) + 1e-10 * rng.random((D, 150))
+    rc = g.rand_joint(cl, seed=4)
+    _, tries_o = o.rand_joint(cl, orc.philox_normal(4, np.arange(150)))
+    assert 1 <= rc["tries"] <= 10 and tries_o >= 1
+    m0, v0 = o.predict(cl[:, :1])
+    assert np.all(np.abs(rc["sample"] - rc["sample"][0]) <= 0.02 * np.sqrt(v0[0]) + 1e-3)       # one draw, shared by the whole cluster
