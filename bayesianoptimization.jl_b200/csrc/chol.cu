@@ -18,9 +18,12 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cooperative_groups.h>
 #include "tma.cuh"
 #include "tilegemm.cuh"
 #include "handle.h"
+
+namespace cg = cooperative_groups;
 
 namespace b200bo {
 
@@ -317,13 +320,132 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
 #endif
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Head of panel k (look-ahead schedule): everything the NEXT diagonal block needs from panel k, as ONE launch of an 8-CTA cluster.
+//   phase 1   X = L_{k+1,k} = A_{k+1,k} W_k^T   (W_k = L_kk^-1, lower triangular: only l <= j contributes)
+//   phase 2   A_{k+1,k+1} -= X X^T              (lower tiles; + the scratch accumulator D of an outer-panel boundary)
+// CTA r owns the 8-row tiles r and 15 - r of the block row (balanced triangle); W_k and the CTA's rows of A arrive by 1-D TMA bulk
+// copies; every CTA keeps its 16 rows of X in shared memory and phase 2 reads the other CTAs' rows through distributed shared
+// memory.  All products on the FP64 tensor pipe (DMMA.8x8x4), four independent accumulator chains per warp.
+// The tile GEMM kernels need ~12 us per launch for this (one 128 x 64 x 128 tile per CTA is 8.4 us of DMMA on one SM): twice that sat
+// between every two diagonal blocks.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int HC = 8;
+constexpr size_t HEAD_SMEM = (size_t)(NB * PLD + 2 * 16 * PLD) * sizeof(double) + 16;
+
+__global__ void __cluster_dims__(HC, 1, 1) __launch_bounds__(256, 1) chol_head_kernel(double* __restrict__ A, int64_t ld, int kb,
+                                                                                       const double* __restrict__ Linv,
+                                                                                       const double* __restrict__ Dacc) {
+  extern __shared__ __align__(16) double sm[];
+  double* W = sm;                        // [128][PLD] lower triangle of W_k
+  double* As = W + NB * PLD;             // [16][PLD] this CTA's rows of A_{k+1,k}
+  double* Xs = As + 16 * PLD;            // [16][PLD] this CTA's rows of X
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Xs + 16 * PLD);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int r = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int b = kb + 1;
+  const int mrow0 = 8 * r, mrow1 = 8 * (15 - r);
+  double* Ablk = A + ((int64_t)b * NB) * ld;            // block row b
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(8 * (NB / 2) * (NB / 2 + 1) * 2 + 16 * NB * 8));
+  __syncthreads();
+  if (tid < NB) {
+    const uint32_t bytes = (uint32_t)(((tid + 2) & ~1) * 8);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(W + tid * PLD)),
+                 "l"(Linv + (int64_t)kb * NB * NB + (int64_t)tid * NB), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  } else if (tid < NB + 16) {
+    const int rr = tid - NB, row = (rr < 8 ? mrow0 : mrow1) + (rr & 7);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(As + rr * PLD)),
+                 "l"(Ablk + (int64_t)row * ld + (int64_t)kb * NB), "r"((uint32_t)(NB * 8)), "r"(smem_u32(bar))
+                 : "memory");
+  }
+  // phase-2 accumulators start from the diagonal block (issued now: the loads fly during phase 1).  Tile t of the CTA: t <= r ->
+  // (m-tile r, column tile t), else (m-tile 15 - r, column tile t - r - 1); warp w owns t = w, w + 8, w + 16.
+  double2 c[3];
+  int tm[3], tj[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int t = warp + 8 * i;
+    tm[i] = -1; tj[i] = 0; c[i] = make_double2(0.0, 0.0);
+    if (t < 17) {
+      tm[i] = t <= r ? 0 : 1;
+      tj[i] = t <= r ? t : t - r - 1;
+      const int row = (tm[i] ? mrow1 : mrow0) + g, col = 8 * tj[i] + 2 * q;
+      c[i] = *reinterpret_cast<const double2*>(Ablk + (int64_t)row * ld + (int64_t)b * NB + col);
+      if (Dacc) { const double2 d = *reinterpret_cast<const double2*>(Dacc + row * NB + col); c[i].x += d.x; c[i].y += d.y; }
+    }
+  }
+  mbar_wait(bar, 0);
+  // ---- phase 1: X(16 x 128) = As W^T; warp w computes column tiles w and 15 - w for both m-tiles ----
+#pragma unroll
+  for (int ni = 0; ni < 2; ++ni) {
+    const int jt = ni ? 15 - warp : warp;
+    const double* brow = W + (8 * jt + g) * PLD + q;
+    const double* a0 = As + g * PLD + q;
+    const double* a1 = As + (8 + g) * PLD + q;
+    double2 x0 = make_double2(0.0, 0.0), x1 = x0, y0 = x0, y1 = x0;
+#pragma unroll 2
+    for (int ks = 0; ks < 2 * jt; ks += 2) {          // l < 8 jt: full k-steps, two chains per m-tile
+      const double b0 = brow[4 * ks], b1 = brow[4 * ks + 4];
+      dmma884(x0.x, x0.y, a0[4 * ks], b0);
+      dmma884(x1.x, x1.y, a1[4 * ks], b0);
+      dmma884(y0.x, y0.y, a0[4 * ks + 4], b1);
+      dmma884(y1.x, y1.y, a1[4 * ks + 4], b1);
+    }
+    {                                                 // the two k-steps that straddle the diagonal of W: l <= j only
+      const double b0 = (q <= g) ? brow[8 * jt] : 0.0, b1 = (4 + q <= g) ? brow[8 * jt + 4] : 0.0;
+      dmma884(x0.x, x0.y, a0[8 * jt], b0);
+      dmma884(x1.x, x1.y, a1[8 * jt], b0);
+      dmma884(y0.x, y0.y, a0[8 * jt + 4], b1);
+      dmma884(y1.x, y1.y, a1[8 * jt + 4], b1);
+    }
+    x0.x += y0.x; x0.y += y0.y; x1.x += y1.x; x1.y += y1.y;
+    const int col = 8 * jt + 2 * q;
+    *reinterpret_cast<double2*>(Xs + g * PLD + col) = x0;
+    *reinterpret_cast<double2*>(Xs + (8 + g) * PLD + col) = x1;
+    // L_{k+1,k} to the factor: lower triangle and its mirror
+    *reinterpret_cast<double2*>(Ablk + (int64_t)(mrow0 + g) * ld + (int64_t)kb * NB + col) = x0;
+    *reinterpret_cast<double2*>(Ablk + (int64_t)(mrow1 + g) * ld + (int64_t)kb * NB + col) = x1;
+    double* up = A + ((int64_t)kb * NB + col) * ld + (int64_t)b * NB;
+    up[mrow0 + g] = x0.x; up[ld + mrow0 + g] = x0.y;
+    up[mrow1 + g] = x1.x; up[ld + mrow1 + g] = x1.y;
+  }
+  cluster.sync();                                     // every CTA's rows of X are in its shared memory
+  // ---- phase 2: A_{k+1,k+1}(own rows, column tiles <= m-tile) -= X X^T, K = 128 in four chains ----
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (tm[i] < 0) continue;
+    const int jt = tj[i];
+    const int owner = jt < 8 ? jt : 15 - jt;
+    const double* xb = cluster.map_shared_rank(Xs, owner) + ((jt < 8 ? 0 : 8) + g) * PLD + q;
+    const double* xa = Xs + (8 * tm[i] + g) * PLD + q;
+    double2 e1 = make_double2(0.0, 0.0), e2 = e1, e3 = e1;
+#pragma unroll 2
+    for (int ks = 0; ks < NB / 4; ks += 4) {
+      dmma884(c[i].x, c[i].y, -xa[4 * ks], xb[4 * ks]);
+      dmma884(e1.x, e1.y, -xa[4 * ks + 4], xb[4 * ks + 4]);
+      dmma884(e2.x, e2.y, -xa[4 * ks + 8], xb[4 * ks + 8]);
+      dmma884(e3.x, e3.y, -xa[4 * ks + 12], xb[4 * ks + 12]);
+    }
+    c[i].x += (e1.x + e2.x) + e3.x; c[i].y += (e1.y + e2.y) + e3.y;
+    const int row = (tm[i] ? mrow1 : mrow0) + g, col = 8 * jt + 2 * q;
+    *reinterpret_cast<double2*>(Ablk + (int64_t)row * ld + (int64_t)b * NB + col) = c[i];
+  }
+  cluster.sync();                                     // no CTA leaves while its rows of X are still being read
+}
+
 struct CholMaps { CUtensorMap L128, L64, Linv; };
 
 // K3: one CTA per 64 rows below the diagonal block.  acc[n_panel][row] = sum_l Linv[n_panel][l] * A[row][l]  = L[row][n_panel].
-__global__ void __launch_bounds__(TG_THREADS, 2) trsm_panel_kernel(double* __restrict__ A, int64_t ld, int kb,
+__global__ void __launch_bounds__(TG_THREADS, 2) trsm_panel_kernel(double* __restrict__ A, int64_t ld, int kb, int tile0,
                                                                    const __grid_constant__ CholMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int row0 = (kb + 1) * NB + blockIdx.x * TG_BN;
+  const int row0 = (kb + 1) * NB + (tile0 + blockIdx.x) * TG_BN;
   double acc[4][4][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -352,7 +474,8 @@ __global__ void __launch_bounds__(TG_THREADS, 2) trsm_panel_kernel(double* __res
 // of everything to the right of the panel is ONE launch with nkb = 4, where per-tile overheads are amortised over K = 512.
 __global__ void __launch_bounds__(TG_THREADS, 2) syrk_trailing_kernel(double* __restrict__ A, int64_t ld, int kb0, int nkb, int bi_lo,
                                                                       int col2_lo, int col2_hi, int nblk,
-                                                                      const __grid_constant__ CholMaps maps) {
+                                                                      const __grid_constant__ CholMaps maps, double* __restrict__ Cd = nullptr,
+                                                                      int xbi = -1) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   int t = blockIdx.x, bi = bi_lo, c2 = 0;
   for (; bi < nblk; ++bi) {
@@ -360,7 +483,10 @@ __global__ void __launch_bounds__(TG_THREADS, 2) syrk_trailing_kernel(double* __
     const int cnt = hi - col2_lo;
     if (cnt > 0) { if (t < cnt) { c2 = col2_lo + t; break; } t -= cnt; }
   }
-  if (bi >= nblk) return;
+  if (bi >= nblk) {
+    if (xbi < 0 || t >= 2) return;
+    bi = xbi; c2 = 2 * xbi + t;           // the two extra CTAs of the launch: the diagonal block of row block xbi
+  }
   double acc[4][4][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -369,7 +495,9 @@ __global__ void __launch_bounds__(TG_THREADS, 2) syrk_trailing_kernel(double* __
   tile_gemm(acc, &maps.L128, kb0 * NB, bi * NB, &maps.L64, kb0 * NB, c2 * TG_BN, nkb * (NB / KC), smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3, rg = rho(g);
-  double* C = A + ((int64_t)bi * NB) * ld + (int64_t)c2 * TG_BN;
+  // Cd: the update of ONE diagonal block goes to a 128 x 128 scratch accumulator instead (look-ahead schedule, outer-panel boundary)
+  double* C = Cd ? Cd + (int64_t)(c2 - 2 * bi) * TG_BN : A + ((int64_t)bi * NB) * ld + (int64_t)c2 * TG_BN;
+  if (Cd) ld = NB;
   const int diag_off = bi * NB - c2 * TG_BN;      // element (m, n) is on/below the diagonal iff n <= m + diag_off
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
@@ -393,7 +521,7 @@ static int syrk_tiles(int bi_lo, int nblk, int col2_lo, int col2_hi) {
 
 static const int OB = (getenv("B200BO_OB") && atoi(getenv("B200BO_OB")) >= 1 && atoi(getenv("B200BO_OB")) <= 4) ? atoi(getenv("B200BO_OB")) : 4;   // inner panels per outer panel (developer knob; 4 = 512 columns)
 
-cudaError_t launch_cholesky(b200bo_handle_s* h) {
+static cudaError_t launch_cholesky_inorder(b200bo_handle_s* h) {
   const int nblk = (int)(h->Np / NB);
   const size_t sm_potrf = PD_SMEM;
   cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf);
@@ -433,7 +561,7 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
       launch_fwd_step(h, sb, k - 1, nblk);
       const int rem = nblk - k - 1;
       if (rem <= 0) break;
-      trsm_panel_kernel<<<rem * (NB / TG_BN), TG_THREADS, TG_SMEM, sa>>>(h->dL, h->ld, k, maps);
+      trsm_panel_kernel<<<rem * (NB / TG_BN), TG_THREADS, TG_SMEM, sa>>>(h->dL, h->ld, k, 0, maps);
       h->launches++;
       syrk(sa, k, 1, k + 1, 2 * (k + 1), 2 * p1);            // inner update: only the columns still inside the outer panel
     }
@@ -475,6 +603,155 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
   }
 #endif
   return cudaGetLastError();
+}
+
+// Look-ahead schedule (round 2).  The only work between two diagonal blocks that the NEXT diagonal block needs is the "head" of panel k:
+// L_{k+1,k} (one 128-row slab of the panel solve) and the rank-128 update of A_{k+1,k+1}.  The chain stream therefore runs
+//     potrf(k) -> head(k) -> potrf(k+1) -> ...
+// and everything else of panel k runs underneath potrf(k+1), itself split by what the next head needs:
+//   stream C (column path)  R1(k): the panel solve below block k+1;  R2a(k): the update of block column k+1 and of the diagonal block
+//                           A_{k+2,k+2} -- what head(k+1) and R1(k+1) read -- then event Re(k);  at an outer-panel boundary the int8
+//                           slicing and the near K = 512 update (tcgen05);
+//   stream D (bulk)         R2b(k): the rest of the inner update (columns k+2 .. end of the outer panel);
+//   stream E (riders)       the forward solve of y - m, and panel k's share of the boundary block A_{p1,p1} into a scratch accumulator
+//                           (A_{p1,p1} itself is still being written by the far update of the previous outer panel);
+//   stream B (far)          the far K = 512 update, low priority, on num_sms - reserve SMs as before.
+// Every tile still receives its updates in a fixed order (events), so repeated factorisations stay bit-identical.
+static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head) {
+  const int nblk = (int)(h->Np / NB);
+  cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM);
+  cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
+  cudaFuncSetAttribute(syrk_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
+  cudaFuncSetAttribute(chol_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM);
+  CholMaps maps;
+  maps.L128 = h->tmL; maps.L64 = h->tmL64; maps.Linv = h->tmLinv;
+  if (!h->dD) { const cudaError_t e = cudaMalloc(&h->dD, sizeof(double) * NB * NB); if (e != cudaSuccess) return e; }
+  if (!h->stream3) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    const int mid = hi < lo ? hi + 1 : hi;
+    cudaError_t e = cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, mid);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, mid < lo ? mid + 1 : mid);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->stream5, cudaStreamNonBlocking, mid < lo ? mid + 1 : mid);
+    if (e != cudaSuccess) return e;
+  }
+  cudaStream_t sa = h->stream, sb = h->stream2, sc = h->stream3, sd = h->stream4, se = h->stream5;
+  cudaMemsetAsync(h->dinfo, 0, sizeof(int), sa);
+  const int npan = (nblk + OB - 1) / OB;
+  auto grow = [](std::vector<cudaEvent_t>& v, size_t n, bool timing) {
+    while (v.size() < n) { cudaEvent_t e; if (timing) cudaEventCreate(&e); else cudaEventCreateWithFlags(&e, cudaEventDisableTiming); v.push_back(e); }
+  };
+  grow(h->syrk_ev, 2 * npan + 2, true);
+  grow(h->la_ev, 3 * npan + 2, false);
+  grow(h->fw_ev, nblk + 2, false);
+  grow(h->ch_ev, 6 * (size_t)nblk + 8, false);
+  h->syrk_ev_used = 0;
+  const int big = 1 << 30;
+  auto Pe = [&](int k) { return h->ch_ev[6 * k]; };        // potrf(k) done (chain)
+  auto He = [&](int k) { return h->ch_ev[6 * k + 1]; };    // head(k) done (chain)
+  auto Re = [&](int k) { return h->ch_ev[6 * k + 2]; };    // column path of panel k done (C)
+  auto R1e = [&](int k) { return h->ch_ev[6 * k + 3]; };   // panel solve of panel k done (C)
+  auto Be = [&](int k) { return h->ch_ev[6 * k + 4]; };    // bulk inner update of panel k done (D)
+  auto De = [&](int k) { return h->ch_ev[6 * k + 5]; };    // panel k's share of the boundary block accumulated (E)
+  auto syrk = [&](cudaStream_t st, int kb0, int nkb, int bi_lo, int bi_hi, int lo, int hi, double* Cd = nullptr, int xbi = -1) {
+    const int n = syrk_tiles(bi_lo, bi_hi, lo, hi) + (xbi >= 0 ? 2 : 0);
+    if (n > 0) {
+      syrk_trailing_kernel<<<n, TG_THREADS, TG_SMEM, st>>>(h->dL, h->ld, kb0, nkb, bi_lo, lo, hi, bi_hi, maps, Cd, xbi);
+      h->launches++;
+    }
+    return n;
+  };
+  auto trsm = [&](cudaStream_t st, int k, int tile0, int ntile) {
+    if (ntile > 0) {
+      trsm_panel_kernel<<<ntile, TG_THREADS, TG_SMEM, st>>>(h->dL, h->ld, k, tile0, maps);
+      h->launches++;
+    }
+  };
+  static const int reserve = getenv("B200BO_I8_RESERVE") ? atoi(getenv("B200BO_I8_RESERVE")) : 40;
+  static const int near_reserve = getenv("B200BO_I8_NEAR_RESERVE") ? atoi(getenv("B200BO_I8_NEAR_RESERVE")) : 16;
+  cudaEventRecord(h->fw_ev[nblk], sa);
+  for (cudaStream_t st : {sb, sc, sd, se}) cudaStreamWaitEvent(st, h->fw_ev[nblk], 0);
+  launch_residual(h, se);                                  // the forward solve z = L^-1 (y - m) rides along (solve.cu: launch_fwd_step)
+  for (int P = 0; P < npan; ++P) {
+    const int p0 = P * OB, p1 = (p0 + OB < nblk) ? p0 + OB : nblk, p2 = (p1 + OB < nblk) ? p1 + OB : nblk;
+    const bool use_D = fused_head && p1 < nblk && p1 - p0 > 1;
+    for (int k = p0; k < p1; ++k) {
+      potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
+      h->launches++;
+      cudaEventRecord(Pe(k), sa);
+      cudaStreamWaitEvent(se, Pe(k), 0);
+      if (use_D && k == p0) cudaMemsetAsync(h->dD, 0, sizeof(double) * NB * NB, se);   // its last reader, head(p0-1), precedes potrf(p0)
+      if (k > 0) cudaStreamWaitEvent(se, R1e(k - 1), 0);                    // L_{.,k-1} complete
+      launch_fwd_step(h, se, k - 1, nblk);
+      const int rem = nblk - k - 1;
+      if (rem <= 0) break;
+      // ---- head(k) on the chain ----
+      const bool boundary = k + 1 == p1;                                    // A_{p1,p1} lies outside the inner updates
+      if (k > 0) cudaStreamWaitEvent(sa, Re(k - 1), 0);                     // A_{k+1,k}, A_{k+1,k+1} carry every update of the panels < k
+      if (boundary && P > 0) cudaStreamWaitEvent(sa, h->la_ev[3 * (P - 1) + 1], 0);   // the far update of panel P-1 also writes A_{p1,p1}
+      if (fused_head) {
+        if (boundary && k > p0) cudaStreamWaitEvent(sa, De(k - 1), 0);      // panels p0 .. p1-2 left their share in the scratch accumulator
+        chol_head_kernel<<<HC, 256, HEAD_SMEM, sa>>>(h->dL, h->ld, k, h->dLinv, (boundary && k > p0) ? h->dD : nullptr);
+        h->launches++;
+      } else {
+        trsm(sa, k, 0, NB / TG_BN);                                        // L_{k+1,k}
+        if (!boundary) syrk(sa, k, 1, k + 1, k + 2, 2 * (k + 1), 2 * (k + 1) + 2);   // A_{k+1,k+1} -= L_{k+1,k} L_{k+1,k}^T
+        else syrk(sa, p0, p1 - p0, p1, p1 + 1, 2 * p1, 2 * p1 + 2);        // outer boundary: the whole K = 128 (p1 - p0) update of A_{p1,p1}
+      }
+      cudaEventRecord(He(k), sa);
+      // ---- column path of panel k (stream C) ----
+      cudaStreamWaitEvent(sc, Pe(k), 0);
+      trsm(sc, k, NB / TG_BN, (rem - 1) * (NB / TG_BN));                   // R1: L_{i,k}, i >= k+2
+      cudaEventRecord(R1e(k), sc);
+      cudaStreamWaitEvent(sc, He(k), 0);                                    // L_{k+1,k}
+      if (k > p0) cudaStreamWaitEvent(sc, Be(k - 1), 0);                    // the bulk update of panel k-1 wrote these tiles first
+      if (!boundary) syrk(sc, k, 1, k + 2, nblk, 2 * (k + 1), 2 * (k + 1) + 2, nullptr, (k + 2 < p1) ? k + 2 : -1);   // R2a: block column k+1 (+ A_{k+2,k+2})
+      if (!boundary) cudaEventRecord(Re(k), sc);
+      // ---- bulk inner update (stream D): columns k+2 .. p1-1 below the diagonal blocks taken by R2a ----
+      if (k + 2 < p1) {
+        cudaStreamWaitEvent(sd, R1e(k), 0);
+        syrk(sd, k, 1, k + 3, nblk, 2 * (k + 2), 2 * p1);
+      }
+      cudaEventRecord(Be(k), sd);
+      // ---- this panel's share of the boundary block, off the chain (stream E) ----
+      if (use_D && !boundary) {
+        cudaStreamWaitEvent(se, R1e(k), 0);
+        syrk(se, k, 1, p1, p1 + 1, 2 * p1, 2 * p1 + 2, h->dD);
+        cudaEventRecord(De(k), se);
+      }
+    }
+    if (p1 >= nblk) break;
+    // ---- outer panel P is complete on stream C: K = 512 updates (tcgen05 int8 slices when enabled and the panel is full) ----
+    cudaEvent_t Sk = h->la_ev[3 * P], Rk = h->la_ev[3 * P + 1];
+    const bool i8 = (h->syrk_engine < 0 ? syrk_i8_enabled() : h->syrk_engine >= 1) && (p1 - p0) == OB;
+    if (P > 0) cudaStreamWaitEvent(sc, h->la_ev[3 * (P - 1) + 1], 0);       // far(P-1) still reads the previous slices and writes these columns
+    if (i8) launch_slice_panel(h, sc, p1 * NB, p0 * NB, p1 - p0);
+    const bool have_far = syrk_tiles(p1, nblk, 2 * p2, big) > 0;
+    if (have_far) { cudaEventRecord(Sk, sc); cudaStreamWaitEvent(sb, Sk, 0); }
+    // near part: the next outer panel's columns below its first diagonal block (head(p1-1) took A_{p1,p1})
+    if (i8) launch_syrk_i8(h, sc, p1 + 1, 2 * p1, 2 * p2, nullptr, std::max(8, h->num_sms - near_reserve));
+    else syrk(sc, p0, p1 - p0, p1 + 1, nblk, 2 * p1, 2 * p2);
+    cudaEventRecord(Re(p1 - 1), sc);
+    if (have_far) {
+      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
+      if (i8) launch_syrk_i8(h, sb, p1, 2 * p2, big, nullptr, std::max(8, h->num_sms - reserve)); else syrk(sb, p0, p1 - p0, p1, nblk, 2 * p2, big);
+      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
+      cudaEventRecord(Rk, sb);
+    }
+  }
+  int j = 0;
+  for (cudaStream_t st : {sb, sc, sd, se}) {               // join
+    cudaEventRecord(h->ch_ev[6 * nblk + j], st);
+    cudaStreamWaitEvent(sa, h->ch_ev[6 * nblk + j], 0);
+    ++j;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cholesky(b200bo_handle_s* h) {
+  static const int sched = getenv("B200BO_CHOL_SCHED") ? atoi(getenv("B200BO_CHOL_SCHED")) : 1;   // developer knob: 0 = the in-order schedule of round 1
+  const int sc = h->chol_sched >= 0 ? h->chol_sched : sched;       // 1: look-ahead with the fused cluster head, 2: look-ahead with tile-GEMM heads
+  return sc ? launch_cholesky_lookahead(h, sc == 1) : launch_cholesky_inorder(h);
 }
 
 }  // namespace b200bo

@@ -81,6 +81,11 @@ struct b200bo_handle_s {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaStream_t stream2 = nullptr;     // look-ahead stream of the factorisation (trailing update k overlaps panel k+1)
+  cudaStream_t stream3 = nullptr;     // rest stream of the look-ahead schedule (chol.cu): everything of panel k that potrf(k+1) does not need
+  cudaStream_t stream4 = nullptr, stream5 = nullptr;   //   its bulk-update and rider streams
+  std::vector<cudaEvent_t> ch_ev;     // per block: potrf / head / column path / panel solve / bulk update / boundary share done
+  double* dD = nullptr;               // [128][128] scratch accumulator of the boundary diagonal block (look-ahead schedule)
+  int chol_sched = -1;                // -1: default (look-ahead), 0: in-order schedule of round 1, 1: look-ahead
   std::vector<cudaEvent_t> la_ev;     // look-ahead dependencies
   std::vector<cudaEvent_t> fw_ev;     // per panel: the forward solve of y - m rides along the factorisation on stream2
   cudaEvent_t ev[8] = {};
