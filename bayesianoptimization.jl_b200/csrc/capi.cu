@@ -40,6 +40,7 @@ int num_params(const b200bo_handle_s* h) {
 }
 
 void free_device(b200bo_handle_s* h) {
+  release_cholesky_graph(h);
   cudaFree(h->dX); cudaFree(h->dZ); cudaFree(h->dZk); cudaFree(h->dy); cudaFree(h->dw); cudaFree(h->dalpha); cudaFree(h->dz); cudaFree(h->dflags); cudaFree(h->dinv_ell);
   cudaFree(h->dL); cudaFree(h->dLinv); cudaFree(h->dLinvT); cudaFree(h->dV); cudaFree(h->dKi); cudaFree(h->dWT); cudaFree(h->dTT); cudaFree(h->dSl); cudaFree(h->dSe); cudaFree(h->dscal); cudaFree(h->dinfo);
   cudaFree(h->dcta_best); cudaFree(h->dbest); cudaFree(h->dpart); cudaFree(h->dD); h->dD = nullptr;
@@ -1285,7 +1286,7 @@ static int32_t mll_sweep_impl(b200bo_handle_t h, const double* Theta, int32_t P,
         if (e) { rcs[k] = e; return; }
         wk->synced_version = h->data_version;
       }
-      wk->hp = h->hp; wk->syrk_engine = h->syrk_engine; wk->chol_sched = h->chol_sched; wk->fitted = false;
+      wk->hp = h->hp; wk->syrk_engine = h->syrk_engine; wk->chol_sched = h->chol_sched; wk->chol_graph = h->chol_graph; wk->fitted = false;
       int64_t lo, hi; shard_bounds(S, K, k, &lo, &hi);
       if (hi > lo) rcs[k] = b200bo_mll_sweep(wk, Theta + lo * P, P, (int32_t)(hi - lo), mask, mll + lo, dmll ? dmll + lo * P : nullptr);
     };
@@ -1392,6 +1393,7 @@ B200BO_API int32_t b200bo_set_knob(b200bo_handle_t h, const char* name, int64_t 
   else if (k == "acq_gemm_timing") h->acq_time_gemm = value != 0;
   else if (k == "sweep_workers") { if (value < 0 || value > 32) return fail(h, B200BO_ERR_ARG, "sweep_workers must be in 0..32"); h->sweep_workers = (int)value; }
   else if (k == "chol_sched") { if (value < -1 || value > 2) return fail(h, B200BO_ERR_ARG, "chol_sched must be -1 (default), 0 (in-order), 1 (look-ahead, fused head) or 2 (look-ahead, tile-GEMM heads)"); h->chol_sched = (int)value; for (auto* w : h->workers) w->chol_sched = (int)value; }
+  else if (k == "chol_graph") { if (value < -1 || value > 1) return fail(h, B200BO_ERR_ARG, "chol_graph must be -1 (default), 0 (eager launches) or 1 (captured CUDA graph)"); h->chol_graph = (int)value; for (auto* w : h->workers) w->chol_graph = (int)value; }
   else return fail(h, B200BO_ERR_ARG, "unknown knob: " + k);
   for (auto* r : h->replicas) b200bo_set_knob(r, name, value);
   return B200BO_OK;

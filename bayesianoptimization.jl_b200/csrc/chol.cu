@@ -41,9 +41,10 @@ namespace b200bo {
 constexpr int PLD = 132;                 // shared-memory row stride of the block (doubles)
 constexpr int PD_THREADS = 256;
 constexpr int PSUB = 32;                 // sub-panel width
-constexpr size_t PD_SMEM = (size_t)(NB * PLD + PSUB * PSUB + 3 * PSUB * PSUB + 2 * NB + 2 * PSUB + 2) * sizeof(double);
+constexpr size_t PD_SMEM = (size_t)(NB * PLD + PSUB * PSUB + 3 * PSUB * PSUB + 2 * NB + 2 * PSUB + 2 + PSUB) * sizeof(double);
 
 #ifdef POTRF_PROF
+__device__ unsigned long long g_head_prof[8];
 __device__ unsigned long long g_potrf_prof[16];
 #define PROF_T(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); g_potrf_prof[i] += (unsigned long long)(_t - t_prev); t_prev = _t; } } while (0)
 #else
@@ -65,6 +66,31 @@ __device__ __forceinline__ void rank32_tile(double* __restrict__ S, int r0, int 
   }
   c.x += e0; c.y += e1;
   *cp = c;
+}
+
+
+// two independent tiles at once (four accumulator chains in flight): the loads of both are issued before either product chain
+__device__ __forceinline__ void rank32_tile_pair(double* __restrict__ S, int r0a, int q0a, int r0b, int q0b, int k0, int g, int q) {
+  double2* cpa = reinterpret_cast<double2*>(S + (r0a + g) * PLD + q0a + 2 * q);
+  double2* cpb = reinterpret_cast<double2*>(S + (r0b + g) * PLD + q0b + 2 * q);
+  double2 ca = *cpa, cb2 = *cpb;
+  double ea0 = 0.0, ea1 = 0.0, eb0 = 0.0, eb1 = 0.0;
+  const double* apa = S + (r0a + g) * PLD + k0 + q;
+  const double* bpa = S + (q0a + g) * PLD + k0 + q;
+  const double* apb = S + (r0b + g) * PLD + k0 + q;
+  const double* bpb = S + (q0b + g) * PLD + k0 + q;
+  double aa[PSUB / 4], ba[PSUB / 4], ab[PSUB / 4], bb[PSUB / 4];
+#pragma unroll
+  for (int ks = 0; ks < PSUB / 4; ++ks) { aa[ks] = apa[4 * ks]; ba[ks] = bpa[4 * ks]; ab[ks] = apb[4 * ks]; bb[ks] = bpb[4 * ks]; }
+#pragma unroll
+  for (int ks = 0; ks < PSUB / 4; ks += 2) {
+    dmma884(ca.x, ca.y, -aa[ks], ba[ks]);
+    dmma884(cb2.x, cb2.y, -ab[ks], bb[ks]);
+    dmma884(ea0, ea1, -aa[ks + 1], ba[ks + 1]);
+    dmma884(eb0, eb1, -ab[ks + 1], bb[ks + 1]);
+  }
+  ca.x += ea0; ca.y += ea1; cb2.x += eb0; cb2.y += eb1;
+  *cpa = ca; *cpb = cb2;
 }
 
 // 1/d and 1/sqrt(d) for d > 0 (normal range): MUFU seed + ONE cubically convergent step (3 dependent FP64 operations instead of
@@ -91,6 +117,7 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 // `phases`: 1 = the products P_j only (they need block rows < i of W, not W_ii), 2 = the final products only, 3 = both.
 __device__ __forceinline__ void winv_block_row(double* __restrict__ S, double* __restrict__ Pb, int i, int wid, int nw, bool named, int g,
                                                int q, int phases = 3) {
+  const int nthr = 32 * nw;
   // P_j = sum_k L_ik W_kj  (32 x 32, K = 32 (i - j)); two accumulator chains per 8 x 8 tile
   if (phases & 1)
   for (int t = wid; t < i * 16; t += nw) {
@@ -113,7 +140,7 @@ __device__ __forceinline__ void winv_block_row(double* __restrict__ S, double* _
     double* pp = Pb + (j * PSUB + 8 * tr + g) * PSUB + 8 * tc + 2 * q;
     *reinterpret_cast<double2*>(pp) = make_double2(c0a + e0a, c1a + e1a);
   }
-  if (phases == 3) { if (named) asm volatile("bar.sync 1, 224;\n" ::: "memory"); else __syncthreads(); }
+  if (phases == 3) { if (named) asm volatile("bar.sync 1, %0;\n" ::"r"(nthr) : "memory"); else __syncthreads(); }
   // W_ij = -W_ii P_j, stored transposed into the upper triangle
   if (phases & 2)
   for (int t = wid; t < i * 16; t += nw) {
@@ -142,8 +169,9 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
   double* Pb = Mt + PSUB * PSUB;           // [3][32][32] products of the block inverse
   double* rinv = Pb + 3 * PSUB * PSUB;     // [NB] 1 / l_ii
   double* ldiag = rinv + NB;               // [NB] l_ii
-  double* cb = ldiag + NB;                 // [2][32] column exchange buffer of F(s)
+  double* cb = ldiag + NB;                 // [32] pivots d_j of the current sub-block, published column by column (+ 32 spare)
   uint64_t* bar = reinterpret_cast<uint64_t*>(cb + 2 * PSUB);
+  uint64_t* colbar = bar + 1;              // [32] "column j of the current sub-block's unit factor is in Mt" (phase = s & 1)
   const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler
   double* Ab = A + ((int64_t)kb * NB) * ld + (int64_t)kb * NB;
@@ -152,6 +180,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
 #endif
   // ---- load the lower triangle: one 1-D TMA bulk copy per row (the strictly upper part is never read before it is written) ----
   if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (tid < PSUB) mbar_init(&colbar[tid], 1);      // generic-proxy waiters only: the __syncthreads below publishes them
   __syncthreads();
   if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(8 * (NB / 2) * (NB / 2 + 1) * 2));   // sum_i 8 * ((i + 2) & ~1)
   __syncthreads();
@@ -166,11 +195,17 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
 #pragma unroll 1
   for (int s = 0; s < NB / PSUB; ++s) {
     const int c0 = s * PSUB;
+    // Roles while the diagonal sub-block is factored.  warp 0: F(s).  warps 1 .. 3-s: T(s), one thread per row below, TRAILING the
+    // factorisation column by column (column j of the unit factor is published through colbar[j] the moment F(s) has it).  warp 5: the
+    // inverse of the sub-block, trailing likewise.  The other 3 + s warps: the look-ahead work U2(s-1) and block row s-1 of L^-1.
+    const int nT = NB / PSUB - 1 - s;                  // warps that own rows below
+    const uint32_t cpar = (uint32_t)s & 1u;
+    double y[PSUB];                                    // T(s): this thread's row;  inverse: this lane's column
     if (warp == 0) {
       // ---------------- F(s): 32 x 32 factorisation in registers, lane = row, square-root free on the chain ----------------
       // a[j] holds the UNSCALED column c_ij = l_ij sqrt(d_j); the update is a_ik -= c_ij (c_kj / d_j).  The only serial chain is
-      // d_j -> 1/d_j -> d_{j+1} (the diagonal stays in the owning lane); the scaled column c_kj / d_j reaches the other lanes
-      // through a 2 x 32 shared-memory buffer (one STS + broadcast LDS.128 instead of 31 shuffle pairs per column).
+      // d_j -> 1/d_j -> d_{j+1} (the diagonal stays in the owning lane); the scaled column c_kj / d_j = l_kj / l_jj reaches the other
+      // lanes -- and the trailing warps -- through Mt (one STS + broadcast LDS.128 instead of 31 shuffle pairs per column).
       double a[PSUB];
       const double* row = S + (c0 + lane) * PLD + c0;
 #pragma unroll
@@ -188,8 +223,8 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
       double rc = fast_rcp(d);
 #pragma unroll
       for (int j = 0; j < PSUB; ++j) {
-        double* cbj = cb + (j & 1) * PSUB;
-        cbj[lane] = a[j] * rc;                        // c_ij / d_j
+        double* cbj = Mt + j * PSUB;
+        cbj[lane] = a[j] * rc;                        // c_ij / d_j  (meaningful for lanes i > j)
         my_d = (lane == j) ? d : my_d;
         dg = fma(-(a[j] * a[j]), rc, dg);             // lanes i > j (a[j]^2 is ready before rc is)
         double dn = 1.0, rcn = 1.0;
@@ -200,6 +235,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
           rcn = fast_rcp(dn);
         }
         __syncwarp();
+        if (lane == 0) { cb[j] = d; mbar_arrive(&colbar[j]); }   // column j and its pivot d_j are published (release)
 #pragma unroll
         for (int k = (j + 1) & ~1; k < PSUB; k += 2) {
           const double2 m = *reinterpret_cast<const double2*>(cbj + k);
@@ -216,17 +252,46 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
       double* wrow = S + (c0 + lane) * PLD + c0;
 #pragma unroll
       for (int j = 0; j < PSUB; ++j) {
-        const double rj = rinv[c0 + j];
-        const double l = a[j] * rj;                   // l_ij
+        const double l = a[j] * rinv[c0 + j];         // l_ij
         if (j < lane) wrow[j] = l;
-        Mt[j * PSUB + lane] = (j < lane) ? l * rj : 0.0;
       }
       wrow[lane] = my_rs;                             // the diagonal of S carries w_ii = 1 / l_ii
+    } else if (warp <= nT) {
+      // ---------------- T(s), trailing: y_c = x_c l_cc;  y_c2 -= y_c (l_c2,c / l_cc) as soon as column c is out ----------------
+      const int r = c0 + PSUB + (tid - 32);
+      double* row = S + r * PLD + c0;
+#pragma unroll
+      for (int j = 0; j < PSUB; j += 2) { const double2 v = *reinterpret_cast<const double2*>(row + j); y[j] = v.x; y[j + 1] = v.y; }
+      double xe = 0.0;
+#pragma unroll
+      for (int c = 0; c < PSUB; ++c) {
+        mbar_wait(&colbar[c], cpar);
+        const double x = y[c] * fast_rsqrt(cb[c]);    // l_rc = y_c / l_cc: final, stored in pairs (the trailing warp has the time for the rsqrt)
+        if (c & 1) *reinterpret_cast<double2*>(row + c - 1) = make_double2(xe, x); else xe = x;
+#pragma unroll
+        for (int c2 = c + 1; c2 < PSUB; ++c2) y[c2] = fma(-y[c], Mt[c * PSUB + c2], y[c2]);
+      }
+    } else if (warp == 5) {
+      // ---------------- W = L11^-1, trailing, lane = column c:  v_k = w_k l_kk = (k == c) ? 1 : acc_k,  acc_i -= (l_ik / l_kk) v_k ------
+#pragma unroll
+      for (int i = 0; i < PSUB; ++i) y[i] = 0.0;
+      double* wrow = S + (c0 + lane) * PLD + c0;      // (W^T)[c][i] = W[i][c] -> strictly upper part of row c
+#pragma unroll
+      for (int k = 0; k < PSUB; ++k) {
+        mbar_wait(&colbar[k], cpar);
+        const double vk = (k == lane) ? 1.0 : y[k];
+        if (k > lane) wrow[k] = vk * fast_rsqrt(cb[k]);
+#pragma unroll
+        for (int i = k + 1; i < PSUB; ++i) y[i] = fma(-Mt[k * PSUB + i], vk, y[i]);
+      }
     } else {
+      // ---------------- look-ahead workers: the warps of {1..7} that are neither T(s) rows nor the inverse ----------------
+      const int nw = NB / PSUB - 1 + s;                                   // 3 + s
+      const int wid = (warp - (nT + 1)) - (warp > 5 ? 1 : 0);
       if (s > 0) {
-        // ---------------- U2(s-1): far part of the previous rank-32 update (columns >= c0 + 32) ----------------
+        // U2(s-1): far part of the previous rank-32 update (columns >= c0 + 32)
         const int k0 = c0 - PSUB, t0 = (c0 + PSUB) / 8, n = NB / 8 - t0;     // tile rows/cols t0 .. 15
-        for (int t = warp - 1; t < n * (n + 1) / 2; t += PD_THREADS / 32 - 1) {
+        for (int t = wid; t < n * (n + 1) / 2; t += nw) {
           int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
           while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
           while (ti * (ti + 1) / 2 > t) --ti;
@@ -235,59 +300,38 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
         }
       }
       // block row s-1 of L^-1 (needs the inverses of diagonal sub-blocks 0 .. s-1): hidden behind F(s)
-      if (s >= 2) winv_block_row(S, Pb, s - 1, warp - 1, PD_THREADS / 32 - 1, true, g, q);
+      if (s >= 2) winv_block_row(S, Pb, s - 1, wid, nw, true, g, q);
       if (s == NB / PSUB - 1) {   // the products of the LAST block row only need rows < 3 of W: also hidden behind F(3)
-        asm volatile("bar.sync 1, 224;\n" ::: "memory");       // row s-1 of W complete, Pb free again
-        winv_block_row(S, Pb, s, warp - 1, PD_THREADS / 32 - 1, true, g, q, 1);
+        asm volatile("bar.sync 1, %0;\n" ::"r"(32 * nw) : "memory");       // row s-1 of W complete, Pb free again
+        winv_block_row(S, Pb, s, wid, nw, true, g, q, 1);
       }
     }
 #ifdef POTRF_PROF
     if (threadIdx.x == 0) g_potrf_prof[8 + s] += (unsigned long long)(clock64() - t_prev);      // warp 0's own F(s) time
 #endif
     __syncthreads();
+#ifdef POTRF_PROF
+    if (threadIdx.x == 0) g_potrf_prof[12 + s] += (unsigned long long)(clock64() - t_prev);     // the whole phase A(s)
+#endif
     PROF_T(1);
-    // ---------------- T(s): rows below (warps 1-3) and the inverse of L11 (warp 4); one FMA per column on either chain --------
-    if (warp >= 1 && warp <= 3) {
-      const int r = c0 + PSUB + (tid - 32);
-      if (r < NB) {
-        double y[PSUB];                               // y_c = x_c l_cc:  y_c2 -= y_c (l_c2,c / l_cc)
-        double* row = S + r * PLD + c0;
-#pragma unroll
-        for (int j = 0; j < PSUB; j += 2) { const double2 v = *reinterpret_cast<const double2*>(row + j); y[j] = v.x; y[j + 1] = v.y; }
-#pragma unroll
-        for (int c = 0; c < PSUB; ++c) {
-#pragma unroll
-          for (int c2 = c + 1; c2 < PSUB; ++c2) y[c2] = fma(-y[c], Mt[c * PSUB + c2], y[c2]);
-        }
-#pragma unroll
-        for (int j = 0; j < PSUB; j += 2)
-          *reinterpret_cast<double2*>(row + j) = make_double2(y[j] * rinv[c0 + j], y[j + 1] * rinv[c0 + j + 1]);
-      }
-    } else if (warp == 4) {
-      // W = L11^-1, lane = column c:  v_k = w_k l_kk = (k == c) ? 1 : nacc_k,   nacc_i -= (l_ik / l_kk) v_k   (v_k = 0 for k < c)
-      double nacc[PSUB];
-#pragma unroll
-      for (int i = 0; i < PSUB; ++i) nacc[i] = 0.0;
-      double* wrow = S + (c0 + lane) * PLD + c0;      // (W^T)[c][i] = W[i][c] -> strictly upper part of row c
-#pragma unroll
-      for (int k = 0; k < PSUB; ++k) {
-        const double vk = (k == lane) ? 1.0 : nacc[k];
-        if (k > lane) wrow[k] = vk * rinv[c0 + k];
-#pragma unroll
-        for (int i = k + 1; i < PSUB; ++i) nacc[i] = fma(-Mt[k * PSUB + i], vk, nacc[i]);
-      }
-    }
-    __syncthreads();
     PROF_T(2);
     // ---------------- U1(s): rank-32 update of the next sub-panel's columns ----------------
     if (s + 1 < NB / PSUB) {
       const int t0 = (c0 + PSUB) / 8, nr = NB / 8 - t0;                    // tile rows t0 .. 15, tile cols t0 .. t0 + 3
       const int ntile = 10 + 4 * (nr - 4);
-      for (int t = warp; t < ntile; t += PD_THREADS / 32) {
-        int ti, tj;
+      auto tile_of = [&](int t, int& ti, int& tj) {
         if (t < 10) { ti = (t >= 6) ? 3 : (t >= 3) ? 2 : (t >= 1) ? 1 : 0; tj = t - ti * (ti + 1) / 2; }
         else { ti = 4 + ((t - 10) >> 2); tj = (t - 10) & 3; }
-        rank32_tile(S, 8 * (t0 + ti), 8 * (t0 + tj), c0, g, q);
+      };
+      for (int t = warp; t < ntile; t += 2 * (PD_THREADS / 32)) {           // two tiles per step: t and t + 8
+        int ti, tj, ui, uj;
+        tile_of(t, ti, tj);
+        if (t + PD_THREADS / 32 < ntile) {
+          tile_of(t + PD_THREADS / 32, ui, uj);
+          rank32_tile_pair(S, 8 * (t0 + ti), 8 * (t0 + tj), 8 * (t0 + ui), 8 * (t0 + uj), c0, g, q);
+        } else {
+          rank32_tile(S, 8 * (t0 + ti), 8 * (t0 + tj), c0, g, q);
+        }
       }
       __syncthreads();
     }
@@ -297,21 +341,25 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
   winv_block_row(S, Pb, NB / PSUB - 1, warp, PD_THREADS / 32, false, g, q, 2);   // W_3j = -W_33 P_j (P_j computed during F(3))
   __syncthreads();
   PROF_T(4);
-  // ---------------- write-back: mirrored factor block (full), L^-1 (lower) and L^-T (upper); the other triangles of the inverse
-  // buffers are zero from allocation and never written.  Every warp store = 4 rows x 64 bytes. ----------------
+  // ---------------- write-back of the two triangles that shared memory holds row-wise: L (lower, with its diagonal) into the factor and
+  // L^-T (upper) into LinvT -- 16-byte pieces, a warp store = 512 contiguous bytes of one row.  Their transposes (the mirrored upper
+  // triangle of the factor block, L^-1) are written by chol_mirror_kernel OFF the critical chain: one SM stores ~64 B/clk, and the four
+  // triangles together (393 KB) were 10.7 k of this kernel's 80 k cycles. ----------------
   {
-    double* Li = Linv + (int64_t)kb * NB * NB;
     double* LiT = LinvT + (int64_t)kb * NB * NB;
-    const int il = lane >> 3, cl = lane & 7;
 #pragma unroll 4
-    for (int pt = warp; pt < (NB / 4) * (NB / 8); pt += PD_THREADS / 32) {
-      const int i = 4 * (pt >> 4) + il, c = 8 * (pt & 15) + cl;
-      const int hi = i >= c ? i : c, lo = i >= c ? c : i;
-      const double lv = (i == c) ? ldiag[i] : S[hi * PLD + lo];   // L[max][min]
-      const double wv = S[lo * PLD + hi];                          // W[max][min]
-      Ab[(int64_t)i * ld + c] = lv;
-      if (i >= c) Li[i * NB + c] = wv;                // W[i][c]
-      if (i <= c) LiT[i * NB + c] = wv;               // (W^T)[i][c] = W[c][i]
+    for (int p = tid; p < NB * (NB / 2); p += PD_THREADS) {
+      const int i = p >> 6, c = 2 * (p & 63);
+      const double2 t = *reinterpret_cast<const double2*>(S + i * PLD + c);
+      if (c <= i) {                                    // L[i][c .. c+1]; beyond the diagonal the mirror kernel writes
+        double2 v = t;
+        if (c == i) v.x = ldiag[i];
+        if (c + 1 == i) v.y = ldiag[i];
+        if (c + 1 <= i) *reinterpret_cast<double2*>(Ab + (int64_t)i * ld + c) = v; else Ab[(int64_t)i * ld + c] = v.x;
+      }
+      if (c + 1 >= i) {                                // (W^T)[i][c .. c+1] = W[c .. c+1][i]: row i of S, diagonal w_ii included
+        if (c >= i) *reinterpret_cast<double2*>(LiT + i * NB + c) = t; else LiT[i * NB + c + 1] = t.y;
+      }
     }
   }
 #ifdef POTRF_PROF
@@ -327,7 +375,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
 //   phase 2   A_{k+1,k+1} -= X X^T              (lower tiles; + the scratch accumulator D of an outer-panel boundary)
 // CTA r owns the 8-row tiles r and 15 - r of the block row (balanced triangle); W_k and the CTA's rows of A arrive by 1-D TMA bulk
 // copies; every CTA keeps its 16 rows of X in shared memory and phase 2 reads the other CTAs' rows through distributed shared
-// memory.  All products on the FP64 tensor pipe (DMMA.8x8x4), four independent accumulator chains per warp.
+// memory (gathered into local shared memory in one sweep).  All products on the FP64 tensor pipe (DMMA.8x8x4), four independent accumulator chains per warp.
 // The tile GEMM kernels need ~12 us per launch for this (one 128 x 64 x 128 tile per CTA is 8.4 us of DMMA on one SM): twice that sat
 // between every two diagonal blocks.
 // ------------------------------------------------------------------------------------------------------------
@@ -335,10 +383,10 @@ constexpr int HC = 8;
 constexpr size_t HEAD_SMEM = (size_t)(NB * PLD + 2 * 16 * PLD) * sizeof(double) + 16;
 
 __global__ void __cluster_dims__(HC, 1, 1) __launch_bounds__(256, 1) chol_head_kernel(double* __restrict__ A, int64_t ld, int kb,
-                                                                                       const double* __restrict__ Linv,
+                                                                                       const double* __restrict__ LinvT,
                                                                                        const double* __restrict__ Dacc) {
   extern __shared__ __align__(16) double sm[];
-  double* W = sm;                        // [128][PLD] lower triangle of W_k
+  double* W = sm;                        // [128][PLD] upper triangle of W_k^T: W[j][l] at W[l * PLD + j]  (later: the gathered rows of X)
   double* As = W + NB * PLD;             // [16][PLD] this CTA's rows of A_{k+1,k}
   double* Xs = As + 16 * PLD;            // [16][PLD] this CTA's rows of X
   uint64_t* bar = reinterpret_cast<uint64_t*>(Xs + 16 * PLD);
@@ -353,10 +401,10 @@ __global__ void __cluster_dims__(HC, 1, 1) __launch_bounds__(256, 1) chol_head_k
   __syncthreads();
   if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(8 * (NB / 2) * (NB / 2 + 1) * 2 + 16 * NB * 8));
   __syncthreads();
-  if (tid < NB) {
-    const uint32_t bytes = (uint32_t)(((tid + 2) & ~1) * 8);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(W + tid * PLD)),
-                 "l"(Linv + (int64_t)kb * NB * NB + (int64_t)tid * NB), "r"(bytes), "r"(smem_u32(bar))
+  if (tid < NB) {                                      // row l = tid of W^T: entries j >= l (from the even column below l)
+    const int c0 = tid & ~1;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(W + tid * PLD + c0)),
+                 "l"(LinvT + (int64_t)kb * NB * NB + (int64_t)tid * NB + c0), "r"((uint32_t)((NB - c0) * 8)), "r"(smem_u32(bar))
                  : "memory");
   } else if (tid < NB + 16) {
     const int rr = tid - NB, row = (rr < 8 ? mrow0 : mrow1) + (rr & 7);
@@ -380,25 +428,32 @@ __global__ void __cluster_dims__(HC, 1, 1) __launch_bounds__(256, 1) chol_head_k
       if (Dacc) { const double2 d = *reinterpret_cast<const double2*>(Dacc + row * NB + col); c[i].x += d.x; c[i].y += d.y; }
     }
   }
+#ifdef POTRF_PROF
+  long long hp_t = clock64();
+#define HPROF(i) do { if (tid == 0 && r == 0) { const long long _t = clock64(); g_head_prof[i] += (unsigned long long)(_t - hp_t); hp_t = _t; } } while (0)
+#else
+#define HPROF(i) do {} while (0)
+#endif
   mbar_wait(bar, 0);
+  HPROF(0);
   // ---- phase 1: X(16 x 128) = As W^T; warp w computes column tiles w and 15 - w for both m-tiles ----
 #pragma unroll
   for (int ni = 0; ni < 2; ++ni) {
     const int jt = ni ? 15 - warp : warp;
-    const double* brow = W + (8 * jt + g) * PLD + q;
+    const double* brow = W + q * PLD + 8 * jt + g;     // B[k = q][n = g] = W[8 jt + g][l0 + q] = (W^T)[l0 + q][8 jt + g]
     const double* a0 = As + g * PLD + q;
     const double* a1 = As + (8 + g) * PLD + q;
     double2 x0 = make_double2(0.0, 0.0), x1 = x0, y0 = x0, y1 = x0;
-#pragma unroll 2
+#pragma unroll 4
     for (int ks = 0; ks < 2 * jt; ks += 2) {          // l < 8 jt: full k-steps, two chains per m-tile
-      const double b0 = brow[4 * ks], b1 = brow[4 * ks + 4];
+      const double b0 = brow[4 * ks * PLD], b1 = brow[(4 * ks + 4) * PLD];
       dmma884(x0.x, x0.y, a0[4 * ks], b0);
       dmma884(x1.x, x1.y, a1[4 * ks], b0);
       dmma884(y0.x, y0.y, a0[4 * ks + 4], b1);
       dmma884(y1.x, y1.y, a1[4 * ks + 4], b1);
     }
     {                                                 // the two k-steps that straddle the diagonal of W: l <= j only
-      const double b0 = (q <= g) ? brow[8 * jt] : 0.0, b1 = (4 + q <= g) ? brow[8 * jt + 4] : 0.0;
+      const double b0 = (q <= g) ? brow[8 * jt * PLD] : 0.0, b1 = (4 + q <= g) ? brow[(8 * jt + 4) * PLD] : 0.0;
       dmma884(x0.x, x0.y, a0[8 * jt], b0);
       dmma884(x1.x, x1.y, a1[8 * jt], b0);
       dmma884(y0.x, y0.y, a0[8 * jt + 4], b1);
@@ -415,17 +470,40 @@ __global__ void __cluster_dims__(HC, 1, 1) __launch_bounds__(256, 1) chol_head_k
     up[mrow0 + g] = x0.x; up[ld + mrow0 + g] = x0.y;
     up[mrow1 + g] = x1.x; up[ld + mrow1 + g] = x1.y;
   }
-  cluster.sync();                                     // every CTA's rows of X are in its shared memory
+  HPROF(1);
+  cluster.sync();                                     // every CTA's rows of X are in its shared memory; W is dead from here on
+  HPROF(2);
+  // ---- gather the rows of X this CTA multiplies with (rows 0 .. 8 (16 - r) - 1 of the slab) into the W region.  They come back from
+  //      L2, where every CTA has just written its rows of L_{k+1,k} (cluster.sync orders those writes; ld.global.cg bypasses L1): pulling
+  //      them through distributed shared memory instead measured 8.8 k cycles for the 128 KB of CTA 0 (~15 B/clk) ----
+  {
+    const int npiece = (16 - r) * 8 * (NB / 2);        // 16-byte pieces: 64 per row
+    const double* Xg = Ablk + (int64_t)kb * NB;        // row i of the slab at Xg + i * ld
+    for (int p = tid; p < npiece; p += 8 * 256) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int pp = p + u * 256;
+        if (pp < npiece) v[u] = __ldcg(reinterpret_cast<const double2*>(Xg + (int64_t)(pp >> 6) * ld + 2 * (pp & 63)));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int pp = p + u * 256;
+        if (pp < npiece) *reinterpret_cast<double2*>(W + (pp >> 6) * PLD + 2 * (pp & 63)) = v[u];
+      }
+    }
+  }
+  __syncthreads();
+  HPROF(3);
   // ---- phase 2: A_{k+1,k+1}(own rows, column tiles <= m-tile) -= X X^T, K = 128 in four chains ----
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (tm[i] < 0) continue;
     const int jt = tj[i];
-    const int owner = jt < 8 ? jt : 15 - jt;
-    const double* xb = cluster.map_shared_rank(Xs, owner) + ((jt < 8 ? 0 : 8) + g) * PLD + q;
+    const double* xb = W + (8 * jt + g) * PLD + q;
     const double* xa = Xs + (8 * tm[i] + g) * PLD + q;
     double2 e1 = make_double2(0.0, 0.0), e2 = e1, e3 = e1;
-#pragma unroll 2
+#pragma unroll
     for (int ks = 0; ks < NB / 4; ks += 4) {
       dmma884(c[i].x, c[i].y, -xa[4 * ks], xb[4 * ks]);
       dmma884(e1.x, e1.y, -xa[4 * ks + 4], xb[4 * ks + 4]);
@@ -436,7 +514,40 @@ __global__ void __cluster_dims__(HC, 1, 1) __launch_bounds__(256, 1) chol_head_k
     const int row = (tm[i] ? mrow1 : mrow0) + g, col = 8 * jt + 2 * q;
     *reinterpret_cast<double2*>(Ablk + (int64_t)row * ld + (int64_t)b * NB + col) = c[i];
   }
+  HPROF(4);
   cluster.sync();                                     // no CTA leaves while its rows of X are still being read
+  HPROF(5);
+}
+
+// Mirrors of diagonal block kb, off the critical chain: the upper triangle of the factor block (L^T) from its lower triangle, and
+// L^-1 (lower, row-major) from L^-T.  One CTA per 32 x 32 tile on or below the diagonal and per matrix (2 x 10 CTAs), transposed
+// through shared memory.
+__global__ void __launch_bounds__(256) chol_mirror_kernel(double* __restrict__ A, int64_t ld, int kb, double* __restrict__ Linv,
+                                                          const double* __restrict__ LinvT) {
+  __shared__ double T[32][33];
+  const int which = blockIdx.x / 10;                   // 0: factor block, 1: inverse
+  int t = blockIdx.x % 10, bi = 0;
+  while (t > bi) { t -= bi + 1; ++bi; }
+  const int bj = t;                                    // tile (bi, bj), bj <= bi
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (which == 0) {
+    double* Ab = A + ((int64_t)kb * NB) * ld + (int64_t)kb * NB;
+    for (int r = ty; r < 32; r += 8) T[r][tx] = Ab[(int64_t)(32 * bi + r) * ld + 32 * bj + tx];          // lower tile (bi, bj)
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                 // upper tile (bj, bi): element (32 bj + r, 32 bi + tx) = L[32 bi + tx][32 bj + r]
+      const int gi = 32 * bj + r, gc = 32 * bi + tx;
+      if (gc > gi) Ab[(int64_t)gi * ld + gc] = T[tx][r];
+    }
+  } else {
+    const double* LiT = LinvT + (int64_t)kb * NB * NB;
+    double* Li = Linv + (int64_t)kb * NB * NB;
+    for (int r = ty; r < 32; r += 8) T[r][tx] = LiT[(32 * bj + r) * NB + 32 * bi + tx];                  // upper tile (bj, bi) of W^T
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                 // W[32 bi + r][32 bj + tx] = (W^T)[32 bj + tx][32 bi + r]
+      const int gi = 32 * bi + r, gc = 32 * bj + tx;
+      if (gc <= gi) Li[gi * NB + gc] = T[tx][r];
+    }
+  }
 }
 
 struct CholMaps { CUtensorMap L128, L64, Linv; };
@@ -555,7 +666,8 @@ static cudaError_t launch_cholesky_inorder(b200bo_handle_s* h) {
     const int p0 = P * OB, p1 = (p0 + OB < nblk) ? p0 + OB : nblk, p2 = (p1 + OB < nblk) ? p1 + OB : nblk;
     for (int k = p0; k < p1; ++k) {
       potrf_diag_kernel<<<1, PD_THREADS, sm_potrf, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
-      h->launches++;
+      chol_mirror_kernel<<<20, 256, 0, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT);
+      h->launches += 2;
       cudaEventRecord(h->fw_ev[k], sa);
       cudaStreamWaitEvent(sb, h->fw_ev[k], 0);
       launch_fwd_step(h, sb, k - 1, nblk);
@@ -597,7 +709,8 @@ static cudaError_t launch_cholesky_inorder(b200bo_handle_s* h) {
     cudaMemcpyFromSymbol(pr, g_potrf_prof, sizeof(pr));
     fprintf(stderr, "potrf phases (cycles per kernel, %d kernels): load %llu | F+U2 %llu | T+inv %llu | U1 %llu | offdiag inverse %llu | write-back %llu\n", nblk,
             pr[0] / nblk, pr[1] / nblk, pr[2] / nblk, pr[3] / nblk, pr[4] / nblk, pr[5] / nblk);
-    fprintf(stderr, "  F(s) alone on warp 0: %llu %llu %llu %llu\n", pr[8] / nblk, pr[9] / nblk, pr[10] / nblk, pr[11] / nblk);
+    fprintf(stderr, "  F(s) alone on warp 0: %llu %llu %llu %llu | phase A(s): %llu %llu %llu %llu\n", pr[8] / nblk, pr[9] / nblk, pr[10] / nblk, pr[11] / nblk,
+            pr[12] / nblk, pr[13] / nblk, pr[14] / nblk, pr[15] / nblk);
     memset(pr, 0, sizeof(pr));
     cudaMemcpyToSymbol(g_potrf_prof, pr, sizeof(pr));
   }
@@ -617,7 +730,7 @@ static cudaError_t launch_cholesky_inorder(b200bo_handle_s* h) {
 //                           (A_{p1,p1} itself is still being written by the far update of the previous outer panel);
 //   stream B (far)          the far K = 512 update, low priority, on num_sms - reserve SMs as before.
 // Every tile still receives its updates in a fixed order (events), so repeated factorisations stay bit-identical.
-static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head) {
+static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head, bool capturing) {
   const int nblk = (int)(h->Np / NB);
   cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM);
   cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM);
@@ -644,7 +757,9 @@ static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head
   grow(h->syrk_ev, 2 * npan + 2, true);
   grow(h->la_ev, 3 * npan + 2, false);
   grow(h->fw_ev, nblk + 2, false);
-  grow(h->ch_ev, 6 * (size_t)nblk + 8, false);
+  static const bool trace_env = getenv("B200BO_CHOL_TRACE") != nullptr;  // developer knob: per-panel event timeline on stderr (eager launches only)
+  const bool trace = trace_env && !capturing;
+  grow(h->ch_ev, 6 * (size_t)nblk + 8, trace);
   h->syrk_ev_used = 0;
   const int big = 1 << 30;
   auto Pe = [&](int k) { return h->ch_ev[6 * k]; };        // potrf(k) done (chain)
@@ -668,8 +783,11 @@ static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head
     }
   };
   static const int reserve = getenv("B200BO_I8_RESERVE") ? atoi(getenv("B200BO_I8_RESERVE")) : 40;
-  static const int near_reserve = getenv("B200BO_I8_NEAR_RESERVE") ? atoi(getenv("B200BO_I8_NEAR_RESERVE")) : 16;
+  static const int near_reserve = getenv("B200BO_I8_NEAR_RESERVE") ? atoi(getenv("B200BO_I8_NEAR_RESERVE")) : 32;
+  // start / stop of the far updates (B200BO_T_SYRK): inside a captured graph they must be event-record NODES
+  auto stamp = [&](cudaEvent_t e, cudaStream_t st) { if (capturing) cudaEventRecordWithFlags(e, st, cudaEventRecordExternal); else cudaEventRecord(e, st); };
   cudaEventRecord(h->fw_ev[nblk], sa);
+  if (trace) cudaEventRecord(h->syrk_ev[2 * npan + 1], sa);
   for (cudaStream_t st : {sb, sc, sd, se}) cudaStreamWaitEvent(st, h->fw_ev[nblk], 0);
   launch_residual(h, se);                                  // the forward solve z = L^-1 (y - m) rides along (solve.cu: launch_fwd_step)
   for (int P = 0; P < npan; ++P) {
@@ -678,7 +796,14 @@ static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head
     for (int k = p0; k < p1; ++k) {
       potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT, h->dinfo);
       h->launches++;
+      // the transposed triangles of the block (L^T mirror, row-major L^-1) are nobody's business on the chain: the fused head reads L^-T
+      if (!fused_head) { chol_mirror_kernel<<<20, 256, 0, sa>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT); h->launches++; }
       cudaEventRecord(Pe(k), sa);
+      if (fused_head) {
+        cudaStreamWaitEvent(sc, Pe(k), 0);
+        chol_mirror_kernel<<<20, 256, 0, sc>>>(h->dL, h->ld, k, h->dLinv, h->dLinvT);
+        h->launches++;
+      }
       cudaStreamWaitEvent(se, Pe(k), 0);
       if (use_D && k == p0) cudaMemsetAsync(h->dD, 0, sizeof(double) * NB * NB, se);   // its last reader, head(p0-1), precedes potrf(p0)
       if (k > 0) cudaStreamWaitEvent(se, R1e(k - 1), 0);                    // L_{.,k-1} complete
@@ -691,7 +816,7 @@ static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head
       if (boundary && P > 0) cudaStreamWaitEvent(sa, h->la_ev[3 * (P - 1) + 1], 0);   // the far update of panel P-1 also writes A_{p1,p1}
       if (fused_head) {
         if (boundary && k > p0) cudaStreamWaitEvent(sa, De(k - 1), 0);      // panels p0 .. p1-2 left their share in the scratch accumulator
-        chol_head_kernel<<<HC, 256, HEAD_SMEM, sa>>>(h->dL, h->ld, k, h->dLinv, (boundary && k > p0) ? h->dD : nullptr);
+        chol_head_kernel<<<HC, 256, HEAD_SMEM, sa>>>(h->dL, h->ld, k, h->dLinvT, (boundary && k > p0) ? h->dD : nullptr);
         h->launches++;
       } else {
         trsm(sa, k, 0, NB / TG_BN);                                        // L_{k+1,k}
@@ -733,11 +858,32 @@ static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head
     else syrk(sc, p0, p1 - p0, p1 + 1, nblk, 2 * p1, 2 * p2);
     cudaEventRecord(Re(p1 - 1), sc);
     if (have_far) {
-      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
+      stamp(h->syrk_ev[h->syrk_ev_used++], sb);
       if (i8) launch_syrk_i8(h, sb, p1, 2 * p2, big, nullptr, std::max(8, h->num_sms - reserve)); else syrk(sb, p0, p1 - p0, p1, nblk, 2 * p2, big);
-      cudaEventRecord(h->syrk_ev[h->syrk_ev_used++], sb);
+      stamp(h->syrk_ev[h->syrk_ev_used++], sb);
       cudaEventRecord(Rk, sb);
     }
+  }
+#ifdef POTRF_PROF
+  if (!capturing) {
+    cudaDeviceSynchronize();
+    unsigned long long hp[8];
+    cudaMemcpyFromSymbol(hp, g_head_prof, sizeof(hp));
+    const int n = nblk > 1 ? nblk - 1 : 1;
+    fprintf(stderr, "head phases (cycles per kernel): load wait %llu | phase 1 %llu | sync %llu | gather %llu | phase 2 %llu | sync %llu\n", hp[0] / n, hp[1] / n, hp[2] / n,
+            hp[3] / n, hp[4] / n, hp[5] / n);
+    memset(hp, 0, sizeof(hp));
+    cudaMemcpyToSymbol(g_head_prof, hp, sizeof(hp));
+  }
+#endif
+  if (trace) {
+    cudaEventRecord(h->ch_ev[6 * nblk + 5], sa);
+    cudaStreamSynchronize(sa); cudaStreamSynchronize(sb); cudaStreamSynchronize(sc); cudaStreamSynchronize(sd); cudaStreamSynchronize(se);
+    auto at = [&](cudaEvent_t e) { float ms = -1.f; if (cudaEventElapsedTime(&ms, h->syrk_ev[2 * npan + 1], e) != cudaSuccess) { cudaGetLastError(); return -1.0; } return (double)ms * 1e3; };
+    fprintf(stderr, "# k: potrf done | head done | panel solve done | column path done | bulk done   (us since start)\n");
+    for (int k = 0; k < nblk - 1; ++k)
+      fprintf(stderr, "%3d: %9.1f %9.1f %9.1f %9.1f %9.1f\n", k, at(Pe(k)), at(He(k)), at(R1e(k)), at(Re(k)), at(Be(k)));
+    fprintf(stderr, "chain end %9.1f\n", at(h->ch_ev[6 * nblk + 5]));
   }
   int j = 0;
   for (cudaStream_t st : {sb, sc, sd, se}) {               // join
@@ -748,10 +894,60 @@ static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head
   return cudaGetLastError();
 }
 
+// The look-ahead schedule is ~25 launches and ~40 event operations per 128-column panel over five streams: enqueued one by one the HOST
+// becomes the critical path (the chain itself is ~50 us per panel).  The whole factorisation is therefore captured ONCE per shape into
+// a CUDA graph (the second time a shape is seen: the first run has made every lazy allocation) and replayed with one launch.
+// The graph bakes in pointers and panel counts: it is keyed on them and rebuilt when they change.
+static void drop_chol_graph(b200bo_handle_s* h) {
+  if (h->chol_graph_exec) cudaGraphExecDestroy(h->chol_graph_exec);
+  h->chol_graph_exec = nullptr; h->chol_graph_key = 0;
+}
+
+void release_cholesky_graph(b200bo_handle_s* h) { drop_chol_graph(h); }
+
 cudaError_t launch_cholesky(b200bo_handle_s* h) {
   static const int sched = getenv("B200BO_CHOL_SCHED") ? atoi(getenv("B200BO_CHOL_SCHED")) : 1;   // developer knob: 0 = the in-order schedule of round 1
+  static const int graph_env = getenv("B200BO_CHOL_GRAPH") ? atoi(getenv("B200BO_CHOL_GRAPH")) : 1;
   const int sc = h->chol_sched >= 0 ? h->chol_sched : sched;       // 1: look-ahead with the fused cluster head, 2: look-ahead with tile-GEMM heads
-  return sc ? launch_cholesky_lookahead(h, sc == 1) : launch_cholesky_inorder(h);
+  if (!sc) return launch_cholesky_inorder(h);
+  const bool want_graph = (h->chol_graph >= 0 ? h->chol_graph : graph_env) != 0;
+  if (!want_graph) return launch_cholesky_lookahead(h, sc == 1, false);
+  const bool i8 = h->syrk_engine < 0 ? syrk_i8_enabled() : h->syrk_engine >= 1;
+  uint64_t key = 1469598103934665603ull;
+  for (uint64_t v : {(uint64_t)(h->Np / NB), (uint64_t)sc, (uint64_t)(i8 ? 1 + h->syrk_engine : 0), (uint64_t)(uintptr_t)h->dL, (uint64_t)(uintptr_t)h->dLinv,
+                     (uint64_t)(uintptr_t)h->dSl, (uint64_t)(uintptr_t)h->dw, (uint64_t)h->ld, (uint64_t)(uintptr_t)h->stream})
+    key = (key ^ v) * 1099511628211ull;
+  if (h->chol_graph_exec && h->chol_graph_key == key) {
+    h->launches += h->chol_graph_launches;
+    h->syrk_ev_used = h->chol_graph_syrk_ev;
+    return cudaGraphLaunch(h->chol_graph_exec, h->stream);
+  }
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (h->chol_seen_key != key || cudaStreamIsCapturing(h->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    h->chol_seen_key = key;                                          // first sight of this shape (or a caller stream that is itself capturing): eager
+    return launch_cholesky_lookahead(h, sc == 1, false);
+  }
+  drop_chol_graph(h);
+  const int64_t launches0 = h->launches;
+  cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) { cudaGetLastError(); return launch_cholesky_lookahead(h, sc == 1, false); }
+  e = launch_cholesky_lookahead(h, sc == 1, true);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+  if (e != cudaSuccess || e2 != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    h->launches = launches0;
+    h->chol_graph = 0;                                               // capture is not possible here: stay eager
+    return launch_cholesky_lookahead(h, sc == 1, false);
+  }
+  e = cudaGraphInstantiate(&h->chol_graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { cudaGetLastError(); h->chol_graph_exec = nullptr; h->launches = launches0; h->chol_graph = 0; return launch_cholesky_lookahead(h, sc == 1, false); }
+  h->chol_graph_key = key;
+  h->chol_graph_launches = h->launches - launches0;
+  h->chol_graph_syrk_ev = h->syrk_ev_used;
+  return cudaGraphLaunch(h->chol_graph_exec, h->stream);
 }
 
 }  // namespace b200bo

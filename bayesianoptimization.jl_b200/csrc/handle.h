@@ -85,6 +85,11 @@ struct b200bo_handle_s {
   cudaStream_t stream4 = nullptr, stream5 = nullptr;   //   its bulk-update and rider streams
   std::vector<cudaEvent_t> ch_ev;     // per block: potrf / head / column path / panel solve / bulk update / boundary share done
   double* dD = nullptr;               // [128][128] scratch accumulator of the boundary diagonal block (look-ahead schedule)
+  cudaGraphExec_t chol_graph_exec = nullptr;   // the captured look-ahead factorisation of the current shape (chol.cu: launch_cholesky)
+  uint64_t chol_graph_key = 0, chol_seen_key = 0;
+  int64_t chol_graph_launches = 0;
+  int chol_graph_syrk_ev = 0;
+  int chol_graph = -1;                // -1: default (on), 0: eager launches, 1: captured graph
   int chol_sched = -1;                // -1: default (look-ahead), 0: in-order schedule of round 1, 1: look-ahead
   std::vector<cudaEvent_t> la_ev;     // look-ahead dependencies
   std::vector<cudaEvent_t> fw_ev;     // per panel: the forward solve of y - m rides along the factorisation on stream2
@@ -129,6 +134,7 @@ cudaError_t launch_scale_inputs(b200bo_handle_s* h, int64_t n0, int64_t n1);
 cudaError_t launch_kmat(b200bo_handle_s* h, double* dK, int64_t ld, int64_t N, int64_t Np, double noise, bool pad_identity);
 // chol.cu
 cudaError_t launch_cholesky(b200bo_handle_s* h);   // in place on h->dL (lower triangle), fills dLinv/dLinvT, upper mirror
+void release_cholesky_graph(b200bo_handle_s* h);
 // syrk_i8.cu
 bool syrk_i8_enabled();
 cudaError_t launch_slice_panel(b200bo_handle_s* h, cudaStream_t st, int row0, int col0, int nkb);
