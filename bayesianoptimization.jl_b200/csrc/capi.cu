@@ -1286,7 +1286,8 @@ static int32_t mll_sweep_impl(b200bo_handle_t h, const double* Theta, int32_t P,
         if (e) { rcs[k] = e; return; }
         wk->synced_version = h->data_version;
       }
-      wk->hp = h->hp; wk->syrk_engine = h->syrk_engine; wk->chol_sched = h->chol_sched; wk->chol_graph = h->chol_graph; wk->fitted = false;
+      wk->hp = h->hp; wk->syrk_engine = h->syrk_engine; wk->chol_sched = h->chol_sched; wk->fitted = false;
+      wk->chol_graph = K > 1 ? 0 : h->chol_graph;      // several factorisations in flight: graph launches of different workers serialise (measured 0.108 vs 0.068 s); eager look-ahead overlaps them
       int64_t lo, hi; shard_bounds(S, K, k, &lo, &hi);
       if (hi > lo) rcs[k] = b200bo_mll_sweep(wk, Theta + lo * P, P, (int32_t)(hi - lo), mask, mll + lo, dmll ? dmll + lo * P : nullptr);
     };

@@ -436,6 +436,29 @@ def main():
                 t0 = time.perf_counter(); m4.mll_sweep(Theta, want_grad=False); t_sv = time.perf_counter() - t0
                 side["cfg4_map_sweep"] = {"workload": "BASELINE configs[3]: N=4096, D=8, 64 (logNoise, length-scale) settings, mll + dmll",
                                           "seconds_with_gradient": t_sw, "seconds_values_only": t_sv, "settings": 64}
+                # the look-ahead schedule + CUDA graph against the in-order schedule of round 1 (same kernels), N=4096
+                sched = {}
+                for name, (sc, gr) in dict(in_order=(0, 0), look_ahead_eager=(1, 0), look_ahead_graph=(1, 1)).items():
+                    m4.set_knob("chol_sched", sc); m4.set_knob("chol_graph", gr)
+                    ts = []
+                    for _ in range(4):
+                        m4.fit(X4, y4); ts.append(m4.timing_ms(_lib.T_CHOL))
+                    sched[name + "_ms"] = min(ts[1:])
+                m4.set_knob("chol_sched", -1); m4.set_knob("chol_graph", -1)
+                side["fit_n4096_d8"]["cholesky_schedules"] = sched
+                # the reference's derivative-free search for ThompsonSamplingSimple (GN_DIRECT_L, maxeval = 2000) and the joint
+                # posterior sample of myrand(model, X::Matrix), both inside the library
+                m4.fit(X4, y4)
+                lb4, ub4 = np.zeros(8), np.ones(8)
+                m4.acquire_direct("TS", (), lb4, ub4, maxeval=2000)
+                t0 = time.perf_counter(); rd = m4.acquire_direct("TS", (), lb4, ub4, maxeval=2000, seed=1); t_d = time.perf_counter() - t0
+                Xj = rng4.random((8, 1024))
+                m4.rand_joint(Xj)
+                t0 = time.perf_counter(); rj = m4.rand_joint(Xj, seed=1); t_j = time.perf_counter() - t0
+                side["direct_l_search"] = {"workload": "N=4096, D=8, ThompsonSamplingSimple, maxeval=2000 (src/acquisition.jl:7-9)", "seconds": t_d,
+                                           "evaluations": rd["evals"], "device_launch_batches": rd["batches"]}
+                side["joint_posterior_sample"] = {"workload": "N=4096, D=8, one joint draw over M=1024 points (src/models/gp.jl:7)", "seconds": t_j,
+                                                  "make_posdef_tries": rj["tries"]}
                 del m4
             except Exception as exc:                                   # a side metric must never take the bench line down
                 side["fit_n4096_d8"] = {"error": str(exc)}
