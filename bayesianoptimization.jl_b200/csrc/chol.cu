@@ -5,16 +5,20 @@
 // Sigma = U'U in column-major storage; that is byte-identical to the row-major lower L = U' kept here.
 //
 //   for each 128-wide panel k:
-//     K2 potrf_diag   : L_kk = chol(A_kk) and L_kk^-1 by ONE 256-thread CTA (latency-first; see the kernel's header).
+//     K2 potrf_diag   : L_kk = chol(A_kk) and L_kk^-1 by ONE 256-thread CTA (latency-first; see the kernel's header);
+//        chol_mirror  : the transposed triangles of that block (L^T mirror, row-major L^-1), off the chain.
 //     K3 trsm_panel   : A_ik <- A_ik L_kk^-T = (L_kk^-1 A_ik^T)^T                (TMA + DMMA tile GEMM, K = 128)
 //     K4 syrk_trailing: A_ij <- A_ij - L_ik L_jk^T  for i >= j > k              (inner updates: TMA + DMMA tile GEMM, K = 128)
 //   The upper triangle of h->dL receives L^T ("mirrored factor") so the backward solve L^T w = v reads the same
 //   k-major rows as the forward one.
 //   Two-level blocking: inner panels of 128 inside outer panels of 512; the update right of a full outer panel is a K = 512
 //   launch on the 5th-generation tensor cores (syrk_i8.cu: int8-slice product on tcgen05.mma, TMEM accumulators) -- the DMMA
-//   kernel serves ragged panels and `b200bo_set_syrk_engine(h, 0)`.  Look-ahead: the next outer panel is factorised on the
-//   handle's stream while the far part of the previous K = 512 update runs on a second stream, on num_sms - 40 persistent CTAs so
-//   that the critical chain always finds free SMs; the forward solve of y - m rides along on that stream too.
+//   kernel serves ragged panels and `b200bo_set_syrk_engine(h, 0)`.
+//   Schedule (round 2, launch_cholesky_lookahead): only K2 and the HEAD of each panel (chol_head_kernel: the 128-row slab of K3 that
+//   the next diagonal block needs + its rank-128 update, one 8-CTA cluster) sit on the critical chain; the rest of K3 / K4, the int8
+//   slicing, the near and far K = 512 updates and the forward solve of y - m run on four side streams underneath the next K2, ordered by
+//   events so every tile gets its updates in one fixed order.  The whole factorisation is captured into a CUDA graph per shape.  The
+//   in-order schedule of round 1 stays selectable (knob "chol_sched" = 0) for A/B timing.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -33,7 +37,9 @@ namespace b200bo {
 //   F(s)   warp 0 factors the 32 x 32 diagonal sub-block in REGISTERS (lane = row, columns exchanged by shuffles: no barrier, no
 //          shared-memory round trip on the 128-column dependency chain), while warps 1-7 finish the far part U2(s-1) of the
 //          previous rank-32 update (look-ahead);
-//   T(s)   warps 1-3: one thread per row below solves X L11^T = A21 by substitution; warp 4 inverts L11 (lane = column);
+//   T(s)   warps 1 .. 3-s: one thread per row below solves X L11^T = A21 by substitution, warp 5 inverts L11 (lane = column) -- both
+//          TRAILING F(s) column by column (colbar[j]: column j of the unit factor and its pivot are published) instead of waiting
+//          for the sub-block; the remaining warps do the look-ahead work U2(s-1) / block row s-1 of L^-1;
 //   U1(s)  all warps: rank-32 update of the NEXT sub-panel's 32 columns on the FP64 tensor pipe (DMMA.8x8x4, K = 32).
 // Then the off-diagonal blocks of L^-1 (W_ij = -W_ii sum_k L_ik W_kj) as 32^3 DMMA products, and a coalesced write-back of the
 // mirrored factor block, L^-1 and L^-T.  Shared-memory image: lower triangle = L, strictly upper triangle = (L^-1)^T, rinv = 1/l_ii.

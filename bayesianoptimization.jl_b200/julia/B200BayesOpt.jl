@@ -114,7 +114,12 @@ function acquire(m::B200GPE, a::AbstractAcquisition, X::AbstractMatrix; seed = 0
     (values = vals, grad = g, best = best[], best_x = bx)
 end
 myrand(m::B200GPE, x::AbstractVector) = acquire(m, ThompsonSamplingSimple(), reshape(x, :, 1); seed = rand(UInt64)).values[1]   # gp.jl:6
-myrand(m::B200GPE, X::AbstractMatrix) = acquire(m, ThompsonSamplingSimple(), X; seed = rand(UInt64)).values                    # gp.jl:7 (independent, quirk 9)
+function myrand(m::B200GPE, X::AbstractMatrix)                                       # gp.jl:7: ONE joint draw, EXT rand(gp, X) (quirk 9)
+    Xs = Matrix{Float64}(X); M = size(Xs, 2); out = Vector{Float64}(undef, M)
+    GC.@preserve Xs out check(ccall((:b200bo_rand_joint, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, UInt64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), m.h, Xs, M, rand(UInt64), 0, out, C_NULL, C_NULL), m.h)
+    out
+end
 
 # acquisitionfunction(a, model) (acquisitionfunctions.jl:4-9,108,111): vector -> scalar, matrix -> vector
 acquisitionfunction(a::AbstractAcquisition, m::B200GPE) =
@@ -139,6 +144,15 @@ function acquire_max(s::B200Search, lb, ub, restarts)                           
     seq = ScaledLHSIterator(lb, ub, restarts)
     a, m, o = s.acquisition, s.model, s.options
     r = acquire(m, a, seq.data; seed = rand(UInt64))
+    if startswith(string(o.method), "GN_DIRECT")     # the reference's derivative-free global search (acquisition.jl:7-9), batched inside the library
+        p = acqparams(a); lbv = Vector{Float64}(lb); ubv = Vector{Float64}(ub); bd = Ref(Best(-Inf, -1)); bxd = fill(NaN, m.dim)
+        GC.@preserve p lbv ubv bxd check(ccall((:b200bo_acquire_direct, LIB), Int32,
+            (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Int32, UInt64, Ptr{Float64}, Ptr{Float64},
+             Ptr{Int32}, Ptr{Int32}, Ref{Best}, Ptr{Float64}),
+            m.h, acqkind(a), isempty(p) ? C_NULL : pointer(p), length(p), lbv, ubv, Int32(optget(o, :maxeval, 2000)), Float64(optget(o, :maxtime, 0.0)),
+            Int32(1), rand(UInt64), C_NULL, C_NULL, C_NULL, C_NULL, bd, bxd), m.h)
+        bd[].index >= 0 && (r.best.index < 0 || bd[].value > r.best.value) && return (bd[].value, bxd)
+    end
     r.best.index < 0 && return (-Inf, lb)
     (a isa ThompsonSamplingSimple || string(o.method)[2] != 'D') && return (r.best.value, r.best_x)     # derivative-free (acquisition.jl:31)
     # what NLopt :LD_LBFGS does per start (acquisition.jl:59), for the best starts of the sweep at once, inside the library, with the
