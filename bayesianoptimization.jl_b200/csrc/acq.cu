@@ -452,6 +452,19 @@ cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& l) {
   // engine 1 (default): error-free int8-slice GEMM against W = L^-1 on tcgen05 (acq_i8.cu); its int32 accumulators hold 7 N 2^14 < 2^31
   const bool i8 = h->acq_engine < 0 ? acq_i8_default() : h->acq_engine == 1;
   if (i8 && h->Np <= 16384) return launch_acquire_i8(h, l);
+  if (l.hXs) {                                                // the DMMA engine has no chunk lanes: one copy in, the outputs out behind the launch
+    AcqLaunch d = l;
+    d.hXs = nullptr;
+    cudaError_t e = l.M > 0 ? cudaMemcpyAsync(const_cast<double*>(l.dXs), l.hXs, sizeof(double) * l.M * h->D, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
+    if (e == cudaSuccess) e = launch_acquire(h, d);
+    if (e == cudaSuccess && l.M > 0) {
+      if (l.hvalues) e = cudaMemcpyAsync(l.hvalues, l.dvalues, sizeof(double) * l.M, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess && l.hmu) e = cudaMemcpyAsync(l.hmu, l.dmu, sizeof(double) * l.M, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess && l.hvar) e = cudaMemcpyAsync(l.hvar, l.dvar, sizeof(double) * l.M, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess && l.hgrad) e = cudaMemcpyAsync(l.hgrad, l.dgrad, sizeof(double) * l.M * h->D, cudaMemcpyDeviceToHost, h->stream);
+    }
+    return e;
+  }
   AcqArgs a;
   a.L = h->dL; a.ld = h->ld; a.Linv = h->dLinv; a.LinvT = h->dLinvT;
   a.Z = h->dZ; a.alpha = h->dalpha; a.inv_ell = h->dinv_ell; a.Xs = l.dXs; a.V = h->dV;

@@ -691,6 +691,8 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
     const int64_t mc = std::min<int64_t>(CH, M - c0);
     const int64_t mcp = (mc + 127) / 128 * 128;
     const int nct = (int)(mcp / A8_BM);
+    if (l.hXs && (e = cudaMemcpyAsync(const_cast<double*>(l.dXs) + c0 * h->D, l.hXs + c0 * h->D, sizeof(double) * mc * h->D, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+      return e;                                               // this chunk's candidates arrive on its own lane, under the other lane's kernels
     if (nblk > 0) {
       KsArgs k;
       k.Z = h->dZ; k.alpha = h->dalpha; k.inv_ell = h->dinv_ell; k.Xs = l.dXs; k.Bs = dBs; k.MuP = dMuP;
@@ -722,9 +724,15 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
     h->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     blk0 += mcp / 32;
+    if (l.hXs) {                                              // the chunk's outputs go home behind its own kernels
+      if (l.hvalues && (e = cudaMemcpyAsync(l.hvalues + c0, l.dvalues + c0, sizeof(double) * mc, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+      if (l.hmu && (e = cudaMemcpyAsync(l.hmu + c0, l.dmu + c0, sizeof(double) * mc, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+      if (l.hvar && (e = cudaMemcpyAsync(l.hvar + c0, l.dvar + c0, sizeof(double) * mc, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    }
     if (want_grad) {
       if (nblk == 0) {
         if ((e = cudaMemsetAsync(l.dgrad + c0 * h->D, 0, sizeof(double) * mc * h->D, st)) != cudaSuccess) return e;
+        if (l.hgrad && (e = cudaMemcpyAsync(l.hgrad + c0 * h->D, l.dgrad + c0 * h->D, sizeof(double) * mc * h->D, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         continue;
       }
       const int total = nct * nit;
@@ -742,6 +750,7 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
       const int nb = (int)((mc + 31) / 32);
       g.nsplit = std::max(1, std::min(16, (nblk + 3) / 4));      // a function of N only: the summation order of a candidate's gradient must not depend on the batch
       if ((e = launch_grad(h, st, g, nb, mc)) != cudaSuccess) return e;
+      if (l.hgrad && (e = cudaMemcpyAsync(l.hgrad + c0 * h->D, l.dgrad + c0 * h->D, sizeof(double) * mc * h->D, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     }
   }
   if (two) {                                                  // join: the handle's stream continues behind lane 1

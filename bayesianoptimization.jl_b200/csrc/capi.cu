@@ -667,8 +667,11 @@ B200BO_API int32_t b200bo_kmat(b200bo_handle_t h, double* K) {
 
 // enqueue the acquisition step; with a communicator attached the local best is packed into this rank's exchange record and, when
 // `exchange` is set (one process per GPU), gathered from all ranks and merged: *dbest then holds the GLOBAL best on every rank
+struct AcqHostIO { const double* Xs = nullptr; double *values = nullptr, *grad = nullptr, *mu = nullptr, *var = nullptr; };
+
 static int32_t acquire_dev_impl(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* dXs, int64_t M, uint64_t seed,
-                                int64_t idx_offset, double* dvalues, double* dgrad, double* dmu, double* dvar, b200bo_best_t* dbest, bool exchange) {
+                                int64_t idx_offset, double* dvalues, double* dgrad, double* dmu, double* dvar, b200bo_best_t* dbest, bool exchange,
+                                const AcqHostIO* io = nullptr) {
   if (!h || M < 0 || (M > 0 && !dXs)) return fail(h, B200BO_ERR_ARG, "bad arguments to acquire");
   int32_t rc = check_acq(h, kind, np, dgrad != nullptr);
   if (rc) return rc;
@@ -679,6 +682,7 @@ static int32_t acquire_dev_impl(b200bo_handle_t h, int32_t kind, const double* p
   AcqLaunch l;
   l.acq_kind = kind; l.p0 = np > 0 ? p[0] : 0.0; l.p1 = np > 1 ? p[1] : 0.0; l.seed = seed; l.idx_offset = idx_offset;
   l.dXs = dXs; l.M = M; l.dvalues = dvalues; l.dgrad = dgrad; l.dmu = dmu; l.dvar = dvar; l.dbest = dbest;
+  if (io) { l.hXs = io->Xs; l.hvalues = io->values; l.hgrad = io->grad; l.hmu = io->mu; l.hvar = io->var; }
   CU(cudaEventRecord(h->ev[4], h->stream));
   if (M == 0 && dbest) {
     const b200bo_best_t none = {-INFINITY, -1};
@@ -736,10 +740,22 @@ static int32_t acquire_host_enqueue(b200bo_handle_t h, int32_t kind, const doubl
   double* dvar = dmu + M;
   double* dgrad = grad ? dvar + M : nullptr;
   b200bo_best_t* dbest = reinterpret_cast<b200bo_best_t*>(dvar + M + (grad ? M * D : 0));
-  if (M > 0) CU(cudaMemcpyAsync(dXs, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, h->stream));
-  rc = acquire_dev_impl(h, kind, p, np, dXs, M, seed, idx_offset, dval, dgrad, mu ? dmu : nullptr, var ? dvar : nullptr, dbest, exchange);
+  // With PINNED host buffers the transfers are issued by the acquisition step itself, chunk by chunk on its stream lanes (H2D of chunk
+  // c+1 and D2H of chunk c-1 run under the kernels of chunk c).  Pageable buffers make cudaMemcpyAsync block the enqueuing thread, which
+  // would stall the chunk pipeline: those are copied in one piece before / after the step.
+  auto pinned = [](const void* ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+  };
+  const bool pipelined = M > 0 && pinned(Xs) && pinned(values) && pinned(grad) && pinned(mu) && pinned(var);
+  AcqHostIO io;
+  io.Xs = Xs; io.values = values; io.grad = grad; io.mu = mu; io.var = var;
+  if (M > 0 && !pipelined) CU(cudaMemcpyAsync(dXs, Xs, sizeof(double) * M * D, cudaMemcpyHostToDevice, h->stream));
+  rc = acquire_dev_impl(h, kind, p, np, dXs, M, seed, idx_offset, dval, dgrad, mu ? dmu : nullptr, var ? dvar : nullptr, dbest, exchange, pipelined ? &io : nullptr);
   if (rc) return rc;
-  if (M > 0) {
+  if (M > 0 && !pipelined) {
     if (values) CU(cudaMemcpyAsync(values, dval, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
     if (mu) CU(cudaMemcpyAsync(mu, dmu, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
     if (var) CU(cudaMemcpyAsync(var, dvar, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));

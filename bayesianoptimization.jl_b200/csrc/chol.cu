@@ -214,8 +214,13 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
       // lanes -- and the trailing warps -- through Mt (one STS + broadcast LDS.128 instead of 31 shuffle pairs per column).
       double a[PSUB];
       const double* row = S + (c0 + lane) * PLD + c0;
+      // only the lower triangle is read: the strictly upper part of the sub-block is where the trailing inverse warp writes W^T
 #pragma unroll
-      for (int j = 0; j < PSUB; j += 2) { const double2 v = *reinterpret_cast<const double2*>(row + j); a[j] = v.x; a[j + 1] = v.y; }
+      for (int j = 0; j < PSUB; j += 2) {
+        double2 v = make_double2(0.0, 0.0);
+        if (j + 1 <= lane) v = *reinterpret_cast<const double2*>(row + j); else if (j == lane) v.x = row[j];
+        a[j] = v.x; a[j + 1] = v.y;
+      }
       double dg = 0.0;                                 // this lane's diagonal element, fully updated once column lane-1 is done
 #pragma unroll
       for (int j = 0; j < PSUB; ++j) if (j == lane) dg = a[j];

@@ -159,6 +159,11 @@ struct AcqLaunch {
   int64_t M = 0;
   double *dvalues = nullptr, *dgrad = nullptr, *dmu = nullptr, *dvar = nullptr;
   b200bo_best_t* dbest = nullptr;
+  // host mirrors (host-pointer entries): when hXs is set the candidates are NOT on the device yet -- the tcgen05 engine copies chunk c in
+  // on its stream lane right before the chunk's kernels and its outputs back right behind them, so the PCIe transfers of one chunk run
+  // under the other lane's kernels (the DMMA engine copies everything up front / at the end)
+  const double* hXs = nullptr;
+  double *hvalues = nullptr, *hgrad = nullptr, *hmu = nullptr, *hvar = nullptr;
 };
 cudaError_t launch_acquire(b200bo_handle_s* h, const AcqLaunch& a);       // dispatches on h->acq_engine
 cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& a);    // acq_i8.cu

@@ -255,14 +255,19 @@ class B200GPE:
         return dict(sample=out, mu=mu, tries=tries.value)
 
     def acquire(self, kind: str, params, X, seed: int = 0, idx_offset: int = 0, want_values=True, want_grad=False,
-                want_mu_var=False):
+                want_mu_var=False, values_out=None, grad_out=None):
         """One fused acquisition step over the columns of X.  Returns a dict with best_value, best_index, best_x and
-        the optional per-candidate arrays."""
+        the optional per-candidate arrays.  values_out (M) / grad_out (D x M, F-order) let the caller supply the output buffers: with
+        PINNED buffers (candidates included) the library overlaps the PCIe transfers with the kernels chunk by chunk."""
         Xs = self._cands(X)
         M = Xs.shape[1]
         p = np.ascontiguousarray(params, float).ravel()
-        vals = np.empty(M) if want_values else None
-        grad = np.empty((self.D, M), order="F") if want_grad else None
+        vals = (values_out if values_out is not None else np.empty(M)) if want_values else None
+        grad = (grad_out if grad_out is not None else np.empty((self.D, M), order="F")) if want_grad else None
+        if vals is not None and vals.shape != (M,):
+            raise ValueError("values_out must have M elements")
+        if grad is not None and (grad.shape != (self.D, M) or not grad.flags.f_contiguous):
+            raise ValueError("grad_out must be D x M in column-major order")
         mu = np.empty(M) if want_mu_var else None
         var = np.empty(M) if want_mu_var else None
         best = _lib.Best()

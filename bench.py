@@ -250,8 +250,9 @@ def run_gpu_workload(ctx, w, steps, warmup, want_fit_side=True, m_local=None):
 
     # ---- end-to-end arm: public host API, pinned host candidates, H2D + D2H inside the timed region -------------
     Xs_np = Xs_host.numpy().T                                                      # D x M view of the pinned buffer (F-order)
+    grad_np = torch.empty((M, D), dtype=torch.float64).pin_memory().numpy().T if w["grad"] else None   # pinned result buffer (D x M, F-order)
     def step_e2e():
-        r = model.acquire(w["acq"], par, Xs_np, seed=50, idx_offset=offset, want_values=False, want_grad=w["grad"])
+        r = model.acquire(w["acq"], par, Xs_np, seed=50, idx_offset=offset, want_values=False, want_grad=w["grad"], grad_out=grad_np)
         return r["best_value"], r["best_index"]                                    # global on every rank (library-side exchange)
     for _ in range(warmup):
         step_e2e()

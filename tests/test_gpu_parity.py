@@ -839,3 +839,48 @@ def test_joint_posterior_sample_statistics_and_make_posdef():
     assert 1 <= rc["tries"] <= 10 and tries_o >= 1
     m0, v0 = o.predict(cl[:, :1])
     assert np.all(np.abs(rc["sample"] - rc["sample"][0]) <= 0.02 * np.sqrt(v0[0]) + 1e-3)       # one draw, shared by the whole cluster
+
+
+def test_pinned_pipelined_transfers_equal_pageable_path(bo):
+    """host-pointer b200bo_acquire: with pinned candidate / output buffers the library moves the data chunk by chunk on its stream lanes
+    (under the kernels of the neighbouring chunk); pageable buffers are copied in one piece.  Same bits either way."""
+    torch = pytest.importorskip("torch")
+    _, o, g, X, y = make_pair(bo, "Mat52Ard", "MeanConst", 5, 600, seed=21)
+    rng = np.random.default_rng(22)
+    M = 40000                                   # three chunks at N = 640 (64 MB of k* slices each)
+    Xs = np.asfortranarray(rng.random((5, M)))
+    tau = float(y.max())
+    r1 = g.acquire("EI", (tau,), Xs, want_grad=True)
+    Xp = torch.from_numpy(np.ascontiguousarray(Xs.T)).pin_memory().numpy().T
+    vp = torch.empty(M, dtype=torch.float64).pin_memory().numpy()
+    gp_ = torch.empty((M, 5), dtype=torch.float64).pin_memory().numpy().T
+    r2 = g.acquire("EI", (tau,), Xp, want_grad=True, values_out=vp, grad_out=gp_)
+    assert r2["values"] is vp and r2["grad"] is gp_
+    assert np.array_equal(r1["values"], r2["values"]) and np.array_equal(r1["grad"], r2["grad"])
+    assert r1["best_index"] == r2["best_index"] and r1["best_value"] == r2["best_value"] and np.array_equal(r1["best_x"], r2["best_x"])
+    g.set_acq_engine(0)                         # the DMMA engine has no chunk lanes: one copy in, one out
+    r3 = g.acquire("EI", (tau,), Xp, want_grad=True, values_out=vp, grad_out=gp_)
+    g.set_acq_engine(1)
+    assert r3["best_index"] == r1["best_index"] and np.abs(r3["values"] - r1["values"]).max() <= 1e-9 * np.abs(r1["values"]).max()
+
+
+def test_cholesky_schedules_agree_and_graph_replay_is_bit_identical(bo):
+    """the look-ahead schedule (fused cluster head) against the in-order schedule of round 1, and its CUDA-graph replay against eager launches"""
+    rng = np.random.default_rng(31)
+    D, N = 4, 1700                              # 14 panels: three full outer panels + a ragged one, tcgen05 far / near updates included
+    X = rng.random((D, N)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N)
+    g = bo.B200GPE(D, mean=bo.MeanConst(0.1), kernel=bo.Mat32Ard(np.full(D, -0.6), 0.2), logNoise=-2.0, capacity=N)
+    out = {}
+    for name, (sched, graph) in dict(inorder=(0, 0), eager=(1, 0), tile_heads=(2, 0), graph=(1, 1)).items():
+        g.set_knob("chol_sched", sched); g.set_knob("chol_graph", graph)
+        fs = []
+        for _ in range(3):                      # graph mode: eager first sight, capture on the second, replay on the third
+            g.fit(X, y); fs.append((g.factor, g.alpha, g.mll))
+        assert all(np.array_equal(fs[0][0], f[0]) and np.array_equal(fs[0][1], f[1]) and fs[0][2] == f[2] for f in fs[1:]), name
+        out[name] = fs[-1]
+    assert np.array_equal(out["eager"][0], out["graph"][0]) and np.array_equal(out["eager"][1], out["graph"][1])
+    for name in ("eager", "tile_heads"):
+        assert np.abs(out[name][0] - out["inorder"][0]).max() <= 1e-12 * np.abs(out["inorder"][0]).max()
+        assert abs(out[name][2] - out["inorder"][2]) <= 1e-10 * abs(out["inorder"][2])
+    o = orc.GPOracle(D, "Mat32Ard", "MeanConst", ll=np.full(D, -0.6), lsigma=0.2, lognoise=-2.0, beta=0.1).fit(X, y)
+    assert relmax(out["graph"][1], o.alpha) <= 1e-9 and abs(out["graph"][2] - o.mll) <= 1e-10 * abs(o.mll)
