@@ -165,8 +165,15 @@ def roofline_i8(w, M, gemm_ms, step_ms, peak_i8, peak_fp64, peaks, traffic):
     fp64_flops = N * N * (2.0 if w["grad"] else 1.0)
     ach = ops * M / (gemm_ms * 1e-3) * 1e-12
     bf16 = peaks.get("bf16_tflops")
+    Np = float((int(N) + 127) // 128 * 128)
+    ch = min(float(int(64 * 2 ** 20 / (7 * Np))), float(M))
+    tr = traffic or {}
     return {"kernel": "acq_i8_gemm_kernel (tcgen05.mma.cta_group::1.kind::i8, 128x64x32, TMEM accumulators)", "bound": "tensor",
-            "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8, "traffic": traffic,
+            "achieved": ach, "peak": peak_i8, "unit": "TFLOP/s", "frac": ach / peak_i8, "traffic": tr.get("acq_i8_gemm_kernel_per_launch"),
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE acq_i8_gemm_kernel launch (one chunk of candidates), ncu capture of this "
+                            "workload in profiles/ncu_traffic.json; algorithmic bytes of such a launch = the int8 slices of the triangular factor "
+                            "inverse (7 N^2 / 2) + the chunk's k* slices (7 CH N)",
+            "algorithmic_bytes_per_launch": 3.5 * Np * Np + 7.0 * ch * Np, "traffic_per_step_all_kernels": tr.get("bytes_per_step"),
             "ops": "int8 multiply-adds of the 28 error-free slice products, 2 ops each (achieved and peak are int8 TOP/s)",
             "peak_source": "self-measured tcgen05.mma kind::i8 rate of this GPU (b200bo_i8_peak_tops: back-to-back 128x256x32 MMAs on "
                            "resident operands, all SMs); MEASURED_PEAKS.json has no int8 figure" +
@@ -289,7 +296,7 @@ def line_for(w, r, steps, world, peaks, traffic_key):
         peaks["peak_i8"] = model.i8_peak_tops(); peaks["peak_fp64"] = model.fp64_peak_tflops()
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(traffic_key, {}).get("bytes_per_step")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(traffic_key)
     except Exception:
         pass
     d2h = 16 + 8 * D + (8 * D * M if w["grad"] else 0)
