@@ -178,6 +178,9 @@ def roofline_i8(w, M, gemm_ms, step_ms, peak_i8, peak_fp64, peaks, traffic):
             "peak_source": "self-measured tcgen05.mma kind::i8 rate of this GPU (b200bo_i8_peak_tops: back-to-back 128x256x32 MMAs on "
                            "resident operands, all SMs); MEASURED_PEAKS.json has no int8 figure" +
                            (f" -- its bf16 burst figure x 2 would be {2 * bf16:.0f}" if bf16 else ""),
+            "frac_of_nominal": ach / 4500.0,
+            "peak_note": "the self-measured peak moves with the power state of the run (3.86-4.58 POP/s seen under sw_power_cap); frac_of_nominal "
+                         "divides by the nominal dense int8 rate of 4500 TOP/s instead",
             "algorithmic_int8_ops_per_candidate": ops, "launch_ms_sum_per_step": gemm_ms,
             "launch_timing": "CUDA-event pairs around every acq_i8_gemm_kernel launch of one step on the launching stream (one chunk lane)",
             "step_view": {"achieved": ops * M / (step_ms * 1e-3) * 1e-12, "frac": ops * M / (step_ms * 1e-3) * 1e-12 / peak_i8,
