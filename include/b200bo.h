@@ -228,8 +228,9 @@ B200BO_API int32_t b200bo_i8_peak_tops(b200bo_handle_t h, double* tops);
 /* developer / bench knobs: "acq_lanes" (1 or 2 chunk lanes of the tcgen05 acquisition path), "acq_chunk_mb" (k* slice bytes per chunk,
    0 = default), "acq_gemm_timing" (1: CUDA-event pairs around every slice-product launch, one lane; read B200BO_T_ACQ_GEMM),
    "sweep_workers" (settings of a MAP sweep in flight at once on one GPU, default 6; 0 = one after the other on the model's own buffers),
-   "chol_sched" (schedule of the blocked Cholesky: 1 = look-ahead, only potrf + the head of each panel on the critical chain (default);
-   0 = the in-order schedule of round 1; same kernels, for A/B timing) */
+   "chol_sched" (schedule of the blocked Cholesky: 1 = look-ahead, only potrf + the fused cluster head of each panel on the critical chain
+   (default); 2 = look-ahead with the tile-GEMM kernels as heads; 0 = the in-order schedule of round 1; for A/B timing),
+   "chol_graph" (1 = replay the look-ahead factorisation as one CUDA graph per shape (default), 0 = eager launches) */
 B200BO_API int32_t b200bo_set_knob(b200bo_handle_t h, const char* name, int64_t value);
 B200BO_API int32_t b200bo_version(void);
 
