@@ -204,20 +204,60 @@ cudaError_t launch_lbfgs(b200bo_handle_s* h, const AcqLaunch& base, double* dXe,
   int* drun = h->dinfo + 3;
   const auto t0 = std::chrono::steady_clock::now();
   const int cap = o.maxeval > 0 ? o.maxeval : 100000;
-  int rounds = 0;
-  for (; rounds < cap; ++rounds) {
+  auto enqueue_round = [&]() -> cudaError_t {
     AcqLaunch l = base;
     l.dXs = dXe; l.dvalues = val; l.dgrad = grad; l.dmu = nullptr; l.dvar = nullptr; l.dbest = nullptr;
-    if ((e = launch_acquire(h, l)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(drun, 0, sizeof(int), h->stream)) != cudaSuccess) return e;
+    cudaError_t er = launch_acquire(h, l);
+    if (er != cudaSuccess) return er;
+    if ((er = cudaMemsetAsync(drun, 0, sizeof(int), h->stream)) != cudaSuccess) return er;
     lbfgs_step_kernel<<<(int)((M + 127) / 128), 128, 0, h->stream>>>(state, dXe, val, grad, d_lbub, (int)D, M, o, drun);
     h->launches++;
-    int running = 0;
-    if ((e = cudaMemcpyAsync(&running, drun, sizeof(int), cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return e;
-    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return e;
-    if (running == 0) { ++rounds; break; }
-    if (maxtime_s > 0.0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= maxtime_s) { ++rounds; break; }   // NLopt maxtime
+    return cudaGetLastError();
+  };
+  auto still_running = [&](int* running) -> cudaError_t {
+    cudaError_t er = cudaMemcpyAsync(running, drun, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    return er != cudaSuccess ? er : cudaStreamSynchronize(h->stream);
+  };
+  auto out_of_time = [&]() { return maxtime_s > 0.0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= maxtime_s; };   // NLopt maxtime
+  // A round is ~7 small launches and the host's look at the running count costs a stream synchronisation: at the sizes of a BO loop
+  // (16 starts, N in the hundreds) that latency IS the iteration.  After the first round (eager: it makes every lazy allocation) a block
+  // of RB rounds is captured into a CUDA graph and replayed; the host looks at the running count once per block.  Runs that have stopped
+  // are no-ops in lbfgs_step (their status is set, per-run maxeval is enforced there), so the extra rounds of a block change nothing.
+  constexpr int RB = 8;
+  static const bool use_graph = !(getenv("B200BO_LBFGS_GRAPH") && atoi(getenv("B200BO_LBFGS_GRAPH")) == 0);
+  int rounds = 0, running = 1;
+  if ((e = enqueue_round()) != cudaSuccess) return e;
+  if ((e = still_running(&running)) != cudaSuccess) return e;
+  ++rounds;
+  cudaGraphExec_t exec = nullptr;
+  int64_t block_launches = 0;
+  cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+  if (running != 0 && rounds < cap && !out_of_time() && use_graph && cudaStreamIsCapturing(h->stream, &cst) == cudaSuccess &&
+      cst == cudaStreamCaptureStatusNone && cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+    const int64_t l0 = h->launches;
+    for (int r = 0; r < RB && e == cudaSuccess; ++r) e = enqueue_round();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+    block_launches = h->launches - l0;
+    h->launches = l0;
+    if (e == cudaSuccess && e2 == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    e = cudaSuccess;
   }
+  while (running != 0 && rounds < cap && !out_of_time()) {
+    if (exec) {
+      if ((e = cudaGraphLaunch(exec, h->stream)) != cudaSuccess) break;
+      h->launches += block_launches;
+      rounds += RB;
+    } else {
+      if ((e = enqueue_round()) != cudaSuccess) break;
+      ++rounds;
+    }
+    if ((e = still_running(&running)) != cudaSuccess) break;
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (e != cudaSuccess) return e;
   lbfgs_finish_kernel<<<(int)((M + 127) / 128), 128, 0, h->stream>>>(state, dXe, val, evals, (int)D, M);
   h->launches++;
   if (base.dvalues) cudaMemcpyAsync(base.dvalues, val, sizeof(double) * M, cudaMemcpyDeviceToDevice, h->stream);
