@@ -800,7 +800,8 @@ static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head
   cudaEventRecord(h->fw_ev[nblk], sa);
   if (trace) cudaEventRecord(h->syrk_ev[2 * npan + 1], sa);
   for (cudaStream_t st : {sb, sc, sd, se}) cudaStreamWaitEvent(st, h->fw_ev[nblk], 0);
-  launch_residual(h, se);                                  // the forward solve z = L^-1 (y - m) rides along (solve.cu: launch_fwd_step)
+  // (the forward solve z = L^-1 (y - m) rides along on the rider stream -- solve.cu: launch_fwd_step; its right-hand side y - m was
+  //  written by launch_cholesky BEFORE this schedule, outside any captured graph: it depends on beta and N, which a graph would freeze)
   for (int P = 0; P < npan; ++P) {
     const int p0 = P * OB, p1 = (p0 + OB < nblk) ? p0 + OB : nblk, p2 = (p1 + OB < nblk) ? p1 + OB : nblk;
     const bool use_D = fused_head && p1 < nblk && p1 - p0 > 1;
@@ -921,6 +922,9 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
   static const int graph_env = getenv("B200BO_CHOL_GRAPH") ? atoi(getenv("B200BO_CHOL_GRAPH")) : 1;
   const int sc = h->chol_sched >= 0 ? h->chol_sched : sched;       // 1: look-ahead with the fused cluster head, 2: look-ahead with tile-GEMM heads
   if (!sc) return launch_cholesky_inorder(h);
+  // dw = y - m: the ONE launch of the factorisation whose arguments change with the data (N) and the parameters (beta) while the panel
+  // count and the buffers -- the graph's key -- stay the same.  It runs eagerly, ahead of the (possibly replayed) schedule.
+  { const cudaError_t er = launch_residual(h, h->stream); if (er != cudaSuccess) return er; }
   const bool want_graph = (h->chol_graph >= 0 ? h->chol_graph : graph_env) != 0;
   if (!want_graph) return launch_cholesky_lookahead(h, sc == 1, false);
   const bool i8 = h->syrk_engine < 0 ? syrk_i8_enabled() : h->syrk_engine >= 1;

@@ -884,3 +884,29 @@ def test_cholesky_schedules_agree_and_graph_replay_is_bit_identical(bo):
         assert abs(out[name][2] - out["inorder"][2]) <= 1e-10 * abs(out["inorder"][2])
     o = orc.GPOracle(D, "Mat32Ard", "MeanConst", ll=np.full(D, -0.6), lsigma=0.2, lognoise=-2.0, beta=0.1).fit(X, y)
     assert relmax(out["graph"][1], o.alpha) <= 1e-9 and abs(out["graph"][2] - o.mll) <= 1e-10 * abs(o.mll)
+
+
+def test_replayed_factorisation_graph_follows_data_and_mean_changes(bo):
+    """the CUDA graph of the factorisation is keyed on the panel count and the buffers; N (inside the same 128-padding) and the mean
+    parameter change underneath it -- the right-hand side y - m must follow (it is computed outside the graph)"""
+    rng = np.random.default_rng(41)
+    D, N = 3, 1000
+    X = rng.random((D, N + 10)); y = np.cos(2 * X.sum(0)) + 0.05 * rng.standard_normal(N + 10) + 1.5
+    ll = np.full(D, -0.8)
+    g = bo.B200GPE(D, mean=bo.MeanConst(0.0), kernel=bo.SEArd(ll, 0.0), logNoise=-2.0, capacity=1024)
+    for _ in range(3):
+        g.fit(X[:, :N], y[:N])                   # eager, capture, replay
+    for beta, n in ((0.0, N), (1.5, N), (1.5, N + 7), (-0.4, N + 10), (0.9, N - 3)):
+        th = g.get_params(); th[1] = beta
+        g.set_params(th)
+        g.fit(X[:, :n], y[:n])
+        o = orc.GPOracle(D, "SEArd", "MeanConst", ll=ll, lsigma=0.0, lognoise=-2.0, beta=beta).fit(X[:, :n], y[:n])
+        assert relmax(g.alpha, o.alpha) <= 1e-9, (beta, n)
+        assert abs(g.mll - o.mll) <= 1e-10 * abs(o.mll), (beta, n)
+    # the MAP objective on a worker model (one setting in flight: the worker replays its own graph) with the mean parameter swept
+    Theta = np.stack([np.concatenate([[-2.0, b], ll, [0.0]]) for b in (-1.0, 0.0, 0.7, 1.5, 2.2)], axis=1)
+    for _ in range(3):
+        mll = np.array([g.mll_sweep(Theta[:, [s]], want_grad=False)[0][0] for s in range(Theta.shape[1])])
+    n = N - 3
+    want = [orc.GPOracle(D, "SEArd", "MeanConst", ll=ll, lsigma=0.0, lognoise=-2.0, beta=b).fit(X[:, :n], y[:n]).mll for b in Theta[1]]
+    assert np.all(np.abs(mll - np.array(want)) <= 1e-10 * np.abs(want))
