@@ -14,6 +14,10 @@
 #                 functor parameters set DIRECTLY on the structs (tau, beta_t, sqrt(alpha), gamma_hat), not through setparams!
 #   selection     first strict maximum over the columns                              (src/acquisition.jl:62-65)
 #   MAP target    update_target_and_dtarget!(gp; noise, domean, kern) -> mll, dmll at theta and theta2 (closure of src/models/gp.jl:59-64)
+#   joint sample  predict_f(gp, Xs[:, 1:m]; full_cov = true) -> the m x m posterior covariance behind myrand(model, X::Matrix) = rand(gp, X)
+#                 (src/models/gp.jl:7; the draw itself uses Julia's global RNG, so the covariance is what can be pinned)
+#   DIRECT-L      acquire_max(MaxMean(), gp, lb, ub, (method = :GN_DIRECT_L, restarts = 1, maxeval = 2000)) over the box of the candidates
+#                 (src/acquisition.jl:7-9,49-68): NLopt's own optimum, which b200bo_acquire_direct must reach
 using BayesianOptimization, GaussianProcesses, JSON, Pkg
 const BO = BayesianOptimization
 const GP = GaussianProcesses
@@ -73,6 +77,15 @@ for case in inp["cases"]
         out[k * "_values"] = vals
         out[k * "_best"] = first_strict_argmax(vals)
     end
+    m = min(size(Xs, 2), 24)
+    mu_j, cov_j = GP.predict_f(gp, Xs[:, 1:m]; full_cov = true)
+    out["joint_m"] = m
+    out["joint_mu"] = mu_j
+    out["joint_cov"] = [cov_j[i, :] for i in 1:m]                 # row list
+    lb = vec(minimum(Xs, dims = 2)); ub = vec(maximum(Xs, dims = 2))
+    fdir, xdir = BO.acquire_max(MaxMean(), gp, lb, ub, (method = :GN_DIRECT_L, restarts = 1, maxeval = 2000))
+    out["direct_lb"], out["direct_ub"] = lb, ub
+    out["direct_maxmean_f"], out["direct_maxmean_x"] = fdir, xdir
     for (key, th) in (("", theta), ("2", Float64.(case["theta2"])))
         GP.set_params!(gp, th; noise = true, domean = true, kern = true)
         GP.update_target_and_dtarget!(gp; noise = true, domean = true, kern = true)

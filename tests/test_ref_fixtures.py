@@ -27,7 +27,7 @@ def close(a, b, rtol, atol=ATOL):
 def test_generator_and_inputs_are_in_place():
     """always on: the Julia generator exists, names every quantity this loader reads, and its input file covers every golden case"""
     src = open(os.path.join(ROOT, "oracle", "make_ref_fixtures.jl")).read()
-    for key in ("alpha", "mll", "Udiag", "mu", "var", "_values", "_best", "dmll", "versions"):
+    for key in ("alpha", "mll", "Udiag", "mu", "var", "_values", "_best", "dmll", "versions", "joint_cov", "joint_mu", "direct_maxmean_f", "direct_lb"):
         assert key in src
     inp = json.load(open(os.path.join(GOLD, "ref_inputs.json")))
     names = {c["name"] for c in inp["cases"]}
@@ -61,6 +61,12 @@ def test_cpu_restatement_against_the_reference(path):
     for key, t in (("", th), ("2", z["theta2"])):
         f, g = o.mll_dmll(t)
         assert abs(f - ref["mll" + key]) <= 1e-9 * abs(ref["mll" + key]) and close(g, ref["dmll" + key], 1e-6, 1e-9)
+    if "joint_cov" in ref:                       # the covariance behind the joint draw of myrand(model, X::Matrix) (gp.jl:7)
+        m = int(ref["joint_m"])
+        o.set_params(th); o.fit(z["X"], z["y"])
+        mj, Sj = o.posterior_cov(z["Xs"][:, :m])
+        Sr = np.array(ref["joint_cov"], float)
+        assert close(mj, ref["joint_mu"], RTOL_POST) and np.abs(Sj - Sr).max() <= 1e-6 * np.abs(np.diag(Sr)).max()
 
 
 @pytest.mark.gpu
@@ -83,3 +89,15 @@ def test_cuda_path_against_the_reference(path):
     mll, dmll = g.mll_sweep(np.stack([th, z["theta2"]], axis=1))
     for j, key in enumerate(("", "2")):
         assert abs(mll[j] - ref["mll" + key]) <= 1e-9 * abs(ref["mll" + key]) and close(dmll[:, j], ref["dmll" + key], 1e-6, 1e-9)
+    if "joint_cov" in ref:                       # b200bo_rand_joint == mu_ref + chol(Sigma_ref) eps for the library's own Philox normals
+        from scipy.linalg import cholesky
+        m = int(ref["joint_m"])
+        Sr = np.array(ref["joint_cov"], float)
+        r = g.rand_joint(z["Xs"][:, :m], seed=5)
+        if r["tries"] == 0:
+            want = np.array(ref["joint_mu"], float) + cholesky(Sr, lower=True) @ orc.philox_normal(5, np.arange(m))
+            assert np.abs(r["sample"] - want).max() <= 1e-6 * np.sqrt(np.abs(np.diag(Sr)).max())
+    if "direct_maxmean_f" in ref:                # NLopt's GN_DIRECT_L optimum of the posterior mean over the same box, same budget
+        rd = g.acquire_direct("MaxMean", (), np.array(ref["direct_lb"], float), np.array(ref["direct_ub"], float), maxeval=2000)
+        span = float(np.max(ref["mu"]) - np.min(ref["mu"]))
+        assert rd["best_value"] >= ref["direct_maxmean_f"] - 5e-3 * span
