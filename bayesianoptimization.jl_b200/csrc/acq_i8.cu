@@ -748,7 +748,9 @@ cudaError_t launch_acquire_i8(b200bo_handle_s* h, const AcqLaunch& l) {
       g.amu = dAmu; g.as2 = dAs2; g.part = dWg + 2 * (size_t)CH * (size_t)Np; g.grad = l.dgrad;
       g.M = M; g.c0 = c0; g.CH = CH; g.N = (int)h->N; g.D = h->D; g.nblk = nblk;
       const int nb = (int)((mc + 31) / 32);
-      g.nsplit = std::max(1, std::min(16, (nblk + 3) / 4));      // a function of N only: the summation order of a candidate's gradient must not depend on the batch
+      // a function of N only (the summation order of a candidate's gradient must not depend on the batch); two blocks of observations per
+      // split up to 8 splits: the lock-step L-BFGS rounds of a BO loop are 16 candidates against N in the hundreds, where this kernel was 2 CTAs
+      g.nsplit = std::max(1, std::min(8, (nblk + 1) / 2));
       if ((e = launch_grad(h, st, g, nb, mc)) != cudaSuccess) return e;
       if (l.hgrad && (e = cudaMemcpyAsync(l.hgrad + c0 * h->D, l.dgrad + c0 * h->D, sizeof(double) * mc * h->D, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     }
