@@ -140,7 +140,9 @@ B200BO_API int32_t b200bo_rand_joint(b200bo_handle_t h, const double* Xs, int64_
  *    (acquisitionfunctions.jl:4-9, acquisition.jl:54-68).  One fused launch over the M candidate columns:
  *    k(x*,X), both triangular solves, mu, sigma^2, a(mu, sigma^2), optional gradient D x M, arg-max with
  *    first-strict-maximum (lowest index) tie-break, NaN never wins.  idx_offset = global index of column 0 (keys
- *    the TS Philox stream and is added to best->index) so shards of one candidate matrix agree with the whole. */
+ *    the TS Philox stream and is added to best->index) so shards of one candidate matrix agree with the whole.
+ *    Host buffers may be pageable or pinned (cudaHostAlloc / cudaHostRegister); with pinned Xs and outputs the library moves the data chunk
+ *    by chunk on its stream lanes, under the kernels of the neighbouring chunk (same results, the PCIe time disappears from the call). */
 B200BO_API int32_t b200bo_acquire(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params,
                        const double* Xs, int64_t M, uint64_t seed, int64_t idx_offset,
                        double* values /*M or NULL*/, double* grad /*D x M or NULL*/,
