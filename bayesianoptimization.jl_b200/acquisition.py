@@ -103,7 +103,7 @@ def acquire_max(opt, lowerbounds=None, upperbounds=None, restarts=None, options=
         rd = model.acquire_direct(a.kind, a.params(), lb, ub, maxeval=int(opt.maxeval) if opt.maxeval else 2000, maxtime=float(opt.maxtime),
                                   width=int(opt.direct_width), seed=opt.seed + (1 << 32))
         if rd["best_index"] >= 0 and (r["best_index"] < 0 or rd["best_value"] > r["best_value"]):
-            r = dict(r, best_value=rd["best_value"], best_x=rd["best_x"], best_index=rd["best_index"])
+            r = dict(r, best_value=rd["best_value"], best_x=rd["best_x"], best_index=rd["best_index"], best_from="direct")
     opt.seed += 1
     opt.last = r
     if r["best_index"] < 0:

@@ -1077,7 +1077,7 @@ B200BO_API int32_t b200bo_acquire_direct(b200bo_handle_t h, int32_t kind, const 
   }
   if (evals_out) *evals_out = (int32_t)s.evals;
   if (batches_out) *batches_out = batches;
-  if (best) { best->value = s.best_f; best->index = s.best_f > -INFINITY ? 0 : -1; }
+  if (best) { best->value = s.best_f; best->index = s.best_eval; }
   if (best_x && s.best_f > -INFINITY)
     for (int d = 0; d < D; ++d) best_x[d] = lb[d] + s.best_c[d] * (ub[d] - lb[d]);
   return B200BO_OK;

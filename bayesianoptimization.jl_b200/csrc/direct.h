@@ -33,6 +33,7 @@ struct DirectL {
   int width = 1;
   int64_t evals = 0;
   double best_f = -INFINITY;
+  int64_t best_eval = -1;                        // evaluation number (0-based) that produced the incumbent
   std::vector<double> best_c;                    // unit-cube coordinates of the incumbent
   bool finished = false;
   // rectangles, structure of arrays
@@ -49,7 +50,7 @@ struct DirectL {
 
   void init(int D_, int64_t maxeval_, int width_) {
     D = D_; maxeval = maxeval_; width = width_ < 1 ? 1 : width_;
-    evals = 0; best_f = -INFINITY; best_c.assign(D, 0.5); finished = (D < 1 || D > 64);
+    evals = 0; best_f = -INFINITY; best_eval = -1; best_c.assign(D, 0.5); finished = (D < 1 || D > 64);
     c.clear(); lev.clear(); f.clear(); smin.clear(); pend.clear(); pend_points = 0; started = false;
     third[0] = 1.0;
     for (int k = 1; k < MAX_LEVEL + 2; ++k) third[k] = third[k - 1] / 3.0;      // the same sequence of divisions in the restatement
@@ -122,8 +123,8 @@ struct DirectL {
   }
 
   void note(double v, const double* x) {
+    if (v > best_f) { best_f = v; best_eval = evals; best_c.assign(x, x + D); }     // first strict maximum (acquire_max's rule, src/acquisition.jl:62)
     ++evals;
-    if (v > best_f) { best_f = v; best_c.assign(x, x + D); }     // first strict maximum (acquire_max's rule, src/acquisition.jl:62)
   }
   void push(const double* x, const int8_t* lv, double v) {
     c.insert(c.end(), x, x + D);

@@ -197,8 +197,8 @@ B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t acq_kind, co
  *   new centres -- all potentially optimal rectangles, all their longest sides -- scored by ONE fused acquisition launch.  maxeval = total
  *   evaluations (exactly, as NLopt counts them), maxtime in seconds (<= 0 unlimited), width = rectangles divided per hull size class
  *   (1 = DIRECT-L).  Evaluation e uses the Thompson stream (seed, global index e).  Xtrace (D x maxeval) / ftrace (maxeval) optionally
- *   receive every evaluated point and value in evaluation order; evals = evaluations used, batches = device launches.  best->index = 0
- *   when a point was found, -1 if nothing beat -Inf. */
+ *   receive every evaluated point and value in evaluation order; evals = evaluations used, batches = device launches.  best->index = the
+ *   evaluation (0-based, = column of Xtrace) that produced the best value, -1 if nothing beat -Inf. */
 B200BO_API int32_t b200bo_acquire_direct(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params, const double* lb,
                                          const double* ub, int32_t maxeval, double maxtime, int32_t width, uint64_t seed,
                                          double* Xtrace /*D x maxeval or NULL*/, double* ftrace /*maxeval or NULL*/, int32_t* evals /*or NULL*/,

@@ -125,7 +125,9 @@ def test_library_direct_equals_restatement_on_library_values(kind):
     params = (float(y.max()),) if kind == "EI" else ()
     me, seed = 500, 11
     r = g.acquire_direct(kind, params, lb, ub, maxeval=me, seed=seed, want_trace=True)
-    assert r["evals"] == me and r["best_index"] == 0
+    assert r["evals"] == me and 0 <= r["best_index"] < me
+    assert r["values"][r["best_index"]] == r["best_value"] and np.array_equal(r["X"][:, r["best_index"]], r["best_x"])
+    assert r["best_index"] == int(np.argmax(np.where(np.isnan(r["values"]), -np.inf, r["values"])))      # first strict maximum
     state = dict(n=0)
 
     def f(P):      # the library's own values at the same global evaluation indices
