@@ -185,3 +185,35 @@ def test_acquire_max_with_the_reference_thompson_defaults():
 def orc_branin(x):
     from oracle import gp_oracle as orc
     return float(orc.branin(x[0], x[1]))
+
+
+def test_hull_selection_matches_the_definition_of_potentially_optimal():
+    """Jones' definition (epsilon = 0, maximisation): size class j is potentially optimal iff some rate K >= 0 has
+    f_j + K d_j >= f_i + K d_i for every class i.  The hull routine of the restatement (and, through the point-for-point tests above, of
+    csrc/direct.h) must select exactly the classes the definition admits among those at least as large as the incumbent's."""
+    rng = np.random.default_rng(3)
+    for trial in range(300):
+        n = int(rng.integers(1, 9))
+        levels = sorted(rng.choice(np.arange(0, 12), size=n, replace=False))          # distinct size classes, s ascending = size descending
+        d = np.array([3.0 ** -int(s) for s in levels])
+        f = np.round(rng.normal(size=n), 1 if trial % 2 else 3)                        # coarse values: ties and collinear triples occur
+        star = int(np.argmax(f))                                                       # first maximum = largest size among ties
+        pts = [(d[i], f[i], levels[i]) for i in range(star, -1, -1)]                   # from the incumbent's class towards larger sizes
+        got = set(dor._upper_right_hull(pts))
+        want = set()
+        for j in range(star + 1):
+            lo, hi = 0.0, np.inf                                                       # feasible K: f_j - f_i >= K (d_i - d_j) for all i
+            ok = True
+            for i in range(n):
+                if i == j:
+                    continue
+                dd, df = d[i] - d[j], f[j] - f[i]
+                if dd > 0:
+                    hi = min(hi, df / dd)
+                elif dd < 0:
+                    lo = max(lo, df / dd)
+                elif df < 0:
+                    ok = False
+            if ok and lo <= hi and hi >= 0:
+                want.add(levels[j])
+        assert got == want, (levels, f.tolist(), got, want)
