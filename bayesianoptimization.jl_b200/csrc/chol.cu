@@ -384,9 +384,11 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(double* __res
 // Head of panel k (look-ahead schedule): everything the NEXT diagonal block needs from panel k, as ONE launch of an 8-CTA cluster.
 //   phase 1   X = L_{k+1,k} = A_{k+1,k} W_k^T   (W_k = L_kk^-1, lower triangular: only l <= j contributes)
 //   phase 2   A_{k+1,k+1} -= X X^T              (lower tiles; + the scratch accumulator D of an outer-panel boundary)
-// CTA r owns the 8-row tiles r and 15 - r of the block row (balanced triangle); W_k and the CTA's rows of A arrive by 1-D TMA bulk
-// copies; every CTA keeps its 16 rows of X in shared memory and phase 2 reads the other CTAs' rows through distributed shared
-// memory (gathered into local shared memory in one sweep).  All products on the FP64 tensor pipe (DMMA.8x8x4), four independent accumulator chains per warp.
+// CTA r owns the 8-row tiles r and 15 - r of the block row (balanced triangle); W_k^T (from L^-T) and the CTA's rows of A arrive by 1-D
+// TMA bulk copies; every CTA writes its 16 rows of X to the factor, the cluster barrier orders those writes, and phase 2 gathers the rows
+// it multiplies with back from L2 into shared memory in one sweep (reading them through distributed shared memory measured ~15 B/clk).
+// The cluster is what makes the two phases ONE launch: its barrier is the grid-wide synchronisation between them.  All products on the
+// FP64 tensor pipe (DMMA.8x8x4), four independent accumulator chains per warp.
 // The tile GEMM kernels need ~12 us per launch for this (one 128 x 64 x 128 tile per CTA is 8.4 us of DMMA on one SM): twice that sat
 // between every two diagonal blocks.
 // ------------------------------------------------------------------------------------------------------------
