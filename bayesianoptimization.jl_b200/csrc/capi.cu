@@ -1410,7 +1410,7 @@ B200BO_API int32_t b200bo_set_knob(b200bo_handle_t h, const char* name, int64_t 
   else if (k == "acq_gemm_timing") h->acq_time_gemm = value != 0;
   else if (k == "sweep_workers") { if (value < 0 || value > 32) return fail(h, B200BO_ERR_ARG, "sweep_workers must be in 0..32"); h->sweep_workers = (int)value; }
   else if (k == "chol_sched") { if (value < -1 || value > 2) return fail(h, B200BO_ERR_ARG, "chol_sched must be -1 (default), 0 (in-order), 1 (look-ahead, fused head) or 2 (look-ahead, tile-GEMM heads)"); h->chol_sched = (int)value; for (auto* w : h->workers) w->chol_sched = (int)value; }
-  else if (k == "chol_graph") { if (value < -1 || value > 1) return fail(h, B200BO_ERR_ARG, "chol_graph must be -1 (default), 0 (eager launches) or 1 (captured CUDA graph)"); h->chol_graph = (int)value; for (auto* w : h->workers) w->chol_graph = (int)value; }
+  else if (k == "chol_graph") { if (value < -1 || value > 1000) return fail(h, B200BO_ERR_ARG, "chol_graph must be -1 / 1 (default: capture a shape at its 6th consecutive factorisation), 0 (eager launches) or k >= 2 (capture at the k-th)"); h->chol_graph = (int)value; for (auto* w : h->workers) w->chol_graph = (int)value; }
   else return fail(h, B200BO_ERR_ARG, "unknown knob: " + k);
   for (auto* r : h->replicas) b200bo_set_knob(r, name, value);
   return B200BO_OK;

@@ -910,7 +910,7 @@ static cudaError_t launch_cholesky_lookahead(b200bo_handle_s* h, bool fused_head
 
 // The look-ahead schedule is ~25 launches and ~40 event operations per 128-column panel over five streams: enqueued one by one the HOST
 // becomes the critical path (the chain itself is ~50 us per panel).  The whole factorisation is therefore captured ONCE per shape into
-// a CUDA graph (the second time a shape is seen: the first run has made every lazy allocation) and replayed with one launch.
+// a CUDA graph and replayed with one launch.
 // The graph bakes in pointers and panel counts: it is keyed on them and rebuilt when they change.
 static void drop_chol_graph(b200bo_handle_s* h) {
   if (h->chol_graph_exec) cudaGraphExecDestroy(h->chol_graph_exec);
@@ -939,11 +939,17 @@ cudaError_t launch_cholesky(b200bo_handle_s* h) {
     h->syrk_ev_used = h->chol_graph_syrk_ev;
     return cudaGraphLaunch(h->chol_graph_exec, h->stream);
   }
+  // Capturing and instantiating the ~25 nblk nodes is not free (measured: 3.3 ms at N = 2048, 8 ms at N = 4096, 17 ms at N = 8192) against
+  // 0.12-0.35 ms saved per replay: a shape is captured at its `thr`-th consecutive factorisation (default 6; knob "chol_graph" = k >= 2
+  // sets it), so that a one-off refit never pays and the evaluations of a MAP fit do from the sixth on.  The first sight is always eager
+  // (it makes every lazy allocation).
+  const int knob = h->chol_graph >= 0 ? h->chol_graph : graph_env;
+  const int thr = knob <= 1 ? 6 : knob;
+  h->chol_seen_count = h->chol_seen_key == key ? h->chol_seen_count + 1 : 1;
+  h->chol_seen_key = key;
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  if (h->chol_seen_key != key || cudaStreamIsCapturing(h->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
-    h->chol_seen_key = key;                                          // first sight of this shape (or a caller stream that is itself capturing): eager
-    return launch_cholesky_lookahead(h, sc == 1, false);
-  }
+  if (h->chol_seen_count < thr || cudaStreamIsCapturing(h->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone)
+    return launch_cholesky_lookahead(h, sc == 1, false);             // (also: a caller stream that is itself capturing)
   drop_chol_graph(h);
   const int64_t launches0 = h->launches;
   cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed);

@@ -87,9 +87,10 @@ struct b200bo_handle_s {
   double* dD = nullptr;               // [128][128] scratch accumulator of the boundary diagonal block (look-ahead schedule)
   cudaGraphExec_t chol_graph_exec = nullptr;   // the captured look-ahead factorisation of the current shape (chol.cu: launch_cholesky)
   uint64_t chol_graph_key = 0, chol_seen_key = 0;
+  int chol_seen_count = 0;            // consecutive factorisations of the shape chol_seen_key
   int64_t chol_graph_launches = 0;
   int chol_graph_syrk_ev = 0;
-  int chol_graph = -1;                // -1: default (on), 0: eager launches, 1: captured graph
+  int chol_graph = -1;                // -1 / 1: default (capture a shape at its 6th consecutive factorisation), 0: eager launches, k >= 2: capture at the k-th
   int chol_sched = -1;                // -1: default (look-ahead), 0: in-order schedule of round 1, 1: look-ahead
   std::vector<cudaEvent_t> la_ev;     // look-ahead dependencies
   std::vector<cudaEvent_t> fw_ev;     // per panel: the forward solve of y - m rides along the factorisation on stream2

@@ -232,7 +232,8 @@ B200BO_API int32_t b200bo_i8_peak_tops(b200bo_handle_t h, double* tops);
    "sweep_workers" (settings of a MAP sweep in flight at once on one GPU, default 6; 0 = one after the other on the model's own buffers),
    "chol_sched" (schedule of the blocked Cholesky: 1 = look-ahead, only potrf + the fused cluster head of each panel on the critical chain
    (default); 2 = look-ahead with the tile-GEMM kernels as heads; 0 = the in-order schedule of round 1; for A/B timing),
-   "chol_graph" (1 = replay the look-ahead factorisation as one CUDA graph per shape (default), 0 = eager launches) */
+   "chol_graph" (the look-ahead factorisation replays as one CUDA graph per shape, captured at the shape's 6th consecutive factorisation
+   (default; capture + instantiation cost 3-17 ms once, a replay saves 0.12-0.35 ms); k >= 2 = capture at the k-th, 0 = always eager) */
 B200BO_API int32_t b200bo_set_knob(b200bo_handle_t h, const char* name, int64_t value);
 B200BO_API int32_t b200bo_version(void);
 

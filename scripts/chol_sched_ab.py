@@ -11,7 +11,7 @@ for N, D in cfgs:
     g = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.0), kernel=b200bo.SEArd(np.full(D, np.log(np.sqrt(D) * 0.25)), 0.0), logNoise=-2.0, capacity=N)
     res = {}
     for sched in (0, 2, 1):
-        g.set_knob("chol_sched", sched)
+        g.set_knob("chol_sched", sched); g.set_knob("chol_graph", 2)      # capture at the second fit of a shape (default: the sixth)
         hs, ts = set(), []
         for it in range(5 if N < 8192 else 3):
             g.fit(X, y)

@@ -7,6 +7,7 @@ for N, D in ((4096, 8), (2176, 5), (8192, 16)):
     rng = np.random.default_rng(N)
     X = rng.random((D, N)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N)
     g = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.0), kernel=b200bo.SEArd(np.full(D, np.log(np.sqrt(D) * 0.25)), 0.0), logNoise=-2.0, capacity=N)
+    g.set_knob("chol_graph", 2)
     hs = set()
     for it in range(6 if N < 8192 else 3):
         g.fit(X, y)
@@ -22,6 +23,7 @@ Xall = rng.random((D, 2600)); yall = np.sin(3 * Xall.sum(0)) + 0.1 * rng.standar
 g = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.2), kernel=b200bo.Mat52Ard(np.full(D, -0.5), 0.1), logNoise=-2.0, capacity=2600)
 ref = b200bo.B200GPE(D, mean=b200bo.MeanConst(0.2), kernel=b200bo.Mat52Ard(np.full(D, -0.5), 0.1), logNoise=-2.0, capacity=2600)
 ref.set_knob("chol_sched", 0)
+g.set_knob("chol_graph", 2)
 seq = [1000, 1000, 1000, 1001, 1200, 1200, 1000, 1000, 2600, 2600, 2600, 1200, 1000, 1000, 1023, 1024, 1025, 1025, 1025]
 for n in seq:
     g.fit(Xall[:, :n], yall[:n]); ref.fit(Xall[:, :n], yall[:n])

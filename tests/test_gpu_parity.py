@@ -871,10 +871,10 @@ def test_cholesky_schedules_agree_and_graph_replay_is_bit_identical(bo):
     X = rng.random((D, N)); y = np.sin(3 * X.sum(0)) + 0.1 * rng.standard_normal(N)
     g = bo.B200GPE(D, mean=bo.MeanConst(0.1), kernel=bo.Mat32Ard(np.full(D, -0.6), 0.2), logNoise=-2.0, capacity=N)
     out = {}
-    for name, (sched, graph) in dict(inorder=(0, 0), eager=(1, 0), tile_heads=(2, 0), graph=(1, 1)).items():
+    for name, (sched, graph) in dict(inorder=(0, 0), eager=(1, 0), tile_heads=(2, 0), graph=(1, 2)).items():
         g.set_knob("chol_sched", sched); g.set_knob("chol_graph", graph)
         fs = []
-        for _ in range(3):                      # graph mode: eager first sight, capture on the second, replay on the third
+        for _ in range(3):                      # graph mode (knob 2): eager first sight, capture on the second, replay on the third
             g.fit(X, y); fs.append((g.factor, g.alpha, g.mll))
         assert all(np.array_equal(fs[0][0], f[0]) and np.array_equal(fs[0][1], f[1]) and fs[0][2] == f[2] for f in fs[1:]), name
         out[name] = fs[-1]
@@ -894,6 +894,7 @@ def test_replayed_factorisation_graph_follows_data_and_mean_changes(bo):
     X = rng.random((D, N + 10)); y = np.cos(2 * X.sum(0)) + 0.05 * rng.standard_normal(N + 10) + 1.5
     ll = np.full(D, -0.8)
     g = bo.B200GPE(D, mean=bo.MeanConst(0.0), kernel=bo.SEArd(ll, 0.0), logNoise=-2.0, capacity=1024)
+    g.set_knob("chol_graph", 2)                  # capture at the second consecutive factorisation of a shape (default: the sixth)
     for _ in range(3):
         g.fit(X[:, :N], y[:N])                   # eager, capture, replay
     for beta, n in ((0.0, N), (1.5, N), (1.5, N + 7), (-0.4, N + 10), (0.9, N - 3)):
