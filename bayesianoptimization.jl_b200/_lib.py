@@ -79,7 +79,7 @@ PROTOTYPES = {
     "b200bo_sobol": [_H, _dp, _dp, C.c_uint64, C.c_int64, _dp],
     "b200bo_acquire_lbfgs": [_H, C.c_int32, _dp, C.c_int32, _dp, C.c_int64, _dp, _dp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
                              C.c_double, C.c_double, C.c_int64, _dp, _dp, _dp, C.POINTER(Best), _dp],
-    "b200bo_acquire_direct": [_H, C.c_int32, _dp, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_uint64, _dp, _dp,
+    "b200bo_acquire_direct": [_H, C.c_int32, _dp, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_uint64, _dp, _dp,
                               C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(Best), _dp],
     "b200bo_map_fit": [_H, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                        _dp, _dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],

@@ -101,7 +101,8 @@ def acquire_max(opt, lowerbounds=None, upperbounds=None, restarts=None, options=
     if opt.direct and str(opt.method).startswith("GN_DIRECT"):
         # the reference's derivative-free global search (:GN_DIRECT_L, maxeval evaluations; acquisition.jl:7-9,31-36) inside the library
         rd = model.acquire_direct(a.kind, a.params(), lb, ub, maxeval=int(opt.maxeval) if opt.maxeval else 2000, maxtime=float(opt.maxtime),
-                                  width=int(opt.direct_width), seed=opt.seed + (1 << 32))
+                                  width=int(opt.direct_width), seed=opt.seed + (1 << 32),
+                                  variant=0 if "DIRECT_L" in str(opt.method) else 1)      # :GN_DIRECT_L* -> locally biased, :GN_DIRECT -> Jones' original
         if rd["best_index"] >= 0 and (r["best_index"] < 0 or rd["best_value"] > r["best_value"]):
             r = dict(r, best_value=rd["best_value"], best_x=rd["best_x"], best_index=rd["best_index"], best_from="direct")
     opt.seed += 1

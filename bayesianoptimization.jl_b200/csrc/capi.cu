@@ -1043,7 +1043,7 @@ B200BO_API int32_t b200bo_acquire_lbfgs(b200bo_handle_t h, int32_t kind, const d
 // Thompson sample from the Philox stream at global index e (a fresh epsilon per closure call, as in the reference).  Runs on the handle's
 // first GPU only (the batches are tens of points); with a communicator attached every rank runs the same deterministic search.
 B200BO_API int32_t b200bo_acquire_direct(b200bo_handle_t h, int32_t kind, const double* p, int32_t np, const double* lb, const double* ub,
-                                         int32_t maxeval, double maxtime, int32_t width, uint64_t seed, double* Xtrace, double* ftrace,
+                                         int32_t maxeval, double maxtime, int32_t width, int32_t variant, uint64_t seed, double* Xtrace, double* ftrace,
                                          int32_t* evals_out, int32_t* batches_out, b200bo_best_t* best, double* best_x) {
   if (!h || !lb || !ub || (maxeval <= 0 && !(maxtime > 0.0)) || ((Xtrace || ftrace) && maxeval <= 0))
     return fail(h, B200BO_ERR_ARG, "bad arguments to acquire_direct (a search needs maxeval > 0 or maxtime > 0; a trace needs maxeval)");
@@ -1051,11 +1051,12 @@ B200BO_API int32_t b200bo_acquire_direct(b200bo_handle_t h, int32_t kind, const 
   if (rc) return rc;
   const int D = h->D;
   if (D > 64) return fail(h, B200BO_ERR_ARG, "acquire_direct supports D <= 64");
+  if (variant != B200BO_DIRECT_L && variant != B200BO_DIRECT_ORIG) return fail(h, B200BO_ERR_ARG, "unknown DIRECT variant");
   for (int d = 0; d < D; ++d)
     if (!(lb[d] <= ub[d]) || !std::isfinite(lb[d]) || !std::isfinite(ub[d])) return fail(h, B200BO_ERR_ARG, "DIRECT needs finite bounds with lb <= ub");
   SoloScope solo(h);
   DirectL s;
-  s.init(D, maxeval, width);
+  s.init(D, maxeval, width, variant);
   std::vector<double> pts, xs, vals;
   const auto t0 = std::chrono::steady_clock::now();
   int batches = 0;

@@ -17,6 +17,10 @@
 // NLopt's iterates are not reproduced bit for bit (its hull runs on floating-point diameters in a red-black tree; sizes here are
 // exact integer trisection levels); oracle/direct_oracle.py restates THIS state machine and the two are compared point for point.
 //
+// variant 1 = NLopt's GN_DIRECT (Jones' original, cdirect.c with which_diam = 0, which_div = 0, which_opt = 0): size = half the
+// DIAGONAL of the rectangle, every rectangle that ties for the best value of a hull size class divides, a cube is trisected along
+// all its sides but any other rectangle along ONE longest side only (the first).
+//
 // Pure host C++ (no CUDA): compiled into libb200bo.so and, for the CPU tests, into oracle/_build/libdirect_host.so.
 #pragma once
 #include <algorithm>
@@ -31,6 +35,7 @@ struct DirectL {
   int D = 0;
   int64_t maxeval = 0;                           // total evaluations (<= 0: unlimited)
   int width = 1;
+  int variant = 0;                               // 0: DIRECT-L (GN_DIRECT_L), 1: DIRECT (GN_DIRECT)
   int64_t evals = 0;
   double best_f = -INFINITY;
   int64_t best_eval = -1;                        // evaluation number (0-based) that produced the incumbent
@@ -40,7 +45,8 @@ struct DirectL {
   std::vector<double> c;                         // [n][D] centres in the unit cube
   std::vector<int8_t> lev;                       // [n][D] trisections per dimension: side_d = 3^-lev_d
   std::vector<double> f;                         // [n] value at the centre (NaN stored as -Inf: never wins)
-  std::vector<int> smin;                         // [n] min_d lev_d = the size class
+  std::vector<int> smin;                         // [n] min_d lev_d (the longest side is 3^-smin)
+  std::vector<double> size;                      // [n] the size measure: 3^-smin (DIRECT-L) or the diagonal sqrt(sum_d 9^-lev_d) (DIRECT); equal sizes = one class
   double third[MAX_LEVEL + 2];
   // the division in flight
   struct Pending { int rect; int ndim; int dims[64]; };
@@ -48,10 +54,10 @@ struct DirectL {
   int64_t pend_points = 0;
   bool started = false;
 
-  void init(int D_, int64_t maxeval_, int width_) {
-    D = D_; maxeval = maxeval_; width = width_ < 1 ? 1 : width_;
+  void init(int D_, int64_t maxeval_, int width_, int variant_ = 0) {
+    D = D_; maxeval = maxeval_; width = width_ < 1 ? 1 : width_; variant = variant_ == 1 ? 1 : 0;
     evals = 0; best_f = -INFINITY; best_eval = -1; best_c.assign(D, 0.5); finished = (D < 1 || D > 64);
-    c.clear(); lev.clear(); f.clear(); smin.clear(); pend.clear(); pend_points = 0; started = false;
+    c.clear(); lev.clear(); f.clear(); smin.clear(); size.clear(); pend.clear(); pend_points = 0; started = false;
     third[0] = 1.0;
     for (int k = 1; k < MAX_LEVEL + 2; ++k) third[k] = third[k - 1] / 3.0;      // the same sequence of divisions in the restatement
   }
@@ -68,30 +74,44 @@ struct DirectL {
     }
     int64_t room = maxeval > 0 ? maxeval - evals : INT64_MAX;
     if (room <= 0) { finished = true; return 0; }
-    // ---- best rectangle(s) of every size class ----
-    int smax = 0;
-    for (int s : smin) smax = std::max(smax, s);
-    std::vector<std::vector<int>> top(smax + 1);          // per class: up to `width` rectangles, best first (oldest on ties)
-    for (int i = 0; i < (int)f.size(); ++i) {
-      if (smin[i] >= MAX_LEVEL) continue;                 // too small to divide
-      std::vector<int>& t = top[smin[i]];
-      int pos = (int)t.size();
-      while (pos > 0 && f[i] > f[t[pos - 1]]) --pos;      // strict: an older rectangle of equal value stays ahead
-      if (pos < width) { t.insert(t.begin() + pos, i); if ((int)t.size() > width) t.pop_back(); }
+    // ---- size classes (equal size measure), largest first; per class the dividing candidates, best first (oldest on ties) ----
+    std::vector<int> order;
+    for (int i = 0; i < (int)f.size(); ++i) if (smin[i] < MAX_LEVEL) order.push_back(i);      // smaller ones can no longer be divided
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return size[x] > size[y]; });
+    std::vector<double> cx;                                 // class sizes, descending
+    std::vector<std::vector<int>> top;                      // DIRECT-L: the `width` best of the class; DIRECT: every rectangle tied for its best value
+    for (size_t o = 0; o < order.size();) {
+      size_t e = o;
+      while (e < order.size() && size[order[e]] == size[order[o]]) ++e;
+      std::vector<int> t;
+      if (variant == 0) {
+        for (size_t k = o; k < e; ++k) {
+          const int i = order[k];
+          int pos = (int)t.size();
+          while (pos > 0 && f[i] > f[t[pos - 1]]) --pos;    // strict: an older rectangle of equal value stays ahead
+          if (pos < width) { t.insert(t.begin() + pos, i); if ((int)t.size() > width) t.pop_back(); }
+        }
+      } else {
+        double fb = -INFINITY;
+        for (size_t k = o; k < e; ++k) fb = std::max(fb, f[order[k]]);
+        for (size_t k = o; k < e; ++k) if (f[order[k]] == fb) t.push_back(order[k]);          // age order (stable sort)
+      }
+      cx.push_back(size[order[o]]);
+      top.push_back(t);
+      o = e;
     }
     // ---- upper-right convex hull over (size, best value), epsilon = 0 ----
-    int s_star = -1;                                       // class of the incumbent (largest size on ties)
-    for (int s = 0; s <= smax; ++s)
-      if (!top[s].empty() && (s_star < 0 || f[top[s][0]] > f[top[s_star][0]])) s_star = s;
+    int s_star = -1;                                        // class of the incumbent (largest size on ties)
+    for (int s = 0; s < (int)top.size(); ++s)
+      if (s_star < 0 || f[top[s][0]] > f[top[s_star][0]]) s_star = s;
     if (s_star < 0) { finished = true; return 0; }
-    std::vector<int> hull;                                 // classes, size ascending (= s descending), starting at s_star
+    std::vector<int> hull;                                  // classes, size ascending, starting at s_star
     for (int s = s_star; s >= 0; --s) {
-      if (top[s].empty()) continue;
-      const double xs = third[s], ys = f[top[s][0]];
-      if (!(ys > -INFINITY) && s != s_star) continue;      // a class that only holds failed evaluations never supports the hull
+      const double xs = cx[s], ys = f[top[s][0]];
+      if (!(ys > -INFINITY) && s != s_star) continue;       // a class that only holds failed evaluations never supports the hull
       while (hull.size() >= 2) {
         const int a = hull[hull.size() - 2], b = hull[hull.size() - 1];
-        const double xa = third[a], ya = f[top[a][0]], xb = third[b], yb = f[top[b][0]];
+        const double xa = cx[a], ya = f[top[a][0]], xb = cx[b], yb = f[top[b][0]];
         // b is strictly below the chord a -> s  <=>  (yb - ya)(xs - xa) < (ys - ya)(xb - xa)
         if ((yb - ya) * (xs - xa) < (ys - ya) * (xb - xa)) hull.pop_back(); else break;
       }
@@ -105,6 +125,7 @@ struct DirectL {
         p.rect = r; p.ndim = 0;
         const int8_t* lv = lev.data() + (size_t)r * D;
         for (int d = 0; d < D; ++d) if (lv[d] == smin[r]) p.dims[p.ndim++] = d;
+        if (variant == 1 && p.ndim < D) p.ndim = 1;         // DIRECT: only a cube is cut along all its sides, anything else along its first longest side
         const double w3 = third[smin[r] + 1];
         const double* cr = c.data() + (size_t)r * D;
         for (int k = 0; k < p.ndim && room > 0; ++k) {
@@ -133,6 +154,17 @@ struct DirectL {
     int s = lv[0];
     for (int d = 1; d < D; ++d) s = std::min<int>(s, lv[d]);
     smin.push_back(s);
+    size.push_back(measure(lv, s));
+  }
+  // the size measure of a rectangle with trisection levels lv (smallest level s)
+  double measure(const int8_t* lv, int s) const {
+    if (variant == 0) return third[s];
+    int8_t sorted[64];
+    std::copy(lv, lv + D, sorted);
+    std::sort(sorted, sorted + D);                          // a canonical order: equal level multisets give bit-identical sums
+    double q = 0.0;
+    for (int d = 0; d < D; ++d) { const double w = third[std::min<int>(sorted[d], MAX_LEVEL + 1)]; q += w * w; }
+    return std::sqrt(q);
   }
 
   // values of the batch handed out by the last ask(), in the same order
@@ -170,7 +202,10 @@ struct DirectL {
         push(pts.data() + (size_t)(base + 2 * kk + 1) * D, lv.data(), fv[2 * kk + 1]);
       }
       std::copy(lv.begin(), lv.end(), lev.begin() + (size_t)p.rect * D);
-      smin[p.rect] += 1;                                   // every longest side was cut once
+      int sm = lv[0];
+      for (int d = 1; d < D; ++d) sm = std::min<int>(sm, lv[d]);
+      smin[p.rect] = sm;
+      size[p.rect] = measure(lv.data(), sm);
     }
     pend.clear(); pend_points = 0;
     if (maxeval > 0 && evals >= maxeval) finished = true;

@@ -325,9 +325,10 @@ class B200GPE:
         return dict(X=Xout, values=vals, evals=evals.astype(int), best_value=best.value, best_index=best.index, best_x=bx)
 
     def acquire_direct(self, kind: str, params, lb, ub, maxeval: int = 2000, maxtime: float = 0.0, width: int = 1, seed: int = 0,
-                       want_trace: bool = False):
+                       want_trace: bool = False, variant: int = 0):
         """NLopt :GN_DIRECT_L (the reference's default search for ThompsonSamplingSimple, src/acquisition.jl:7-9) as a batched
-        locally-biased DIRECT inside the library: one fused launch per iteration over all new rectangle centres."""
+        locally-biased DIRECT inside the library: one fused launch per iteration over all new rectangle centres.  variant 1 = Jones'
+        original DIRECT (NLopt :GN_DIRECT)."""
         lb = np.ascontiguousarray(lb, float); ub = np.ascontiguousarray(ub, float)
         if lb.size != self.D or ub.size != self.D:
             raise ValueError("bounds must have length D")
@@ -336,7 +337,7 @@ class B200GPE:
         ft = np.full(int(maxeval), np.nan) if want_trace else None
         ev = C.c_int32(); nb = C.c_int32(); best = _lib.Best(); bx = np.full(self.D, np.nan)
         check(lib.b200bo_acquire_direct(self._h, _lib.ACQ_KINDS[kind], dptr(p) if p.size else None, p.size, dptr(lb), dptr(ub), int(maxeval),
-                                        float(maxtime), int(width), seed & 0xFFFFFFFFFFFFFFFF, dptr(Xt), dptr(ft), C.byref(ev), C.byref(nb),
+                                        float(maxtime), int(width), int(variant), seed & 0xFFFFFFFFFFFFFFFF, dptr(Xt), dptr(ft), C.byref(ev), C.byref(nb),
                                         C.byref(best), dptr(bx)), self._h)
         r = dict(best_value=best.value, best_index=best.index, best_x=bx, evals=ev.value, batches=nb.value)
         if want_trace:

@@ -147,10 +147,10 @@ function acquire_max(s::B200Search, lb, ub, restarts)                           
     if startswith(string(o.method), "GN_DIRECT")     # the reference's derivative-free global search (acquisition.jl:7-9), batched inside the library
         p = acqparams(a); lbv = Vector{Float64}(lb); ubv = Vector{Float64}(ub); bd = Ref(Best(-Inf, -1)); bxd = fill(NaN, m.dim)
         GC.@preserve p lbv ubv bxd check(ccall((:b200bo_acquire_direct, LIB), Int32,
-            (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Int32, UInt64, Ptr{Float64}, Ptr{Float64},
+            (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Int32, Int32, UInt64, Ptr{Float64}, Ptr{Float64},
              Ptr{Int32}, Ptr{Int32}, Ref{Best}, Ptr{Float64}),
             m.h, acqkind(a), isempty(p) ? C_NULL : pointer(p), length(p), lbv, ubv, Int32(optget(o, :maxeval, 2000)), Float64(optget(o, :maxtime, 0.0)),
-            Int32(1), rand(UInt64), C_NULL, C_NULL, C_NULL, C_NULL, bd, bxd), m.h)
+            Int32(1), Int32(occursin("DIRECT_L", string(o.method)) ? 0 : 1), rand(UInt64), C_NULL, C_NULL, C_NULL, C_NULL, bd, bxd), m.h)
         bd[].index >= 0 && (r.best.index < 0 || bd[].value > r.best.value) && return (bd[].value, bxd)
     end
     r.best.index < 0 && return (-Inf, lb)

@@ -63,6 +63,10 @@ enum {
 /* parameter-selection mask for b200bo_mll_sweep == get_params_kwargs(gp; noise, domean, kern) (gp.jl:55-58) */
 enum { B200BO_MASK_NOISE = 1, B200BO_MASK_MEAN = 2, B200BO_MASK_KERN = 4 };
 
+/* variants of b200bo_acquire_direct: NLopt :GN_DIRECT_L (locally biased, the reference's default for ThompsonSamplingSimple) and :GN_DIRECT
+ * (Jones' original) */
+enum { B200BO_DIRECT_L = 0, B200BO_DIRECT_ORIG = 1 };
+
 /* which device timing b200bo_last_timing_ms returns (CUDA events on the handle's stream) */
 enum {
   B200BO_T_KMAT = 0,      /* kernel-matrix assembly (K1) of the last fit */
@@ -196,11 +200,12 @@ B200BO_API int32_t b200bo_acquire_ascent(b200bo_handle_t h, int32_t acq_kind, co
  *   ThompsonSamplingSimple, src/acquisition.jl:7-9; wrapper :31-36): locally-biased DIRECT on [lb, ub] (csrc/direct.h), every iteration's
  *   new centres -- all potentially optimal rectangles, all their longest sides -- scored by ONE fused acquisition launch.  maxeval = total
  *   evaluations (exactly, as NLopt counts them), maxtime in seconds (<= 0 unlimited), width = rectangles divided per hull size class
- *   (1 = DIRECT-L).  Evaluation e uses the Thompson stream (seed, global index e).  Xtrace (D x maxeval) / ftrace (maxeval) optionally
+ *   (1 = DIRECT-L; ignored by the original variant), variant = B200BO_DIRECT_L or B200BO_DIRECT_ORIG (diagonal size measure, every tie of a
+ *   hull class divides, only cubes are cut along all sides).  Evaluation e uses the Thompson stream (seed, global index e).  Xtrace (D x maxeval) / ftrace (maxeval) optionally
  *   receive every evaluated point and value in evaluation order; evals = evaluations used, batches = device launches.  best->index = the
  *   evaluation (0-based, = column of Xtrace) that produced the best value, -1 if nothing beat -Inf. */
 B200BO_API int32_t b200bo_acquire_direct(b200bo_handle_t h, int32_t acq_kind, const double* acq_params, int32_t n_params, const double* lb,
-                                         const double* ub, int32_t maxeval, double maxtime, int32_t width, uint64_t seed,
+                                         const double* ub, int32_t maxeval, double maxtime, int32_t width, int32_t variant, uint64_t seed,
                                          double* Xtrace /*D x maxeval or NULL*/, double* ftrace /*maxeval or NULL*/, int32_t* evals /*or NULL*/,
                                          int32_t* batches /*or NULL*/, b200bo_best_t* best, double* best_x /*D or NULL*/);
 B200BO_API int32_t b200bo_sobol(b200bo_handle_t h, const double* lb, const double* ub, uint64_t index0, int64_t n, double* Xs /* host, D x n */);

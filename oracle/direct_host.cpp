@@ -4,9 +4,9 @@
 #include <cstring>
 
 extern "C" {
-void* direct_host_create(int D, long long maxeval, int width) {
+void* direct_host_create(int D, long long maxeval, int width, int variant) {
   auto* s = new b200bo::DirectL();
-  s->init(D, maxeval, width);
+  s->init(D, maxeval, width, variant);
   return s;
 }
 void direct_host_destroy(void* p) { delete static_cast<b200bo::DirectL*>(p); }

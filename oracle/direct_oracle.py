@@ -37,8 +37,20 @@ def _upper_right_hull(pts):
     return [t for _, _, t in hull]
 
 
-def direct_l(fbatch, D: int, maxeval: int, width: int = 1):
-    """fbatch(P) -> values for the rows of P (n x D, unit cube).  Returns dict(best_f, best_c, evals, batches, X (evals x D), f)."""
+def _measure(lev, third, variant):
+    if variant == 0:
+        return third[min(lev)]
+    q = 0.0
+    for k in sorted(lev):                                             # canonical order: equal level multisets give bit-identical sums
+        w = third[min(k, MAX_LEVEL + 1)]
+        q += w * w
+    return math.sqrt(q)
+
+
+def direct_l(fbatch, D: int, maxeval: int, width: int = 1, variant: int = 0):
+    """fbatch(P) -> values for the rows of P (n x D, unit cube).  variant 0: DIRECT-L (NLopt GN_DIRECT_L), 1: Jones' DIRECT (GN_DIRECT):
+    diagonal size measure, every rectangle tied for the best value of a hull class divides, only cubes are cut along all sides.
+    Returns dict(best_f, best_c, evals, batches, X (evals x D), f)."""
     third = _thirds()
     rects = []                       # dicts: c (np array), lev (list of int), f
     X_all, f_all = [], []
@@ -57,29 +69,32 @@ def direct_l(fbatch, D: int, maxeval: int, width: int = 1):
         best_f, best_c = v, P[0].copy()
     rects.append(dict(c=P[0].copy(), lev=[0] * D, f=v))
     while evals < maxeval:
-        # best rectangles per size class
+        # size classes (equal measure), dividing candidates per class
         classes = {}
         for i, r in enumerate(rects):
-            s = min(r["lev"])
-            if s >= MAX_LEVEL:
+            if min(r["lev"]) >= MAX_LEVEL:
                 continue
-            classes.setdefault(s, []).append(i)
+            classes.setdefault(_measure(r["lev"], third, variant), []).append(i)
         if not classes:
             break
         top = {}
         for s, ids in classes.items():
-            ids = sorted(ids, key=lambda i: (-rects[i]["f"], i))     # best first, oldest on ties
-            top[s] = ids[:width]
+            if variant == 0:
+                ids = sorted(ids, key=lambda i: (-rects[i]["f"], i))     # best first, oldest on ties
+                top[s] = ids[:width]
+            else:
+                fb = max(rects[i]["f"] for i in ids)
+                top[s] = [i for i in ids if rects[i]["f"] == fb]         # every rectangle tied for the best value, oldest first
         s_star = None
-        for s in sorted(top):                                         # largest size first: wins ties
+        for s in sorted(top, reverse=True):                              # largest size first: wins ties
             if s_star is None or rects[top[s][0]]["f"] > rects[top[s_star][0]]["f"]:
                 s_star = s
         pts = []
-        for s in sorted([s for s in top if s <= s_star], reverse=True):   # size ascending
+        for s in sorted([s for s in top if s >= s_star]):                # size ascending
             y = rects[top[s][0]]["f"]
             if y == -math.inf and s != s_star:
                 continue
-            pts.append((third[s], y, s))
+            pts.append((s, y, s))
         hull = _upper_right_hull(pts)
         # divisions, largest rectangles first, cut at maxeval
         room = maxeval - evals
@@ -89,8 +104,11 @@ def direct_l(fbatch, D: int, maxeval: int, width: int = 1):
                 if room <= 0:
                     break
                 r = rects[i]
-                dims = [d for d in range(D) if r["lev"][d] == s]
-                w3 = third[s + 1]
+                smin = min(r["lev"])
+                dims = [d for d in range(D) if r["lev"][d] == smin]
+                if variant == 1 and len(dims) < D:
+                    dims = dims[:1]                                      # only a cube is cut along all its sides
+                w3 = third[smin + 1]
                 cnt = 0
                 for d in dims:
                     for sgn in (-1.0, 1.0):

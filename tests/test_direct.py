@@ -18,7 +18,7 @@ def _host():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     lib = C.CDLL(path)
     lib.direct_host_create.restype = C.c_void_p
-    lib.direct_host_create.argtypes = [C.c_int, C.c_longlong, C.c_int]
+    lib.direct_host_create.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_int]
     lib.direct_host_destroy.argtypes = [C.c_void_p]
     lib.direct_host_ask.restype = C.c_longlong
     lib.direct_host_ask.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_longlong]
@@ -27,9 +27,9 @@ def _host():
     return lib
 
 
-def run_host(fbatch, D, maxeval, width=1):
+def run_host(fbatch, D, maxeval, width=1, variant=0):
     lib = _host()
-    s = lib.direct_host_create(D, maxeval, width)
+    s = lib.direct_host_create(D, maxeval, width, variant)
     buf = np.empty((max(maxeval, 1) + 4 * D, D))
     X, F, batches = [], [], 0
     while True:
@@ -53,16 +53,17 @@ def neg_branin_unit(P):
     return -((y - 5.1 / (4 * np.pi ** 2) * x ** 2 + 5 / np.pi * x - 6) ** 2 + 10 * (1 - 1 / (8 * np.pi)) * np.cos(x) + 10)
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("D,width,maxeval", [(2, 1, 400), (6, 1, 1000), (3, 2, 333), (1, 1, 60), (8, 3, 777)])
-def test_host_state_machine_equals_restatement(D, width, maxeval):
+def test_host_state_machine_equals_restatement(D, width, maxeval, variant):
     rng = np.random.default_rng(D * 100 + width)
     A = rng.normal(size=(4, D)); b = rng.random((4, D))
 
     def f(P):     # smooth multi-modal, deterministic
         return sum(np.exp(-8 * ((P - b[k]) ** 2).sum(axis=1)) * (1 + 0.3 * k) for k in range(4)) + 0.05 * np.sin(P @ A.T).sum(axis=1)
 
-    h = run_host(f, D, maxeval, width)
-    o = dor.direct_l(f, D, maxeval, width)
+    h = run_host(f, D, maxeval, width, variant)
+    o = dor.direct_l(f, D, maxeval, width, variant)
     assert h["evals"] == o["evals"] == maxeval
     assert h["batches"] == o["batches"] and h["nrect"] == o["nrect"]
     assert np.array_equal(h["X"], o["X"]) and np.array_equal(h["f"], o["f"])
@@ -82,6 +83,20 @@ def test_first_iterations_follow_direct():
             x = np.full(D, 0.5); x[d] += s * (1.0 / 3.0); want.append(x)
     assert np.allclose(h["X"][1:], np.array(want), atol=1e-16)
     assert h["best_f"] == f(h["X"]).max() and h["nrect"] == 1 + 2 * D
+
+
+def test_original_direct_cuts_non_cubes_along_one_side_only():
+    """NLopt GN_DIRECT (cdirect which_div = 0): the unit cube is trisected along all D sides; its best child -- no longer a cube -- along ONE
+    longest side only, and every rectangle tied for the best value of a hull class divides"""
+    D = 3
+    f = lambda P: -((P - np.array([0.9, 0.5, 0.5])) ** 2).sum(axis=1)
+    h = run_host(f, D, 1 + 2 * D + 40, variant=1)
+    assert np.array_equal(h["X"][0], np.full(D, 0.5)) and h["batches"] >= 3
+    second = h["X"][1 + 2 * D:]                       # iteration 2: each dividing rectangle contributes exactly one +- pair along one axis
+    moved = np.abs(second[0::2] - second[1::2]) > 0
+    assert np.all(moved.sum(axis=1) == 1)
+    lb = run_host(neg_branin_unit, 2, 2000, variant=1)
+    assert -lb["best_f"] - 0.397887 < 1e-3
 
 
 def test_maxeval_is_exact_and_nan_never_wins():
@@ -112,8 +127,8 @@ def test_branin_global_optimum_within_reference_budget():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["EI", "TS", "MaxMean"])
-def test_library_direct_equals_restatement_on_library_values(kind):
+@pytest.mark.parametrize("kind,variant", [("EI", 0), ("TS", 0), ("MaxMean", 0), ("EI", 1)])
+def test_library_direct_equals_restatement_on_library_values(kind, variant):
     import b200bo
     from oracle import gp_oracle as orc
     rng = np.random.default_rng(5)
@@ -124,7 +139,7 @@ def test_library_direct_equals_restatement_on_library_values(kind):
     lb = np.array([-0.5, 0.0, 0.2, 0.0]); ub = np.array([1.0, 1.0, 0.9, 2.0])
     params = (float(y.max()),) if kind == "EI" else ()
     me, seed = 500, 11
-    r = g.acquire_direct(kind, params, lb, ub, maxeval=me, seed=seed, want_trace=True)
+    r = g.acquire_direct(kind, params, lb, ub, maxeval=me, seed=seed, want_trace=True, variant=variant)
     assert r["evals"] == me and 0 <= r["best_index"] < me
     assert r["values"][r["best_index"]] == r["best_value"] and np.array_equal(r["X"][:, r["best_index"]], r["best_x"])
     assert r["best_index"] == int(np.argmax(np.where(np.isnan(r["values"]), -np.inf, r["values"])))      # first strict maximum
@@ -136,7 +151,7 @@ def test_library_direct_equals_restatement_on_library_values(kind):
         state["n"] += len(P)
         return v
 
-    o = dor.direct_l(f, D, me)
+    o = dor.direct_l(f, D, me, 1, variant)
     Xo = lb[None, :] + o["X"] * (ub - lb)[None, :]
     assert np.array_equal(r["X"].T, Xo) and np.array_equal(r["values"], o["f"])
     assert r["best_value"] == o["best_f"] and r["batches"] == o["batches"]
